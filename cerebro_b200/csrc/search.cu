@@ -1,0 +1,739 @@
+// Descriptor database + all-against-DB inner-product search (sm_100a).
+//
+// Replaces (reference): faiss::IndexFlatIP add/search (src/Cerebro.cpp:390-460) and the three
+// fp64 GEMVs + arg-max of Cerebro::descrip_N__dot__descrip_0_N (src/Cerebro.cpp:1019-1043).
+//
+// Data layout in HBM: rows [capacity][d] fp32 row-major (one keyframe descriptor per row, the
+// IndexFlatIP layout).  A sharded index keeps rows with global label g % world == rank; local
+// row r <-> global label r * world + rank.
+//
+// Kernels
+//   scores_kernel<QT,R> : the HBM sweep.  A CTA owns one d-slice [d0, d0+ds) of QT queries, held in
+//                         shared memory for the whole launch, and streams row blocks through
+//                         128-bit coalesced loads; a warp owns R rows, a lane owns 4 consecutive
+//                         floats of every 128-float segment.  Per-lane fp32 accumulation, then a
+//                         fixed-order warp-shuffle reduce-scatter.  Output: partial[slice][q][row].
+//                         Algorithmic bytes per launch = n_rows * d * 4 (every row read once).
+//   topk_chunk_kernel   : sums the slices and keeps the best 32 (score,label) per chunk of rows with
+//                         a warp-shuffle insertion list (lane i holds the i-th best).
+//   finalize_kernel     : merges chunk lists, re-scores the 32 survivors in fp64 against the query,
+//                         ranks them with the requested tie rule and writes the top k.
+//   merge_lists_kernel  : merges already-final fp64 lists (multi-GPU all-gather result).
+#include "common.cuh"
+
+#include <math_constants.h>
+
+namespace {
+
+using cb::FULL;
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kList = 32;          // candidates carried per list (one per lane)
+constexpr int kChunkRows = 8192;   // rows per top-k chunk CTA
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp reduce-scatter: N (multiple of 32) per-lane values -> lane L ends with the full sum of
+// v[g*32 + L] in v[g] (g < N/32).  Fixed summation order => deterministic.
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void warp_reduce_scatter(float* v, int lane) {
+  static_assert(N % 32 == 0, "N must be a multiple of 32");
+#pragma unroll
+  for (int g = 0; g < N / 32; ++g) {
+    float* w = v + g * 32;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool hi = lane & off;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        float send = hi ? w[i] : w[i + off];
+        float keep = hi ? w[i + off] : w[i];
+        w[i] = keep + __shfl_xor_sync(FULL, send, off);
+      }
+    }
+    v[g] = w[0];
+  }
+}
+
+template <int QT, int R>
+__global__ void __launch_bounds__(kThreads, (QT * R >= 64 ? 1 : 2))
+scores_kernel(const float* __restrict__ rows, long long n_rows, int d, int ds, int n_slices,
+              const float* __restrict__ xq, int nq_valid, float* __restrict__ partial,
+              long long pstride) {
+  extern __shared__ float4 sq[];  // [QT][ds/4]
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int slice = blockIdx.x % n_slices;
+  const int group = blockIdx.x / n_slices;
+  const int n_groups = gridDim.x / n_slices;
+  const int d0 = slice * ds;
+  const int ds4 = ds >> 2;
+
+  for (int i = tid; i < QT * ds4; i += kThreads) {
+    const int t = i / ds4, c = i - t * ds4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < nq_valid) v = reinterpret_cast<const float4*>(xq + (size_t)t * d + d0)[c];
+    sq[i] = v;
+  }
+  __syncthreads();
+
+  constexpr int kRowsPerCta = kWarps * R;
+  const long long n_blocks = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
+  const int nj = ds >> 7;  // 128-float segments per slice
+
+  for (long long rb = group; rb < n_blocks; rb += n_groups) {
+    const long long r0 = rb * kRowsPerCta + (long long)warp * R;
+    if (r0 >= n_rows) continue;  // warp-uniform
+    float acc[R * QT];
+#pragma unroll
+    for (int i = 0; i < R * QT; ++i) acc[i] = 0.f;
+
+    const float4* p[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      long long rr = r0 + r;
+      if (rr >= n_rows) rr = n_rows - 1;  // tail rows: computed, never written
+      p[r] = reinterpret_cast<const float4*>(rows + (size_t)rr * d + d0) + lane;
+    }
+    float4 cur[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) cur[r] = ldg_stream(p[r]);
+
+    for (int j = 0; j < nj; ++j) {
+      float4 nxt[R];
+      if (j + 1 < nj) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) nxt[r] = ldg_stream(p[r] + (j + 1) * 32);
+      }
+      const float4* q = sq + j * 32 + lane;
+#pragma unroll
+      for (int t = 0; t < QT; ++t) {
+        const float4 q4 = q[t * ds4];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float a = acc[r * QT + t];
+          a = fmaf(cur[r].x, q4.x, a);
+          a = fmaf(cur[r].y, q4.y, a);
+          a = fmaf(cur[r].z, q4.z, a);
+          a = fmaf(cur[r].w, q4.w, a);
+          acc[r * QT + t] = a;
+        }
+      }
+      if (j + 1 < nj) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) cur[r] = nxt[r];
+      }
+    }
+
+    float* out = partial + (size_t)slice * QT * pstride;
+    if constexpr ((R * QT) % 32 == 0) {
+      warp_reduce_scatter<R * QT>(acc, lane);
+#pragma unroll
+      for (int g = 0; g < (R * QT) / 32; ++g) {
+        const int id = g * 32 + lane;
+        const int r = id / QT, t = id % QT;
+        if (r0 + r < n_rows && t < nq_valid) out[(size_t)t * pstride + r0 + r] = acc[g];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < R * QT; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+        acc[i] = v;
+      }
+      if (lane < R * QT) {
+        // lane i writes value i (select without dynamic register indexing)
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < R * QT; ++i)
+          if (lane == i) v = acc[i];
+        const int r = lane / QT, t = lane % QT;
+        if (r0 + r < n_rows && t < nq_valid) out[(size_t)t * pstride + r0 + r] = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp-select: sorted list of 32 candidates, lane i holds the i-th best
+// ---------------------------------------------------------------------------------------------
+template <typename S>
+__device__ __forceinline__ bool better(S s1, long long id1, S s2, long long id2, int tie_high) {
+  if (s1 > s2) return true;
+  if (s1 < s2) return false;
+  if (!(s1 == s2)) return false;  // NaN never wins
+  if (id2 < 0) return id1 >= 0;   // any real label beats the sentinel
+  if (id1 < 0) return false;
+  return tie_high ? (id1 > id2) : (id1 < id2);
+}
+
+template <typename S>
+__device__ __forceinline__ S neg_inf();
+template <>
+__device__ __forceinline__ float neg_inf<float>() { return -CUDART_INF_F; }
+template <>
+__device__ __forceinline__ double neg_inf<double>() { return -CUDART_INF; }
+
+template <typename S>
+struct WarpList {
+  S s;
+  long long id;
+  __device__ __forceinline__ void init() {
+    s = neg_inf<S>();
+    id = -1;
+  }
+  // every lane offers one candidate (cs, cid); `valid` false lanes are skipped
+  __device__ __forceinline__ void offer(S cs, long long cid, bool valid, int tie_high, int lane) {
+    S ts = __shfl_sync(FULL, s, 31);
+    long long tid_ = __shfl_sync(FULL, id, 31);
+    unsigned m = __ballot_sync(FULL, valid && better<S>(cs, cid, ts, tid_, tie_high));
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const S bs = __shfl_sync(FULL, cs, src);
+      const long long bid = __shfl_sync(FULL, cid, src);
+      const bool b = better<S>(bs, bid, s, id, tie_high);
+      const unsigned bm = __ballot_sync(FULL, b);
+      const S us = __shfl_up_sync(FULL, s, 1);
+      const long long uid = __shfl_up_sync(FULL, id, 1);
+      if (b) {
+        if (lane == __ffs(bm) - 1) {
+          s = bs;
+          id = bid;
+        } else {
+          s = us;
+          id = uid;
+        }
+      }
+    }
+  }
+};
+
+// partial[slice][q][row] -> chunk lists [q][chunk][32]
+__global__ void __launch_bounds__(kThreads)
+topk_chunk_kernel(const float* __restrict__ partial, int n_slices, int qt_stride, long long pstride,
+                  long long n_rows, int rank, int world, int tie_high, float* __restrict__ cs,
+                  long long* __restrict__ cl, int n_chunks) {
+  __shared__ float ss[kWarps * kList];
+  __shared__ long long sl[kWarps * kList];
+  const int q = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long r_begin = (long long)chunk * kChunkRows;
+  long long r_end = r_begin + kChunkRows;
+  if (r_end > n_rows) r_end = n_rows;
+  WarpList<float> wl;
+  wl.init();
+  const float* base = partial + (size_t)q * pstride;
+  const size_t sstride = (size_t)qt_stride * pstride;
+  for (long long r = r_begin + tid; r < r_begin + kChunkRows; r += kThreads) {
+    const bool valid = r < r_end;
+    float v = 0.f;
+    if (valid) {
+      for (int s = 0; s < n_slices; ++s) v += base[s * sstride + r];
+    }
+    wl.offer(v, r * world + rank, valid, tie_high, lane);
+  }
+  ss[warp * kList + lane] = wl.s;
+  sl[warp * kList + lane] = wl.id;
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < kWarps; ++w) {
+      const float v = ss[w * kList + lane];
+      const long long id = sl[w * kList + lane];
+      wl.offer(v, id, id >= 0, tie_high, lane);
+    }
+    const size_t o = ((size_t)q * n_chunks + chunk) * kList + lane;
+    cs[o] = wl.s;
+    cl[o] = wl.id;
+  }
+}
+
+// one CTA (32 warps) per query: merge chunk lists -> 32 survivors, fp64 re-score, rank, write top k
+__global__ void __launch_bounds__(1024)
+finalize_kernel(const float* __restrict__ cs, const long long* __restrict__ cl, int n_chunks,
+                const float* __restrict__ rows, int d, int rank, int world,
+                const float* __restrict__ xq, int k, int tie_high, double* __restrict__ out_s,
+                long long* __restrict__ out_l) {
+  __shared__ long long s_id[kList];
+  __shared__ double s_sc[kList];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 0) {
+    WarpList<float> wl;
+    wl.init();
+    const size_t o = (size_t)q * n_chunks * kList;
+    for (int i = 0; i < n_chunks; ++i) {
+      const float v = cs[o + i * kList + lane];
+      const long long id = cl[o + i * kList + lane];
+      wl.offer(v, id, id >= 0, tie_high, lane);
+    }
+    s_id[lane] = wl.id;
+  }
+  __syncthreads();
+  // warp w re-scores survivor w in fp64 (fixed order: lane-strided, then butterfly)
+  {
+    const long long id = s_id[warp];
+    double acc = 0.0;
+    if (id >= 0) {
+      const long long r = (id - rank) / world;
+      const float4* pr = reinterpret_cast<const float4*>(rows + (size_t)r * d);
+      const float4* pq = reinterpret_cast<const float4*>(xq + (size_t)q * d);
+      for (int c = lane; c < (d >> 2); c += 32) {
+        const float4 a = pr[c], b = pq[c];
+        acc += (double)a.x * (double)b.x;
+        acc += (double)a.y * (double)b.y;
+        acc += (double)a.z * (double)b.z;
+        acc += (double)a.w * (double)b.w;
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+    } else {
+      acc = -CUDART_INF;
+    }
+    if (lane == 0) s_sc[warp] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const double ms = s_sc[lane];
+    const long long mid = s_id[lane];
+    int rnk = 0;
+    for (int j = 0; j < kList; ++j) {
+      const double os = __shfl_sync(FULL, ms, j);
+      const long long oid = __shfl_sync(FULL, mid, j);
+      if (j != lane && better<double>(os, oid, ms, mid, tie_high)) ++rnk;
+    }
+    // sentinels are all equal: give them distinct ranks after the real ones
+    const unsigned sm = __ballot_sync(FULL, mid < 0);
+    if (mid < 0) rnk = (kList - __popc(sm)) + __popc(sm & ((1u << lane) - 1));
+    if (rnk < k) {
+      out_s[(size_t)q * k + rnk] = ms;
+      out_l[(size_t)q * k + rnk] = mid;
+    }
+  }
+}
+
+// lists [n_lists][nq][k_in] (fp64 score, label) -> [nq][k_out]
+__global__ void __launch_bounds__(32)
+merge_lists_kernel(const double* __restrict__ s, const long long* __restrict__ l, int n_lists, int nq,
+                   int k_in, int k_out, int tie_high, double* __restrict__ out_s,
+                   long long* __restrict__ out_l) {
+  const int q = blockIdx.x, lane = threadIdx.x;
+  WarpList<double> wl;
+  wl.init();
+  const int total = n_lists * k_in;
+  for (int base = 0; base < total; base += 32) {
+    const int i = base + lane;
+    const bool in = i < total;
+    double v = -CUDART_INF;
+    long long id = -1;
+    if (in) {
+      const int li = i / k_in, kk = i % k_in;
+      const size_t o = ((size_t)li * nq + q) * k_in + kk;
+      v = s[o];
+      id = l[o];
+    }
+    wl.offer(v, id, in && id >= 0, tie_high, lane);
+  }
+  if (lane < k_out) {
+    out_s[(size_t)q * k_out + lane] = wl.s;
+    out_l[(size_t)q * k_out + lane] = wl.id;
+  }
+}
+
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+template <int QT, int R>
+cudaError_t launch_scores(int grid, size_t smem, cudaStream_t st, const float* rows, long long n_rows,
+                          int d, int ds, int n_slices, const float* xq, int nq_valid, float* partial,
+                          long long pstride) {
+  auto kern = scores_kernel<QT, R>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kThreads, smem, st>>>(rows, n_rows, d, ds, n_slices, xq, nq_valid, partial, pstride);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// =============================================================================================
+// host side
+// =============================================================================================
+struct cb_index {
+  int d = 0;
+  int64_t capacity = 0;
+  int device = 0, rank = 0, world = 1, sm_count = 0;
+  int64_t ntotal = 0, nlocal = 0;
+  float* rows = nullptr;
+  cudaStream_t stream = nullptr;
+  // scratch (grown on demand)
+  float* partial = nullptr;
+  size_t partial_bytes = 0;
+  float* chunk_s = nullptr;
+  long long* chunk_l = nullptr;
+  size_t chunk_elems = 0;
+  float* q_dev = nullptr;  // host-API staging
+  size_t q_bytes = 0;
+  double* out_s = nullptr;
+  long long* out_l = nullptr;
+  size_t out_elems = 0;
+  void* stage = nullptr;  // add staging
+  size_t stage_bytes = 0;
+  int max_qt = 16;
+};
+
+namespace {
+
+int grow(void** p, size_t* cur, size_t need) {
+  if (*cur >= need) return CB_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cur = 0;
+  cudaError_t e = cudaMalloc(p, need);
+  if (e != cudaSuccess) return cb::fail(CB_ENOMEM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+  *cur = need;
+  return CB_OK;
+}
+
+int64_t local_limit(const cb_index* ix, int64_t limit_rows) {
+  int64_t n = ix->nlocal;
+  if (limit_rows >= 0) {
+    int64_t lim = limit_rows - ix->rank;
+    lim = lim <= 0 ? 0 : (lim + ix->world - 1) / ix->world;
+    if (lim < n) n = lim;
+  }
+  return n;
+}
+
+// pick the query tile and d-slicing for a sweep
+struct SweepPlan {
+  int qt, ds, n_slices, grid;
+  size_t smem;
+};
+
+SweepPlan plan_sweep(const cb_index* ix, int nq_left) {
+  SweepPlan p;
+  int qt = 1;
+  while (qt < nq_left && qt < ix->max_qt) qt <<= 1;
+  for (;; qt >>= 1) {
+    // shared memory budget: one resident CTA for the 8/16-query tiles, two otherwise
+    const size_t cap = (qt >= 8 ? 200 : 100) * 1024;
+    int n_slices = 1;
+    while ((size_t)qt * (ix->d / n_slices) * 4 > cap && (ix->d / (n_slices * 2)) % 128 == 0 &&
+           ix->d % (n_slices * 2) == 0)
+      n_slices <<= 1;
+    p.qt = qt;
+    p.n_slices = n_slices;
+    p.ds = ix->d / n_slices;
+    p.smem = (size_t)qt * p.ds * 4;
+    if (p.smem <= cap || qt == 1) break;
+  }
+  const int ctas_per_sm = (p.qt >= 8) ? 1 : 2;
+  int grid = ix->sm_count * ctas_per_sm;
+  grid = (grid / p.n_slices) * p.n_slices;
+  if (grid < p.n_slices) grid = p.n_slices;
+  p.grid = grid;
+  return p;
+}
+
+int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t limit_rows,
+                       int tie_mode, double* scores_dev, long long* labels_dev, cudaStream_t st) {
+  const int tie_high = tie_mode == CB_TIE_HIGH_LABEL;
+  const int64_t n_rows = local_limit(ix, limit_rows);
+  const int n_chunks = (int)((n_rows + kChunkRows - 1) / kChunkRows);
+  if (n_rows == 0) {
+    // nothing to search on this shard: emit sentinels
+    merge_lists_kernel<<<nq, 32, 0, st>>>(nullptr, nullptr, 0, nq, 1, k, tie_high, scores_dev, labels_dev);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
+  const long long pstride = (n_rows + 31) & ~31LL;
+  int q0 = 0;
+  while (q0 < nq) {
+    SweepPlan p = plan_sweep(ix, nq - q0);
+    const int nq_valid = (nq - q0) < p.qt ? (nq - q0) : p.qt;
+    int rc = grow((void**)&ix->partial, &ix->partial_bytes, (size_t)p.n_slices * p.qt * pstride * sizeof(float));
+    if (rc) return rc;
+    const size_t ce = (size_t)p.qt * n_chunks * kList;
+    if (ix->chunk_elems < ce) {
+      if (ix->chunk_s) cudaFree(ix->chunk_s);
+      if (ix->chunk_l) cudaFree(ix->chunk_l);
+      ix->chunk_s = nullptr;
+      ix->chunk_l = nullptr;
+      ix->chunk_elems = 0;
+      CB_CUDA(cudaMalloc(&ix->chunk_s, ce * sizeof(float)));
+      CB_CUDA(cudaMalloc(&ix->chunk_l, ce * sizeof(long long)));
+      ix->chunk_elems = ce;
+    }
+    const float* xq = xq_dev + (size_t)q0 * ix->d;
+    cudaError_t e = cudaSuccess;
+#define CB_SWEEP(QT, R)                                                                          \
+  e = launch_scores<QT, R>(p.grid, p.smem, st, ix->rows, n_rows, ix->d, p.ds, p.n_slices, xq,    \
+                           nq_valid, ix->partial, pstride)
+    switch (p.qt) {
+      case 1: CB_SWEEP(1, 8); break;
+      case 2: CB_SWEEP(2, 8); break;
+      case 4: CB_SWEEP(4, 8); break;
+      case 8: CB_SWEEP(8, 8); break;
+      default: CB_SWEEP(16, 8); break;
+    }
+#undef CB_SWEEP
+    if (e != cudaSuccess) return cb::fail(CB_ECUDA, "scores_kernel launch failed: %s", cudaGetErrorString(e));
+    topk_chunk_kernel<<<dim3(n_chunks, nq_valid), kThreads, 0, st>>>(
+        ix->partial, p.n_slices, p.qt, pstride, n_rows, ix->rank, ix->world, tie_high, ix->chunk_s,
+        ix->chunk_l, n_chunks);
+    CB_LAUNCH_CHECK();
+    finalize_kernel<<<nq_valid, 1024, 0, st>>>(ix->chunk_s, ix->chunk_l, n_chunks, ix->rows, ix->d,
+                                               ix->rank, ix->world, xq, k, tie_high,
+                                               scores_dev + (size_t)q0 * k, labels_dev + (size_t)q0 * k);
+    CB_LAUNCH_CHECK();
+    q0 += nq_valid;
+  }
+  return CB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cb_index_create(cb_index** out, int d, int64_t capacity, int device, int rank, int world) {
+  if (!out) return cb::fail(CB_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (d <= 0 || d % 128 != 0) return cb::fail(CB_EINVAL, "descriptor dim must be a positive multiple of 128, got %d", d);
+  if (capacity <= 0) return cb::fail(CB_EINVAL, "capacity must be > 0");
+  if (world < 1 || rank < 0 || rank >= world) return cb::fail(CB_EINVAL, "bad shard %d/%d", rank, world);
+  int sm = 0;
+  int rc = cb::select_device(device, &sm);
+  if (rc) return rc;
+  cb::DeviceGuard g(device);
+  cb_index* ix = new cb_index();
+  ix->d = d;
+  ix->capacity = capacity;
+  ix->device = device;
+  ix->rank = rank;
+  ix->world = world;
+  ix->sm_count = sm;
+  cudaError_t e = cudaMalloc(&ix->rows, (size_t)capacity * d * sizeof(float));
+  if (e != cudaSuccess) {
+    delete ix;
+    return cb::fail(CB_ENOMEM, "cudaMalloc of %lld x %d fp32 rows failed: %s", (long long)capacity, d, cudaGetErrorString(e));
+  }
+  e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    cudaFree(ix->rows);
+    delete ix;
+    return cb::fail(CB_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+  }
+  *out = ix;
+  return CB_OK;
+}
+
+int cb_index_destroy(cb_index* ix) {
+  if (!ix) return CB_OK;
+  cb::DeviceGuard g(ix->device);
+  cudaStreamSynchronize(ix->stream);
+  cudaFree(ix->rows);
+  cudaFree(ix->partial);
+  cudaFree(ix->chunk_s);
+  cudaFree(ix->chunk_l);
+  cudaFree(ix->q_dev);
+  cudaFree(ix->out_s);
+  cudaFree(ix->out_l);
+  cudaFree(ix->stage);
+  cudaStreamDestroy(ix->stream);
+  delete ix;
+  return CB_OK;
+}
+
+int cb_index_reset(cb_index* ix) {
+  if (!ix) return cb::fail(CB_EINVAL, "index is NULL");
+  ix->ntotal = 0;
+  ix->nlocal = 0;
+  return CB_OK;
+}
+
+int64_t cb_index_ntotal(const cb_index* ix) { return ix ? ix->ntotal : -1; }
+int64_t cb_index_nlocal(const cb_index* ix) { return ix ? ix->nlocal : -1; }
+int cb_index_dim(const cb_index* ix) { return ix ? ix->d : -1; }
+const float* cb_index_device_rows(const cb_index* ix) { return ix ? ix->rows : nullptr; }
+
+// copies the rows of [g0, g0+n) that belong to this shard from a (host or device) fp32 source
+static int add_impl(cb_index* ix, int64_t n, const float* x, cudaMemcpyKind kind, cudaStream_t st) {
+  const int64_t g0 = ix->ntotal;
+  // first global label >= g0 owned by this shard
+  int64_t first = g0 + ((ix->rank - g0 % ix->world) + ix->world) % ix->world;
+  int64_t mine = first < g0 + n ? (g0 + n - first + ix->world - 1) / ix->world : 0;
+  if (ix->nlocal + mine > ix->capacity)
+    return cb::fail(CB_ENOMEM, "index capacity %lld exceeded (have %lld, adding %lld)", (long long)ix->capacity,
+                    (long long)ix->nlocal, (long long)mine);
+  if (mine > 0) {
+    const size_t rowb = (size_t)ix->d * sizeof(float);
+    CB_CUDA(cudaMemcpy2DAsync(ix->rows + (size_t)ix->nlocal * ix->d, rowb, x + (size_t)(first - g0) * ix->d,
+                              rowb * ix->world, rowb, (size_t)mine, kind, st));
+  }
+  ix->nlocal += mine;
+  ix->ntotal += n;
+  return CB_OK;
+}
+
+int cb_index_add(cb_index* ix, int64_t n, const float* x) {
+  if (!ix || !x || n < 0) return cb::fail(CB_EINVAL, "bad arguments to cb_index_add");
+  if (n == 0) return CB_OK;
+  cb::DeviceGuard g(ix->device);
+  int rc = add_impl(ix, n, x, cudaMemcpyHostToDevice, ix->stream);
+  if (rc) return rc;
+  CB_CUDA(cudaStreamSynchronize(ix->stream));
+  return CB_OK;
+}
+
+int cb_index_add_device(cb_index* ix, int64_t n, const float* x_dev, void* stream) {
+  if (!ix || !x_dev || n < 0) return cb::fail(CB_EINVAL, "bad arguments to cb_index_add_device");
+  if (n == 0) return CB_OK;
+  cb::DeviceGuard g(ix->device);
+  return add_impl(ix, n, x_dev, cudaMemcpyDeviceToDevice, stream ? (cudaStream_t)stream : ix->stream);
+}
+
+int cb_index_add_f64(cb_index* ix, int64_t n, const double* x) {
+  if (!ix || !x || n < 0) return cb::fail(CB_EINVAL, "bad arguments to cb_index_add_f64");
+  if (n == 0) return CB_OK;
+  cb::DeviceGuard g(ix->device);
+  const size_t elems = (size_t)n * ix->d;
+  int rc = grow(&ix->stage, &ix->stage_bytes, elems * (sizeof(double) + sizeof(float)));
+  if (rc) return rc;
+  double* d64 = (double*)ix->stage;
+  float* f32 = (float*)(d64 + elems);
+  CB_CUDA(cudaMemcpyAsync(d64, x, elems * sizeof(double), cudaMemcpyHostToDevice, ix->stream));
+  f64_to_f32_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, ix->stream>>>(d64, f32, (long long)elems);
+  CB_LAUNCH_CHECK();
+  rc = add_impl(ix, n, f32, cudaMemcpyDeviceToDevice, ix->stream);
+  if (rc) return rc;
+  CB_CUDA(cudaStreamSynchronize(ix->stream));
+  return CB_OK;
+}
+
+int cb_index_search_device(cb_index* ix, int nq, const float* xq_dev, int k, int64_t limit_rows,
+                           int tie_mode, double* scores_dev, int64_t* labels_dev, void* stream) {
+  if (!ix || !xq_dev || !scores_dev || !labels_dev) return cb::fail(CB_EINVAL, "NULL argument to cb_index_search_device");
+  if (nq <= 0) return cb::fail(CB_EINVAL, "nq must be > 0");
+  if (k < 1 || k > kList) return cb::fail(CB_EINVAL, "k must be in [1,32], got %d", k);
+  cb::DeviceGuard g(ix->device);
+  return search_device_impl(ix, nq, xq_dev, k, limit_rows, tie_mode, scores_dev, (long long*)labels_dev,
+                            stream ? (cudaStream_t)stream : ix->stream);
+}
+
+int cb_index_search(cb_index* ix, int nq, const float* xq, int k, int64_t limit_rows, int tie_mode,
+                    float* distances, int64_t* labels, double* scores_f64) {
+  if (!ix || !xq || !labels) return cb::fail(CB_EINVAL, "NULL argument to cb_index_search");
+  if (nq <= 0) return cb::fail(CB_EINVAL, "nq must be > 0");
+  if (k < 1 || k > kList) return cb::fail(CB_EINVAL, "k must be in [1,32], got %d", k);
+  cb::DeviceGuard g(ix->device);
+  int rc = grow((void**)&ix->q_dev, &ix->q_bytes, (size_t)nq * ix->d * sizeof(float));
+  if (rc) return rc;
+  const size_t oe = (size_t)nq * k;
+  if (ix->out_elems < oe) {
+    if (ix->out_s) cudaFree(ix->out_s);
+    if (ix->out_l) cudaFree(ix->out_l);
+    ix->out_s = nullptr;
+    ix->out_l = nullptr;
+    ix->out_elems = 0;
+    CB_CUDA(cudaMalloc(&ix->out_s, oe * sizeof(double)));
+    CB_CUDA(cudaMalloc(&ix->out_l, oe * sizeof(long long)));
+    ix->out_elems = oe;
+  }
+  CB_CUDA(cudaMemcpyAsync(ix->q_dev, xq, (size_t)nq * ix->d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+  rc = search_device_impl(ix, nq, ix->q_dev, k, limit_rows, tie_mode, ix->out_s, ix->out_l, ix->stream);
+  if (rc) return rc;
+  double* hs = new double[oe];
+  cudaError_t e1 = cudaMemcpyAsync(hs, ix->out_s, oe * sizeof(double), cudaMemcpyDeviceToHost, ix->stream);
+  cudaError_t e2 = cudaMemcpyAsync(labels, ix->out_l, oe * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream);
+  cudaError_t e3 = cudaStreamSynchronize(ix->stream);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    delete[] hs;
+    cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+    return cb::fail(CB_ECUDA, "search copy-out failed: %s", cudaGetErrorString(e));
+  }
+  for (size_t i = 0; i < oe; ++i) {
+    if (distances) distances[i] = (float)hs[i];
+    if (scores_f64) scores_f64[i] = hs[i];
+  }
+  delete[] hs;
+  return CB_OK;
+}
+
+int cb_topk_merge_device(int n_lists, int nq, int k_in, const double* scores_dev, const int64_t* labels_dev,
+                         int k_out, int tie_mode, double* out_scores_dev, int64_t* out_labels_dev, void* stream) {
+  if (n_lists < 1 || nq < 1 || k_in < 1 || k_out < 1 || k_out > kList)
+    return cb::fail(CB_EINVAL, "bad arguments to cb_topk_merge_device");
+  if (!scores_dev || !labels_dev || !out_scores_dev || !out_labels_dev) return cb::fail(CB_EINVAL, "NULL argument");
+  merge_lists_kernel<<<nq, 32, 0, (cudaStream_t)stream>>>(scores_dev, (const long long*)labels_dev, n_lists, nq, k_in,
+                                                          k_out, tie_mode == CB_TIE_HIGH_LABEL, out_scores_dev,
+                                                          (long long*)out_labels_dev);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+int cb_index_naive_candidate(cb_index* ix, int64_t l, int lag, int locality_thresh, float dot_thresh,
+                             int* out_found, int64_t* out_prev, double* out_score, int64_t argmax3[3]) {
+  if (!ix || !out_found) return cb::fail(CB_EINVAL, "NULL argument to cb_index_naive_candidate");
+  if (ix->world != 1) return cb::fail(CB_EINVAL, "naive candidate needs a non-sharded index");
+  if (l > ix->ntotal || l < 3) return cb::fail(CB_EINVAL, "l=%lld outside [3, ntotal=%lld]", (long long)l, (long long)ix->ntotal);
+  *out_found = 0;
+  const int64_t kk = l - lag;  // Cerebro.cpp:1019
+  if (kk <= 5) return CB_OK;   // Cerebro.cpp:1022
+  cb::DeviceGuard g(ix->device);
+  const size_t oe = 3;
+  if (ix->out_elems < oe) {
+    if (ix->out_s) cudaFree(ix->out_s);
+    if (ix->out_l) cudaFree(ix->out_l);
+    ix->out_s = nullptr;
+    ix->out_l = nullptr;
+    ix->out_elems = 0;
+    CB_CUDA(cudaMalloc(&ix->out_s, 32 * sizeof(double)));
+    CB_CUDA(cudaMalloc(&ix->out_l, 32 * sizeof(long long)));
+    ix->out_elems = 32;
+  }
+  // queries = rows l-3, l-2, l-1 (contiguous) -> order them v, vm, vmm = l-1, l-2, l-3 on return
+  const float* xq = ix->rows + (size_t)(l - 3) * ix->d;
+  int rc = search_device_impl(ix, 3, xq, 1, kk, CB_TIE_HIGH_LABEL, ix->out_s, ix->out_l, ix->stream);
+  if (rc) return rc;
+  double hs[3];
+  long long hl[3];
+  CB_CUDA(cudaMemcpyAsync(hs, ix->out_s, sizeof(hs), cudaMemcpyDeviceToHost, ix->stream));
+  CB_CUDA(cudaMemcpyAsync(hl, ix->out_l, sizeof(hl), cudaMemcpyDeviceToHost, ix->stream));
+  CB_CUDA(cudaStreamSynchronize(ix->stream));
+  const long long a = hl[2], am = hl[1], amm = hl[0];
+  if (argmax3) {
+    argmax3[0] = a;
+    argmax3[1] = am;
+    argmax3[2] = amm;
+  }
+  if (out_prev) *out_prev = a;
+  if (out_score) *out_score = hs[2];
+  const long long d1 = a > am ? a - am : am - a, d2 = a > amm ? a - amm : amm - a;
+  if (d1 < locality_thresh && d2 < locality_thresh && hs[2] > (double)dot_thresh) *out_found = 1;  // :1056
+  return CB_OK;
+}
+
+int cb_index_get_rows(cb_index* ix, int64_t first_local, int64_t n, float* out) {
+  if (!ix || !out || first_local < 0 || n < 0 || first_local + n > ix->nlocal)
+    return cb::fail(CB_EINVAL, "bad range for cb_index_get_rows");
+  cb::DeviceGuard g(ix->device);
+  CB_CUDA(cudaMemcpyAsync(out, ix->rows + (size_t)first_local * ix->d, (size_t)n * ix->d * sizeof(float),
+                          cudaMemcpyDeviceToHost, ix->stream));
+  CB_CUDA(cudaStreamSynchronize(ix->stream));
+  return CB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+/*
+ * cerebro_b200.h -- C ABI of the B200-native loop-detection hot path.
+ *
+ * Drop-in boundary for the three seams of mpkuse/cerebro's loop-closure path
+ * (reference file:line cited per entry point):
+ *
+ *   descriptor  <-  ROS service /whole_image_descriptor_compute
+ *                   (srv/WholeImageDescriptorCompute.srv:1-5, server
+ *                   scripts/whole_image_desc_compute_server.py:596-650, client
+ *                   src/Cerebro.cpp:243-275)
+ *   index       <-  faiss::IndexFlatIP add/search/ntotal (src/Cerebro.cpp:390-460) and the
+ *                   three GEMVs + arg-max of Cerebro::descrip_N__dot__descrip_0_N
+ *                   (src/Cerebro.cpp:1019-1043)
+ *   pnp         <-  StaticTheiaPoseCompute::PNP (src/DlsPnpWithRansac.h:169-179,
+ *                   src/DlsPnpWithRansac.cpp:132-245)
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative CB_E* code on failure; no C++
+ *     exception, abort or exit crosses this boundary.  cb_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.
+ *   - handles are opaque; each handle owns its device memory and one CUDA stream and is
+ *     meant to be driven by ONE host thread (the reference drives each seam from its own
+ *     thread: desc_th, dot_product_th, loopcandidate_consumer_th, cerebro_node.cpp:487-509).
+ *     Different handles may be used concurrently from different threads.
+ *   - "_device" variants take raw device pointers (memory owned by the caller, e.g. a
+ *     torch tensor's data_ptr) and a cudaStream_t passed as void* (NULL = the handle's
+ *     stream); they do not synchronise.  All other variants take HOST pointers, copy in
+ *     and out, and return when the result is in the caller's buffer.
+ *   - there is no CPU fallback anywhere behind this ABI: without a CUDA device every
+ *     create call fails with CB_ENODEVICE.
+ */
+#ifndef CEREBRO_B200_H
+#define CEREBRO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CB_API __attribute__((visibility("default")))
+#else
+#define CB_API
+#endif
+
+#define CB_OK 0
+#define CB_EINVAL (-1)    /* bad argument */
+#define CB_ENODEVICE (-2) /* no usable CUDA device / wrong architecture */
+#define CB_ECUDA (-3)     /* CUDA runtime error, see cb_last_error() */
+#define CB_ENOMEM (-4)    /* capacity exceeded / allocation failed */
+#define CB_EREFUSED (-5)  /* input refused by the algorithm (reference returns -1) */
+
+CB_API int cb_version(void);             /* ABI version, currently 1 */
+CB_API const char* cb_last_error(void);  /* thread-local, never NULL */
+CB_API int cb_device_count(void);        /* number of visible CUDA devices (0 if none) */
+
+/* ------------------------------------------------------------------------------------
+ * index: the keyframe descriptor database (row-major fp32, one row per keyframe)
+ * ---------------------------------------------------------------------------------- */
+typedef struct cb_index cb_index;
+
+/* tie rule when two rows have exactly the same score */
+#define CB_TIE_LOW_LABEL 0  /* lower label wins (stable order, FAISS-like)            */
+#define CB_TIE_HIGH_LABEL 1 /* higher label wins: src/Cerebro.cpp:1039-1043 keeps the   */
+                            /* LAST index equal to the max                             */
+
+/* IndexFlatIP(d) (src/Cerebro.cpp:390).  `capacity` rows are preallocated on `device`
+ * (the reference preallocates 29000 columns, src/Cerebro.cpp:946).  A sharded index
+ * holds the rows whose global label g satisfies g % world == rank; world=1, rank=0 is the
+ * plain single-GPU index.  Labels are always GLOBAL insertion order. */
+CB_API int cb_index_create(cb_index** out, int d, int64_t capacity, int device, int rank, int world);
+CB_API int cb_index_destroy(cb_index* ix);
+CB_API int cb_index_reset(cb_index* ix);
+CB_API int64_t cb_index_ntotal(const cb_index* ix); /* GLOBAL number of rows added (all shards) */
+CB_API int64_t cb_index_nlocal(const cb_index* ix); /* rows resident on this shard */
+CB_API int cb_index_dim(const cb_index* ix);
+
+/* index.add(n, x) (src/Cerebro.cpp:431).  x holds n consecutive GLOBAL rows [n][d]; a
+ * sharded index keeps only its own.  _f64 takes the VectorXd the reference stores in
+ * DataNode (src/DataNode.cpp:427-444) and narrows to fp32 on the device. */
+CB_API int cb_index_add(cb_index* ix, int64_t n, const float* x);
+CB_API int cb_index_add_f64(cb_index* ix, int64_t n, const double* x);
+CB_API int cb_index_add_device(cb_index* ix, int64_t n, const float* x_dev, void* stream);
+
+/* index.search(nq, xq, k, distances, labels) (src/Cerebro.cpp:460): the k largest inner
+ * products per query in descending order, labels = global insertion index, padded with
+ * (-inf, -1).  Only rows with label < limit_rows take part (limit_rows < 0: all rows):
+ * this is the reference's 50/150-descriptor lag (src/Cerebro.cpp:914,1019 / :374,415).
+ * 1 <= k <= 32.  The sweep accumulates in fp32; the 32 best rows per query are then
+ * re-scored in fp64 on the device, so ordering and `scores_f64` match an fp64 reference.
+ * `scores_f64` may be NULL. */
+CB_API int cb_index_search(cb_index* ix, int nq, const float* xq, int k, int64_t limit_rows, int tie_mode,
+                    float* distances, int64_t* labels, double* scores_f64);
+
+/* Same on device buffers; outputs [nq][k] fp64 scores and int64 labels of THIS shard. */
+CB_API int cb_index_search_device(cb_index* ix, int nq, const float* xq_dev, int k, int64_t limit_rows,
+                           int tie_mode, double* scores_dev, int64_t* labels_dev, void* stream);
+
+/* Merge `n_lists` top-k lists laid out [n_lists][nq][k_in] (e.g. the all-gathered
+ * per-shard results) into [nq][k_out], same ordering rule.  Pure device function. */
+CB_API int cb_topk_merge_device(int n_lists, int nq, int k_in, const double* scores_dev,
+                         const int64_t* labels_dev, int k_out, int tie_mode, double* out_scores_dev,
+                         int64_t* out_labels_dev, void* stream);
+
+/* One iteration of Cerebro::descrip_N__dot__descrip_0_N (src/Cerebro.cpp:1019-1081) for
+ * list length l on a NON-sharded index that already holds rows [0,l): scores of rows
+ * l-1, l-2, l-3 against rows [0, l-lag), arg-max with the last-index tie rule, locality
+ * and threshold test.  out[0]=1 if a loop candidate was found else 0; out_prev = arg-max
+ * of the newest descriptor; out_score = its fp64 score; argmax3 = the three arg-maxes. */
+CB_API int cb_index_naive_candidate(cb_index* ix, int64_t l, int lag, int locality_thresh,
+                             float dot_thresh, int* out_found, int64_t* out_prev,
+                             double* out_score, int64_t argmax3[3]);
+
+/* Copy rows [first, first+n) of this shard's LOCAL storage to the host (testing and
+ * DataManager::saveStateToDisk, src/DataManager.cpp:1157-1168). */
+CB_API int cb_index_get_rows(cb_index* ix, int64_t first_local, int64_t n, float* out);
+
+/* raw device pointer to local row storage (row-major, stride d floats) */
+CB_API const float* cb_index_device_rows(const cb_index* ix);
+
+/* ------------------------------------------------------------------------------------
+ * descriptor: NetVLAD whole-image descriptor forward pass
+ * ---------------------------------------------------------------------------------- */
+typedef struct cb_descriptor cb_descriptor;
+
+/* Network description handed over by the host side (weights already BN-folded, fp32):
+ * MobileNet-v1 prefix + NetVLAD as listed in scripts/keras.models/model.json. */
+typedef struct cb_netvlad_weights {
+  int in_channels;        /* 1 or 3 */
+  int n_blocks;           /* depthwise/pointwise blocks after conv1 */
+  const float* conv1_w;   /* [3][3][in_channels][32]  (kh,kw,cin,cout) */
+  const float* conv1_b;   /* [32] */
+  const float* const* dw_w; /* n_blocks x [3][3][C]  */
+  const float* const* dw_b; /* n_blocks x [C]        */
+  const float* const* pw_w; /* n_blocks x [C][Cout]  (NULL entry: block has no pointwise) */
+  const float* const* pw_b; /* n_blocks x [Cout]     */
+  const int* dw_stride;   /* n_blocks, 1 or 2 */
+  const int* channels_out; /* n_blocks, Cout of the block */
+  int vlad_k;             /* clusters */
+  int vlad_d;             /* feature dim entering NetVLAD */
+  const float* vlad_w;    /* [D][K] */
+  const float* vlad_b;    /* [K] */
+  const float* vlad_c;    /* [D][K] */
+} cb_netvlad_weights;
+
+/* HDF5ModelImageDescriptor.__init__(kerasmodel_file, im_rows, im_cols, im_chnls)
+ * (server.py:492-593): allocates activations for `max_batch` frames of rows x cols x chnls. */
+CB_API int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int rows, int cols,
+                         int chnls, int max_batch, int device);
+CB_API int cb_descriptor_destroy(cb_descriptor* d);
+CB_API int cb_descriptor_dim(const cb_descriptor* d); /* K * D, what the probe call learns (Cerebro.cpp:113-120) */
+
+/* handle_req (server.py:596-650) for `n` frames: uint8 images [n][rows][cols][chnls]
+ * (row_stride_bytes between image rows, 0 = tight) -> fp32 descriptors [n][K*D], unit L2 norm,
+ * index k*D+d.  The ROS shim widens to float64[] (srv:4). */
+CB_API int cb_descriptor_compute(cb_descriptor* d, int n, const uint8_t* images, int64_t row_stride_bytes,
+                          float* out);
+CB_API int cb_descriptor_compute_device(cb_descriptor* d, int n, const uint8_t* images_dev, float* out_dev,
+                                 void* stream);
+/* debugging / parity: copy the activation after layer `layer` (0 = conv1, then dw1, pw1, dw2, ...)
+ * of frame 0 as fp32 NHWC to the host. Returns number of floats written or negative error. */
+CB_API int64_t cb_descriptor_get_activation(cb_descriptor* d, int layer, float* out, int64_t max_floats);
+
+/* ------------------------------------------------------------------------------------
+ * pnp: batched DLS-PnP RANSAC
+ * ---------------------------------------------------------------------------------- */
+typedef struct cb_pnp cb_pnp;
+
+typedef struct cb_ransac_params { /* theia::RansacParameters as set at DlsPnpWithRansac.cpp:207-212 */
+  double error_thresh;        /* 0.03 */
+  double min_inlier_ratio;    /* 0.7  */
+  int max_iterations;         /* 50 (hypotheses evaluated per candidate) */
+  int min_iterations;         /* 5  */
+  int use_mle;                /* 1  */
+  double failure_probability; /* 0.01 (Theia default) */
+  int adaptive;               /* 1: Theia's sequential adaptive termination is replayed over the
+                                    hypotheses; 0: all max_iterations hypotheses count (BASELINE config 5) */
+  uint64_t seed;              /* counter-based sampler key (used when samples == NULL) */
+} cb_ransac_params;
+
+CB_API void cb_ransac_params_default(cb_ransac_params* p);
+
+CB_API int cb_pnp_create(cb_pnp** out, int max_candidates, int max_points_total, int max_hypotheses, int device);
+CB_API int cb_pnp_destroy(cb_pnp* p);
+
+/* StaticTheiaPoseCompute::PNP for a batch of loop candidates.
+ *   offsets [n_cand+1]: candidate c owns correspondences [offsets[c], offsets[c+1])
+ *   X  [total][3] fp64 : 3-D points in frame a            (w_X,  DlsPnpWithRansac.cpp:132)
+ *   uv [total][2] fp64 : normalised image coords in b     (c_uv_normalized)
+ *   samples: NULL, or int32 [n_cand][max_iterations][15] indices local to the candidate
+ *   c_T_w [n_cand][16] row-major 4x4, confidence [n_cand] (= return value; -1 when a
+ *   candidate has < 20 points, :136-139), num_iterations, n_inliers, best_hyp (may be NULL). */
+CB_API int cb_pnp_solve_batch(cb_pnp* p, int n_cand, const int32_t* offsets, const double* X,
+                       const double* uv, const cb_ransac_params* params, const int32_t* samples,
+                       double* c_T_w, float* confidence, int32_t* num_iterations,
+                       int32_t* n_inliers, int32_t* best_hyp);
+CB_API int cb_pnp_solve_batch_device(cb_pnp* p, int n_cand, const int32_t* offsets_dev, int total_points,
+                              const double* X_dev, const double* uv_dev, const cb_ransac_params* params,
+                              const int32_t* samples_dev, double* c_T_w_dev, float* confidence_dev,
+                              int32_t* num_iterations_dev, int32_t* n_inliers_dev,
+                              int32_t* best_hyp_dev, void* stream);
+
+/* Minimal solver only (theia::DlsPnp as called at DlsPnpWithRansac.h:61) for n_sets sets of
+ * exactly `m` points: up to 27 solutions per set.  n_solutions [n_sets]; R [n_sets][27][9]
+ * row-major, t [n_sets][27][3].  For parity tests of the solver. */
+CB_API int cb_pnp_dls_minimal(cb_pnp* p, int n_sets, int m, const double* X, const double* uv,
+                       int32_t* n_solutions, double* R, double* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CEREBRO_B200_H */
