@@ -602,7 +602,7 @@ int cb_index_add_device(cb_index* ix, int64_t n, const float* x_dev, void* strea
   if (!ix || !x_dev || n < 0) return cb::fail(CB_EINVAL, "bad arguments to cb_index_add_device");
   if (n == 0) return CB_OK;
   cb::DeviceGuard g(ix->device);
-  return add_impl(ix, n, x_dev, cudaMemcpyDeviceToDevice, stream ? (cudaStream_t)stream : ix->stream);
+  return add_impl(ix, n, x_dev, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
 }
 
 int cb_index_add_f64(cb_index* ix, int64_t n, const double* x) {
@@ -630,7 +630,7 @@ int cb_index_search_device(cb_index* ix, int nq, const float* xq_dev, int k, int
   if (k < 1 || k > kList) return cb::fail(CB_EINVAL, "k must be in [1,32], got %d", k);
   cb::DeviceGuard g(ix->device);
   return search_device_impl(ix, nq, xq_dev, k, limit_rows, tie_mode, scores_dev, (long long*)labels_dev,
-                            stream ? (cudaStream_t)stream : ix->stream);
+                            (cudaStream_t)stream);
 }
 
 int cb_index_search(cb_index* ix, int nq, const float* xq, int k, int64_t limit_rows, int tie_mode,

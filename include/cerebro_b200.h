@@ -23,8 +23,9 @@
  *     thread: desc_th, dot_product_th, loopcandidate_consumer_th, cerebro_node.cpp:487-509).
  *     Different handles may be used concurrently from different threads.
  *   - "_device" variants take raw device pointers (memory owned by the caller, e.g. a
- *     torch tensor's data_ptr) and a cudaStream_t passed as void* (NULL = the handle's
- *     stream); they do not synchronise.  All other variants take HOST pointers, copy in
+ *     torch tensor's data_ptr) and a cudaStream_t passed as void* (NULL = the CUDA default
+ *     stream, as everywhere in CUDA); they enqueue on exactly that stream and do not
+ *     synchronise.  Use one stream per handle for its device calls (scratch is per handle).  All other variants take HOST pointers, copy in
  *     and out, and return when the result is in the caller's buffer.
  *   - there is no CPU fallback anywhere behind this ABI: without a CUDA device every
  *     create call fails with CB_ENODEVICE.

@@ -1,0 +1,193 @@
+"""CPU tests that pin the oracle: committed golden fixtures, invariants, independent solvers."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import dls_pnp as D
+from oracle import netvlad as NV
+from oracle import search as S
+from tests import golden_io, synth
+
+
+# ------------------------------------------------------------------ DLS-PnP
+def _T(C, t):
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = C, t
+    return T
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_dls_noise_free_recovery(seed):
+    rng = np.random.default_rng(seed)
+    X, uv, T, _ = D.synth_candidate(rng, n=15, noise=0.0, outlier_frac=0.0)
+    sols = D.dls_pnp(X, uv)
+    assert len(sols) >= 1
+    err = min(D.pose_error(_T(*s), T) for s in sols)
+    assert err[0] < 1e-9 and err[1] < 1e-9
+
+
+def test_dls_all_27_roots_satisfy_gradient():
+    rng = np.random.default_rng(3)
+    X, uv, _, _ = D.synth_candidate(rng, n=15, noise=1e-3, outlier_frac=0.0)
+    _, coef, _ = D.dls_setup(X, uv)
+    s, real = D.dls_roots(coef)
+    assert s.shape == (27, 3)
+    for j in range(27):
+        mono = np.array([s[j, 0] ** e[0] * s[j, 1] ** e[1] * s[j, 2] ** e[2] for e in D.M3])
+        scale = np.abs(coef).max() * max(1.0, np.abs(mono).max())
+        assert np.abs(coef @ mono).max() < 1e-6 * scale
+    assert real.sum() >= 1
+
+
+def test_macaulay_block_triangular_structure():
+    """The 93x93 block ordered by descending degree is block upper-triangular with diagonal
+    blocks 36,27,18,9,3 -- the structure the CUDA elimination exploits."""
+    rng = np.random.default_rng(0)
+    X, uv, _, _ = D.synth_candidate(rng, n=15)
+    _, coef, _ = D.dls_setup(X, uv)
+    M11 = D.macaulay_matrix(coef)[27:, 27:]
+    deg = np.array([sum(e) for e in D.NONRED])
+    assert [int((deg == p).sum()) for p in (7, 6, 5, 4, 3)] == [36, 27, 18, 9, 3]
+    assert np.all(M11[deg[:, None] < deg[None, :]] == 0)
+
+
+def test_dls_agrees_with_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(11)
+    X, uv, T, _ = D.synth_candidate(rng, n=60, noise=1e-3, outlier_frac=0.0)
+    sols = D.dls_pnp(X, uv)
+    assert len(sols) == 1
+    ok, rvec, tvec = cv2.solvePnP(X, uv, np.eye(3), None, flags=cv2.SOLVEPNP_SQPNP)
+    R, _ = cv2.Rodrigues(rvec)
+    e = D.pose_error(_T(*sols[0]), _T(R, tvec.ravel()))
+    assert e[0] < 1e-3 and e[1] < 1e-2
+
+
+def test_sampler_is_deterministic_and_distinct():
+    a = D.sample_indices(5, 3, 17, 200)
+    b = D.sample_indices(5, 3, 17, 200)
+    assert np.array_equal(a, b) and len(set(a.tolist())) == 15 and a.min() >= 0 and a.max() < 200
+    assert not np.array_equal(a, D.sample_indices(5, 3, 18, 200))
+    small = D.sample_indices(1, 0, 0, 15)
+    assert sorted(small.tolist()) == list(range(15))
+    # known-answer vector so the CUDA sampler can be pinned bit for bit
+    assert D.sample_indices(99, 0, 0, 200).tolist() == golden_io.load("pnp_golden.npz")["c0_tab"][0].tolist()
+
+
+def test_ransac_golden_and_truth():
+    g = golden_io.load("pnp_golden.npz")
+    for c in range(6):
+        X, uv, tab = g["c%d_X" % c], g["c%d_uv" % c], g["c%d_tab" % c]
+        r = D.ransac_pnp(X, uv, tab)
+        meta = g["c%d_adaptive_meta" % c]
+        assert r["num_iterations"] == int(meta[1]) and r["n_inliers"] == int(meta[2]) and r["best_hyp"] == int(meta[3])
+        assert np.allclose(r["T"], g["c%d_adaptive_T" % c], atol=1e-9)
+        assert abs(r["confidence"] - meta[0]) < 1e-12
+        if r["confidence"] > 0.5:  # candidates with 30-40 % outliers legitimately fail at 50 iterations
+            e = D.pose_error(r["T"], g["c%d_Ttrue" % c])
+            assert e[0] < 5e-3 and e[1] < 5e-2
+
+
+def test_ransac_refuses_few_points_and_bookkeeping():
+    rng = np.random.default_rng(4)
+    X, uv, _, _ = D.synth_candidate(rng, n=19)
+    assert D.ransac_pnp(X, uv, D.sample_table(0, 0, 50, 19))["confidence"] == -1.0  # DlsPnpWithRansac.cpp:136-139
+    X, uv, _, _ = D.synth_candidate(rng, n=200, outlier_frac=0.0)
+    r = D.ransac_pnp(X, uv, D.sample_table(0, 0, 50, 200))
+    # all inliers: ratio 1.0 -> bound collapses to min_iterations (5)
+    assert r["num_iterations"] == 5 and r["n_inliers"] == 200 and r["confidence"] == 1.0
+    p = D.RansacParameters(adaptive=False, max_iterations=20)
+    r = D.ransac_pnp(X, uv, D.sample_table(0, 0, 20, 200), p)
+    assert r["num_iterations"] == 20
+
+
+# ------------------------------------------------------------------ search
+def test_last_argmax_tie_rule():
+    assert S.last_argmax(np.array([0.1, 0.9, 0.3, 0.9, 0.2])) == 3  # Cerebro.cpp:1039-1043
+
+
+def test_naive_stream_finds_planted_loops():
+    d, n = 256, 300
+    base = synth.unit_rows(n, d, seed=1)
+    desc = base.copy()
+    for i in range(30):
+        desc[200 + i] = synth.planted_queries(base, [50 + i], seed=10 + i, score=0.95)[0]
+    found = S.naive_stream(desc.astype(np.float64), list(range(3, n + 1, 3)))
+    assert found and all(200 <= a < 230 and abs((a - 150) - b) <= 0 for a, b, _ in found)
+    assert all(s > 0.85 for *_, s in found)
+    # lag: nothing can be found while k = l - 50 <= 5
+    assert S.naive_step(np.ascontiguousarray(desc.T.astype(np.float64)), 55) is None
+
+
+def test_index_flat_ip_contract():
+    db = synth.unit_rows(100, 128, seed=2)
+    ix = S.IndexFlatIP(128)
+    ix.add(db[:40])
+    ix.add(db[40:])
+    assert ix.ntotal == 100
+    Dd, I = ix.search(db[7], 5)
+    assert I[0, 0] == 7 and np.all(np.diff(Dd[0]) <= 0)
+    Dd, I = ix.search(db[7], 5, limit_rows=3)
+    assert set(I[0, :3]) == {0, 1, 2} and np.all(I[0, 3:] == -1) and np.all(np.isinf(Dd[0, 3:]))
+
+
+def test_faiss_naive_stream_runs():
+    d, n = 256, 400
+    base = synth.unit_rows(n, d, seed=5)
+    desc = base.copy()
+    for i in range(30):
+        desc[330 + i] = synth.planted_queries(base, [20 + i], seed=40 + i, score=0.95)[0]
+    found = S.faiss_naive_stream(desc, list(range(3, n + 1, 3)))
+    assert found and all(abs((a - 310) - b) <= 2 for a, b, _ in found)
+
+
+# ------------------------------------------------------------------ NetVLAD
+@pytest.mark.parametrize("model,c,dim", [("mobilenet_conv7", 3, 8192), ("gray_conv6", 1, 4096)])
+def test_netvlad_golden_and_invariants(model, c, dim):
+    w = golden_io.raw_weights(model)
+    gold = golden_io.load("netvlad_golden.npz")["%s_96x128_desc64" % model]
+    imgs = synth.band_limited_images(2, 96, 128, c, seed=96 + c)
+    d64 = NV.describe(imgs, w, dtype="float64")
+    assert d64.shape == (2, dim)
+    assert np.allclose(d64, gold, atol=1e-12)
+    d32 = NV.describe(imgs, w, dtype="float32")
+    assert np.abs(d32 - d64).max() < 2e-5
+    # predict_utils.py:59-61: unit norm; every K-major block was intra-normalised, so all blocks
+    # share one norm -- except clusters whose soft-assignment mass is so small that
+    # tf.nn.l2_normalize's epsilon (1e-12 on the squared norm) clamps them below it.
+    assert np.allclose(np.linalg.norm(d64, axis=1), 1.0, atol=1e-12)
+    K = 16
+    bn = np.linalg.norm(d64.reshape(2, K, dim // K), axis=2)
+    top = bn.max(axis=1, keepdims=True)
+    assert np.all((np.abs(bn - top) < 1e-12) | (bn < top))
+    assert np.all((np.abs(bn - top) < 1e-12).sum(axis=1) >= 4)
+
+
+def test_netvlad_plus_centers_sign():
+    """predict_utils.py:47 adds the cluster centres (x + C); flipping the sign must change the output."""
+    w = golden_io.raw_weights("gray_conv6")
+    imgs = synth.band_limited_images(1, 96, 128, 1, seed=1)
+    a = NV.describe(imgs, w, dtype="float64")
+    w2 = dict(w)
+    w2["net_vlad_layer_1/cluster_centers"] = -w["net_vlad_layer_1/cluster_centers"]
+    b = NV.describe(imgs, w2, dtype="float64")
+    assert np.abs(a - b).max() > 1e-4
+
+
+def test_bn_folding_matches_unfolded_oracle():
+    """The product folds BN into conv weights on the host; check that algebra on CPU."""
+    import torch
+    import torch.nn.functional as F
+
+    from cerebro_b200.keras_weights import fold_mobilenet_netvlad
+
+    w = golden_io.raw_weights("gray_conv6")
+    net = fold_mobilenet_netvlad(w)
+    imgs = synth.band_limited_images(1, 64, 96, 1, seed=2)
+    x = NV.preprocess(imgs, torch.float64)
+    _, acts = NV.backbone(x, w, return_all=True)
+    k = torch.as_tensor(net["conv1_w"], dtype=torch.float64).permute(3, 2, 0, 1)
+    y = F.conv2d(F.pad(x, (0, 1, 0, 1)), k, stride=2) + torch.as_tensor(net["conv1_b"], dtype=torch.float64).view(1, -1, 1, 1)
+    y = torch.clamp(y, 0, 6)
+    assert torch.allclose(y, acts[0], atol=1e-5)
