@@ -1,0 +1,119 @@
+"""GPU parity: NetVLAD forward (through the C ABI) vs the torch-CPU oracle.
+
+Floating-point path: activations and pointwise weights are fp16 on the device (fp32 accumulate in
+TMEM), the oracle is fp64.  north_star states no tolerance for the descriptor ("L2 error reported");
+the bound asserted here -- L2 distance < 1e-2 between unit vectors, i.e. a dot-product perturbation far
+below the 0.85 / 0.9 decision thresholds and the >= 0.05 score gaps -- is this repo's own."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import golden_io, synth
+
+pytestmark = pytest.mark.gpu
+
+L2_TOL = 1e-2
+
+
+def _net(model):
+    from cerebro_b200.keras_weights import fold_mobilenet_netvlad
+
+    return fold_mobilenet_netvlad(golden_io.raw_weights(model))
+
+
+@pytest.mark.parametrize("model,c", [("gray_conv6", 1), ("mobilenet_conv7", 3)])
+@pytest.mark.parametrize("h,w", [(96, 128), (240, 320)])
+def test_descriptor_matches_golden(native_lib, cuda_device, model, c, h, w):
+    from cerebro_b200.descriptor import NetvladDescriptor
+
+    gold = golden_io.load("netvlad_golden.npz")["%s_%dx%d_desc64" % (model, h, w)]
+    imgs = synth.band_limited_images(2, h, w, c, seed=h + c)
+    nd = NetvladDescriptor(_net(model), h, w, c, max_batch=2)
+    d = nd.compute(imgs)
+    assert d.shape == gold.shape
+    err = np.linalg.norm(d.astype(np.float64) - gold, axis=1)
+    cos = (d.astype(np.float64) * gold).sum(1)
+    print("model %s %dx%d: L2 err %s cos %s" % (model, h, w, err, cos))
+    assert np.all(err < L2_TOL), err
+    assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)
+    # batch invariance: frame 1 alone gives the same bits as frame 1 inside the batch
+    d1 = nd.compute(imgs[1:2])
+    assert np.array_equal(d1[0], d[1])
+    nd.close()
+
+
+def test_layerwise_against_oracle(native_lib, cuda_device):
+    """Every layer's activation (fp16 on the device) vs the oracle's fp32 activation of the same layer."""
+    import torch
+
+    from cerebro_b200.descriptor import NetvladDescriptor
+    from oracle import netvlad as NV
+
+    model, c, h, w = "mobilenet_conv7", 3, 96, 128
+    raw = golden_io.raw_weights(model)
+    net = _net(model)
+    imgs = synth.band_limited_images(1, h, w, c, seed=5)
+    x = NV.preprocess(imgs, torch.float32)
+    _, acts = NV.backbone(x, raw, return_all=True)
+    worst = 0.0
+    try:
+        for layer, a in enumerate(acts):
+            os.environ["CB_DEBUG_STOP_LAYER"] = str(layer)
+            nd = NetvladDescriptor(net, h, w, c, max_batch=1)
+            nd.compute(imgs)
+            got = nd.get_activation(layer)
+            ref = a[0].permute(1, 2, 0).contiguous().numpy().reshape(-1)  # NHWC
+            assert got.shape == ref.shape, (layer, got.shape, ref.shape)
+            err = np.abs(got - ref).max()
+            worst = max(worst, err)
+            assert err < 0.05, "layer %d: max abs err %g (activations live in [0,6])" % (layer, err)
+            nd.close()
+    finally:
+        os.environ.pop("CB_DEBUG_STOP_LAYER", None)
+    print("worst layer abs err", worst)
+
+
+def test_tcgen05_path_agrees_with_cuda_core_path(native_lib, cuda_device):
+    from cerebro_b200.descriptor import NetvladDescriptor
+
+    model, c, h, w = "mobilenet_conv7", 3, 240, 320
+    net = _net(model)
+    imgs = synth.band_limited_images(3, h, w, c, seed=9)
+    nd = NetvladDescriptor(net, h, w, c, max_batch=3)
+    a = nd.compute(imgs)
+    nd.close()
+    os.environ["CB_PW_SIMT"] = "1"
+    try:
+        nd = NetvladDescriptor(net, h, w, c, max_batch=3)
+        b = nd.compute(imgs)
+        nd.close()
+    finally:
+        os.environ.pop("CB_PW_SIMT", None)
+    assert np.linalg.norm(a - b, axis=1).max() < 2e-3
+
+
+def test_reference_server_call_shape(native_lib, cuda_device, tmp_path):
+    """HDF5ModelImageDescriptor(kerasmodel_file, rows, cols, chnls).handle_req(req) as in server.py."""
+    from cerebro_b200 import keras_weights
+    from cerebro_b200.descriptor import HDF5ModelImageDescriptor
+
+    path = os.path.join(str(tmp_path), "gray_conv6_K16__centeredinput", "core_model.cbw")
+    os.makedirs(os.path.dirname(path))
+    keras_weights.save_cbw(path, _net("gray_conv6"))
+    srv = HDF5ModelImageDescriptor(path, im_rows=96, im_cols=128, im_chnls=1)
+    assert srv.model_type == "gray_conv6_K16__centeredinput"
+
+    class Req:
+        pass
+
+    req = Req()
+    req.ima = synth.band_limited_images(1, 96, 128, 1, seed=97)[0, :, :, 0]  # 2-D mono8 image
+    req.a = 986
+    res = srv.handle_req(req)
+    assert len(res.desc) == 4096 and res.desc.dtype == np.float64 and res.model_type == srv.model_type
+    gold = golden_io.load("netvlad_golden.npz")["gray_conv6_96x128_desc64"][0]
+    assert np.linalg.norm(res.desc - gold) < L2_TOL
+    req.ima = np.zeros((100, 128), dtype=np.uint8)
+    with pytest.raises(AssertionError):
+        srv.handle_req(req)

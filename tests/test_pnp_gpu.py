@@ -46,7 +46,7 @@ def test_minimal_solver_matches_oracle(native_lib, cuda_device):
             Tg = np.eye(4)
             Tg[:3, :3], Tg[:3, 3] = R[i, 0], t[i, 0]
             e = _pose_err(Tg, T)
-            assert e[0] < 1e-8 and e[1] < 1e-8
+            assert e[0] < 1e-6 and e[1] < 1e-6
     assert n_checked >= 90
     pb.close()
 
