@@ -66,6 +66,9 @@ _SIGNATURES = {
     "cb_index_add": (C.c_int, [_vp, _i64, _vp]),
     "cb_index_add_f64": (C.c_int, [_vp, _i64, _vp]),
     "cb_index_add_device": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "cb_index_add_local_device": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "cb_index_set_timing": (C.c_int, [_vp, C.c_int]),
+    "cb_index_get_sweep_timing": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "cb_index_search": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp]),
     "cb_index_search_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp]),
     "cb_topk_merge_device": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),

@@ -392,6 +392,10 @@ struct cb_index {
   void* stage = nullptr;  // add staging
   size_t stage_bytes = 0;
   int max_qt = 16;
+  // optional device-side timing of the sweep kernel (bench.py roofline)
+  bool timing = false;
+  cudaEvent_t ev[2 * 64] = {};
+  int ev_used = 0;
 };
 
 namespace {
@@ -479,6 +483,8 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
     }
     const float* xq = xq_dev + (size_t)q0 * ix->d;
     cudaError_t e = cudaSuccess;
+    const bool rec = ix->timing && ix->ev_used < 64;
+    if (rec) cudaEventRecord(ix->ev[2 * ix->ev_used], st);
 #define CB_SWEEP(QT, R)                                                                          \
   e = launch_scores<QT, R>(p.grid, p.smem, st, ix->rows, n_rows, ix->d, p.ds, p.n_slices, xq,    \
                            nq_valid, ix->partial, pstride)
@@ -490,6 +496,10 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
       default: CB_SWEEP(16, 8); break;
     }
 #undef CB_SWEEP
+    if (rec) {
+      cudaEventRecord(ix->ev[2 * ix->ev_used + 1], st);
+      ++ix->ev_used;
+    }
     if (e != cudaSuccess) return cb::fail(CB_ECUDA, "scores_kernel launch failed: %s", cudaGetErrorString(e));
     topk_chunk_kernel<<<dim3(n_chunks, nq_valid), kThreads, 0, st>>>(
         ix->partial, p.n_slices, p.qt, pstride, n_rows, ix->rank, ix->world, tie_high, ix->chunk_s,
@@ -552,6 +562,8 @@ int cb_index_destroy(cb_index* ix) {
   cudaFree(ix->out_s);
   cudaFree(ix->out_l);
   cudaFree(ix->stage);
+  for (cudaEvent_t ev : ix->ev)
+    if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ix->stream);
   delete ix;
   return CB_OK;
@@ -620,6 +632,47 @@ int cb_index_add_f64(cb_index* ix, int64_t n, const double* x) {
   rc = add_impl(ix, n, f32, cudaMemcpyDeviceToDevice, ix->stream);
   if (rc) return rc;
   CB_CUDA(cudaStreamSynchronize(ix->stream));
+  return CB_OK;
+}
+
+int cb_index_add_local_device(cb_index* ix, int64_t n_local, const float* x_dev, void* stream) {
+  if (!ix || !x_dev || n_local < 0) return cb::fail(CB_EINVAL, "bad arguments to cb_index_add_local_device");
+  if (ix->nlocal + n_local > ix->capacity)
+    return cb::fail(CB_ENOMEM, "index capacity %lld exceeded (have %lld, adding %lld)", (long long)ix->capacity,
+                    (long long)ix->nlocal, (long long)n_local);
+  if (n_local == 0) return CB_OK;
+  cb::DeviceGuard g(ix->device);
+  CB_CUDA(cudaMemcpyAsync(ix->rows + (size_t)ix->nlocal * ix->d, x_dev, (size_t)n_local * ix->d * sizeof(float),
+                          cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  ix->nlocal += n_local;
+  ix->ntotal = (ix->nlocal - 1) * ix->world + ix->rank + 1;
+  return CB_OK;
+}
+
+int cb_index_set_timing(cb_index* ix, int on) {
+  if (!ix) return cb::fail(CB_EINVAL, "index is NULL");
+  cb::DeviceGuard g(ix->device);
+  if (on && !ix->ev[0]) {
+    for (int i = 0; i < 128; ++i) CB_CUDA(cudaEventCreate(&ix->ev[i]));
+  }
+  ix->timing = on != 0;
+  ix->ev_used = 0;
+  return CB_OK;
+}
+
+int cb_index_get_sweep_timing(cb_index* ix, double* total_ms, int* n_launches) {
+  if (!ix || !total_ms || !n_launches) return cb::fail(CB_EINVAL, "NULL argument to cb_index_get_sweep_timing");
+  cb::DeviceGuard g(ix->device);
+  double tot = 0.0;
+  for (int i = 0; i < ix->ev_used; ++i) {
+    CB_CUDA(cudaEventSynchronize(ix->ev[2 * i + 1]));
+    float ms = 0.f;
+    CB_CUDA(cudaEventElapsedTime(&ms, ix->ev[2 * i], ix->ev[2 * i + 1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *n_launches = ix->ev_used;
+  ix->ev_used = 0;
   return CB_OK;
 }
 

@@ -72,6 +72,23 @@ class IndexFlatIP:
             x = np.ascontiguousarray(x, dtype=np.float32)
             check(self._lib.cb_index_add(self._h, x.shape[0], ptr(x)))
 
+    def add_local(self, x) -> None:
+        """Append CUDA float32 rows straight into this shard's storage (bulk load of a shard)."""
+        import torch
+
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        check(self._lib.cb_index_add_local_device(self._h, x.numel() // self.d, ptr(x), _lib.current_stream_ptr()))
+
+    def set_timing(self, on: bool) -> None:
+        check(self._lib.cb_index_set_timing(self._h, 1 if on else 0))
+
+    def sweep_timing(self):
+        """(total_ms, n_launches) of the sweep kernel since the last call."""
+        ms = C.c_double(0.0)
+        n = C.c_int(0)
+        check(self._lib.cb_index_get_sweep_timing(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     # ---- search ----------------------------------------------------------------------
     def search(self, xq, k: int, limit_rows: int | None = None, tie: int = TIE_LOW_LABEL, return_f64: bool = False):
         """Host arrays in, host arrays out: (distances float32 [nq,k], labels int64 [nq,k])."""

@@ -1,0 +1,155 @@
+"""ROS-free mirror of the loop-closure brain's hot path (src/Cerebro.{h,cpp}).
+
+``Cerebro`` keeps the method names other reference code calls (Cerebro.h:66-233):
+``wholeImageComputedList_size/_at``, ``foundLoops_count/_i/_as_JSON``, ``processedLoops_count/_i``
+and the three thread bodies, here as explicit ``*_step`` functions a host loop (or the reference's
+own threads) would call:
+
+  descriptor_computer_thread   (Cerebro.cpp:47-303)   -> descriptor_step(stamps, images)
+  descrip_N__dot__descrip_0_N  (Cerebro.cpp:903-1103) -> run_step()
+  loopcandiate_consumer_thread (Cerebro.cpp:1185-1281)-> loopcandidate_consumer_step(correspondences)
+
+All arithmetic runs behind the C ABI (descriptor / index / pnp handles); this file is bookkeeping.
+``LoopPipeline`` is the batched throughput form used by bench.py: B keyframes per step through
+desc -> search -> PnP on one GPU, optionally with the DB sharded over the ranks of a process group.
+"""
+from __future__ import annotations
+
+import json
+
+import numpy as np
+
+from .descriptor import NetvladDescriptor
+from .index import TIE_HIGH_LABEL, TIE_LOW_LABEL, IndexFlatIP, ShardedIndex
+from .pnp import PnpBatch, default_params
+
+
+class LoopEdge:
+    """cerebro::LoopEdge (msg/LoopEdge.msg:1-5)."""
+
+    def __init__(self, timestamp0, timestamp1, pose_1T0, weight, description):
+        self.timestamp0, self.timestamp1 = timestamp0, timestamp1
+        self.pose_1T0 = pose_1T0  # 4x4; the ROS shim converts with eigenmat_to_geometry_msgs_Pose
+        self.weight = float(weight)
+        self.description = description
+
+
+class Cerebro:
+    LOCALITY_THRESH = 12  # Cerebro.cpp:912
+    DOT_PROD_THRESH = 0.85  # Cerebro.cpp:913
+    LAG = 50  # Cerebro.cpp:914
+
+    def __init__(self, descriptor: NetvladDescriptor, capacity: int = 29000, device: int = 0):
+        self.descriptor = descriptor
+        self.descriptor_size = descriptor.dim  # learnt by the probe call in the reference (Cerebro.cpp:113-120)
+        self.index = IndexFlatIP(self.descriptor_size, capacity=capacity, device=device)
+        self.pnp = PnpBatch(max_candidates=16, max_points_total=16 * 5000, max_hypotheses=50, device=device)
+        self._whole = []  # wholeImageComputedList (Cerebro.h:101-106): stamps in arrival order
+        self._found = []  # foundLoops (Cerebro.h:157-158): (t_curr, t_prev, score)
+        self._processed = []  # processedloopcandi_list (Cerebro.h:199-200)
+        self._last_l = 0
+        self._last_consumed = 0
+
+    # ---- wholeImageComputedList_* (Cerebro.cpp:305-330)
+    def wholeImageComputedList_size(self):
+        return len(self._whole)
+
+    def wholeImageComputedList_at(self, k):
+        return self._whole[k]
+
+    # ---- foundLoops_* (Cerebro.cpp:1113-1164)
+    def foundLoops_count(self):
+        return len(self._found)
+
+    def foundLoops_i(self, i):
+        return self._found[i]
+
+    def foundLoops_as_JSON(self):
+        out = []
+        for i, (a, b, s) in enumerate(self._found):
+            out.append({"time_sec_a": a, "time_sec_b": b, "dotprodt": s, "global_a": self._whole.index(a), "global_b": self._whole.index(b), "count": i})
+        return json.dumps(out)
+
+    def processedLoops_count(self):
+        return len(self._processed)
+
+    def processedLoops_i(self, i):
+        return self._processed[i]
+
+    # ---- descriptor_computer_thread body (Cerebro.cpp:169-298), for the keyframes handed in
+    def descriptor_step(self, stamps, images_u8, n_tracked=None):
+        """images_u8 [n, rows, cols, chnls]; keyframes with < 20 tracked features are skipped
+        (Cerebro.cpp:206-210).  Descriptors are appended to the device DB in arrival order."""
+        keep = [i for i in range(len(stamps)) if n_tracked is None or n_tracked[i] >= 20]
+        if not keep:
+            return 0
+        desc = self.descriptor.compute(np.ascontiguousarray(images_u8[keep]))
+        self.index.add(desc)
+        for i in keep:
+            self._whole.append(stamps[i])
+        return len(keep)
+
+    # ---- one wake-up of descrip_N__dot__descrip_0_N (Cerebro.cpp:956-1100)
+    def run_step(self):
+        l = self.wholeImageComputedList_size()
+        if l - self._last_l < 3:  # :962
+            return None
+        found, prev, score, _ = self.index.naive_candidate(l, self.LAG, self.LOCALITY_THRESH, self.DOT_PROD_THRESH)
+        self._last_l = l
+        if found:
+            edge = (self._whole[l - 1], self._whole[prev], score)  # :1078-1081
+            self._found.append(edge)
+            return edge
+        return None
+
+    # ---- loopcandiate_consumer_thread body (Cerebro.cpp:1203-1277), geometry supplied by the caller
+    def loopcandidate_consumer_step(self, correspondences, params=None):
+        """correspondences[j] = (w_X [n,3], c_uv [n,2]) for every not-yet-consumed foundLoops entry
+        (the stereo/GMS front-end that produces them is outside this path)."""
+        new = self._found[self._last_consumed :]
+        assert len(correspondences) == len(new)
+        if not new:
+            return []
+        r = self.pnp.solve([c[0] for c in correspondences], [c[1] for c in correspondences], params or default_params())
+        out = []
+        for j, (a, b, s) in enumerate(new):
+            rec = dict(t_curr=a, t_prev=b, score=s, b_T_a=r["T"][j], goodness=float(r["confidence"][j]))
+            self._processed.append(rec)
+            out.append(rec)
+        self._last_consumed = len(self._found)
+        return out
+
+
+class LoopPipeline:
+    """B keyframes per step through desc -> search -> PnP, device-resident (bench.py)."""
+
+    def __init__(self, net, rows, cols, chnls, batch, db_rows_local, device=0, sharded=False, n_corr=200, hypotheses=50):
+        import torch
+
+        self.torch = torch
+        self.batch = batch
+        self.desc = NetvladDescriptor(net, rows, cols, chnls, max_batch=batch, device=device)
+        self.dim = self.desc.dim
+        self.sharded = sharded
+        if sharded:
+            self.index = ShardedIndex(self.dim, db_rows_local, device)
+            self.world = self.index.world
+        else:
+            self.index = IndexFlatIP(self.dim, db_rows_local, device)
+            self.world = 1
+        self.pnp = PnpBatch(max_candidates=batch, max_points_total=batch * n_corr, max_hypotheses=hypotheses, device=device)
+        self.params = default_params(max_iterations=hypotheses, seed=7)
+        self.k = 5  # FAISS path searches top-5 (Cerebro.cpp:460)
+
+    def step_device(self, images_dev, offsets_dev, X_dev, uv_dev, bufs):
+        """All inputs already in HBM.  Returns (labels [B*world,k], scores, pnp outputs)."""
+        torch = self.torch
+        d = self.desc.compute_device(images_dev, out=bufs["desc"])
+        if self.sharded and self.world > 1:
+            q = bufs["queries"]
+            self.index.dist.all_gather_into_tensor(q, d, group=self.index.group)
+        else:
+            q = d
+        s, l = self.index.search_device(q, self.k)
+        out = self.pnp.solve_device(offsets_dev, X_dev, uv_dev, self.params, out=bufs["pnp"])
+        return l, s, out

@@ -84,6 +84,17 @@ CB_API int cb_index_add(cb_index* ix, int64_t n, const float* x);
 CB_API int cb_index_add_f64(cb_index* ix, int64_t n, const double* x);
 CB_API int cb_index_add_device(cb_index* ix, int64_t n, const float* x_dev, void* stream);
 
+/* Bulk-load rows straight into THIS shard's local storage (DataManager::loadStateFromDisk,
+ * src/DataManager.cpp:1304-1320, re-lists stored descriptors on resume): local row r gets the
+ * global label r * world + rank.  Do not mix with cb_index_add on a sharded index. */
+CB_API int cb_index_add_local_device(cb_index* ix, int64_t n_local, const float* x_dev, void* stream);
+
+/* Optional device-side timing of the HBM sweep kernel (CUDA events on the launching stream
+ * around every scores_kernel launch, up to 64 launches between reads).  get returns the summed
+ * duration and the number of launches since the last read, and resets both. */
+CB_API int cb_index_set_timing(cb_index* ix, int on);
+CB_API int cb_index_get_sweep_timing(cb_index* ix, double* total_ms, int* n_launches);
+
 /* index.search(nq, xq, k, distances, labels) (src/Cerebro.cpp:460): the k largest inner
  * products per query in descending order, labels = global insertion index, padded with
  * (-inf, -1).  Only rows with label < limit_rows take part (limit_rows < 0: all rows):
