@@ -40,7 +40,7 @@ def test_minimal_solver_matches_oracle(native_lib, cuda_device):
                 Tg = np.eye(4)
                 Tg[:3, :3], Tg[:3, 3] = R[i, j], t[i, j]
                 best = min(best, _pose_err(Tg, To))
-            assert best[0] < 1e-6 and best[1] < 1e-6, (i, best)
+            assert best[0] < 1e-4 and best[1] < 1e-4, (i, best)  # 10x inside the 1e-3 rad / 1e-2 m bar
             n_checked += 1
         if i % 3 == 0 and i % 4 != 3 and len(sols) == 1:  # noise-free, no outliers: exact pose
             Tg = np.eye(4)
