@@ -70,7 +70,7 @@ def cpu_pipeline_setup(raw, seed=0):
     from oracle import search as osearch
 
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(min(cores, 32))  # batch-1 convolutions do not scale past a few dozen threads
     g = torch.Generator().manual_seed(seed)
     db = torch.randn((DB_ROWS, DIM), generator=g, dtype=torch.float32)
     db /= db.norm(dim=1, keepdim=True)
@@ -143,7 +143,7 @@ class ClockSampler:
         self.p = None
         self.device = device
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None

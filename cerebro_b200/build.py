@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_native")
 LIB = os.path.join(OUT_DIR, "libcerebro_b200.so")
+HARNESS = os.path.join(OUT_DIR, "cerebro_harness")
 SOURCES = ["capi.cu", "search.cu", "pnp.cu", "netvlad.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -57,6 +58,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+    # ROS-free C++ host shim + harness over the C ABI (plain g++, no CUDA headers needed)
+    host = os.path.join(HERE, "host")
+    hsrc = [os.path.join(host, "harness.cpp"), os.path.join(host, "cerebro_shim.hpp"), os.path.join(HERE, "..", "include", "cerebro_b200.h")]
+    if force or _stale(HARNESS, hsrc + [LIB]):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", hsrc[0], "-o", HARNESS, "-L" + OUT_DIR, "-lcerebro_b200",
+               "-Wl,-rpath,$ORIGIN", "-lpthread", "-ldl", "-lrt"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("host harness build failed")
     return LIB
 
 

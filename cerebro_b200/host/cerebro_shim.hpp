@@ -1,0 +1,237 @@
+// ROS-free C++ host shim over the C ABI (include/cerebro_b200.h).
+//
+// Mirrors the slice of the reference's class surface that sits on the loop-detection hot path, with the
+// same method names and semantics, so that the three thread bodies of src/Cerebro.cpp can be pointed at
+// libcerebro_b200.so by replacing only their compute calls (see INTEGRATION.md for the exact patch):
+//
+//   Cerebro::descriptor_computer_thread   src/Cerebro.cpp:47-303    -> cb_descriptor_compute
+//   Cerebro::descrip_N__dot__descrip_0_N  src/Cerebro.cpp:903-1103  -> cb_index_add_f64 + cb_index_naive_candidate
+//   Cerebro::loopcandiate_consumer_thread src/Cerebro.cpp:1185-1281 -> cb_pnp_solve_batch
+//   StaticTheiaPoseCompute::PNP           src/DlsPnpWithRansac.h:169-179
+//
+// ros::Time, DataNode and DataManager are reduced to what those bodies touch (stamp, keyframe flag,
+// tracked-feature count, image, VectorXd descriptor as std::vector<double>).  No Eigen/OpenCV/ROS needed.
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/cerebro_b200.h"
+
+namespace cerebro_b200 {
+
+struct Time {  // stands in for ros::Time (only ordering, toSec and nsec are used on the path)
+  int64_t nsec = 0;
+  double toSec() const { return 1e-9 * (double)nsec; }
+  bool operator<(const Time& o) const { return nsec < o.nsec; }
+  bool operator==(const Time& o) const { return nsec == o.nsec; }
+};
+
+class DataNode {  // src/DataNode.h:52-119, the members the hot path touches
+ public:
+  explicit DataNode(Time t) : stamp(t) {}
+  Time getT() const { return stamp; }
+  bool isKeyFrame() const { return is_keyframe; }
+  int getNumberOfSuccessfullyTrackedFeatures() const { return n_tracked; }
+  void setWholeImageDescriptor(const std::vector<double>& vec) {  // src/DataNode.cpp:427-433
+    std::lock_guard<std::mutex> lk(m);
+    desc = vec;
+    desc_available = true;
+  }
+  std::vector<double> getWholeImageDescriptor() {  // by-value copy, src/DataNode.cpp:435-440
+    std::lock_guard<std::mutex> lk(m);
+    return desc;
+  }
+  bool isWholeImageDescriptorAvailable() const { return desc_available; }
+  // test-harness fields
+  bool is_keyframe = true;
+  int n_tracked = 100;
+  std::vector<uint8_t> left_image;  // rows*cols*chnls, what ImageDataManager::getImage("left_image") returns
+
+ private:
+  Time stamp;
+  std::mutex m;
+  std::vector<double> desc;
+  std::atomic<bool> desc_available{false};
+};
+
+class DataManager {  // src/DataManager.h:96-117: only getDataMapRef is used by the path
+ public:
+  std::map<Time, DataNode*>* getDataMapRef() { return &data_map; }
+  ~DataManager() {
+    for (auto& kv : data_map) delete kv.second;
+  }
+  std::map<Time, DataNode*> data_map;
+};
+
+class StaticTheiaPoseCompute {  // src/DlsPnpWithRansac.h:169-179
+ public:
+  // w_X: n x 3, c_uv_normalized: n x 2 (row-major doubles); c_T_w: 16 doubles row-major 4x4.
+  // Returns summary.confidence, or -1 when fewer than 20 points are supplied (DlsPnpWithRansac.cpp:136-139).
+  static float PNP(cb_pnp* solver, const std::vector<double>& w_X, const std::vector<double>& c_uv_normalized,
+                   double* c_T_w, std::string& pnp__msg, uint64_t seed = 0) {
+    const int n = (int)(w_X.size() / 3);
+    if (n < 20) return -1.f;
+    pnp__msg = "";
+    cb_ransac_params prm;
+    cb_ransac_params_default(&prm);  // error_thresh 0.03, min_inlier_ratio 0.7, 50/5 iterations, MLE (:207-212)
+    prm.seed = seed;
+    int32_t off[2] = {0, n};
+    float conf = -1.f;
+    int32_t nit = 0, ninl = 0, bh = -1;
+    const int rc = cb_pnp_solve_batch(solver, 1, off, w_X.data(), c_uv_normalized.data(), &prm, nullptr, c_T_w, &conf,
+                                      &nit, &ninl, &bh);
+    if (rc != CB_OK) {
+      pnp__msg = std::string("cb_pnp_solve_batch failed: ") + cb_last_error();
+      return -1.f;
+    }
+    std::ostringstream ss;
+    ss << "DlsPnpWithRansac (best_rel_pose.b_T_a): num_iterations=" << nit << "  confidence=" << conf << ";";
+    pnp__msg += ss.str();
+    return conf;
+  }
+};
+
+class Cerebro {
+ public:
+  // constants of descrip_N__dot__descrip_0_N (src/Cerebro.cpp:912-914)
+  static constexpr int LOCALITY_THRESH = 12;
+  static constexpr float DOT_PROD_THRESH = 0.85f;
+  static constexpr int start_adding_descriptors_to_index_after = 50;
+
+  Cerebro(cb_descriptor* desc, int rows, int cols, int chnls, int64_t capacity = 29000 /* Cerebro.cpp:946 */, int device = 0)
+      : desc_(desc), rows_(rows), cols_(cols), chnls_(chnls) {
+    descriptor_size = cb_descriptor_dim(desc_);  // learnt by the probe call in the reference (:113-120)
+    descriptor_size_available = descriptor_size > 0;
+    ok_ = cb_index_create(&index_, descriptor_size, capacity, device, 0, 1) == CB_OK &&
+          cb_pnp_create(&pnp_, 16, 16 * 5000, 50, device) == CB_OK;
+  }
+  ~Cerebro() {
+    cb_index_destroy(index_);
+    cb_pnp_destroy(pnp_);
+  }
+  bool ok() const { return ok_; }
+  void setDataManager(DataManager* dm) {
+    dataManager = dm;
+    m_dataManager_available = true;
+  }
+
+  // ---- wholeImageComputedList (src/Cerebro.h:101-106, Cerebro.cpp:305-330)
+  int wholeImageComputedList_size() {
+    std::lock_guard<std::mutex> lk(m_wholeImageComputedList);
+    return (int)wholeImageComputedList.size();
+  }
+  Time wholeImageComputedList_at(int k) {
+    std::lock_guard<std::mutex> lk(m_wholeImageComputedList);
+    return wholeImageComputedList.at(k);
+  }
+
+  // ---- foundLoops (src/Cerebro.h:152-158, Cerebro.cpp:1113-1124)
+  int foundLoops_count() {
+    std::lock_guard<std::mutex> lk(m_foundLoops);
+    return (int)foundLoops.size();
+  }
+  std::tuple<Time, Time, double> foundLoops_i(int i) {
+    std::lock_guard<std::mutex> lk(m_foundLoops);
+    return foundLoops.at(i);
+  }
+  std::string foundLoops_as_JSON() {
+    std::lock_guard<std::mutex> lk(m_foundLoops);
+    std::ostringstream ss;
+    ss << "[";
+    for (size_t i = 0; i < foundLoops.size(); ++i) {
+      ss << (i ? "," : "") << "{\"time_sec_a\":" << std::get<0>(foundLoops[i]).toSec()
+         << ",\"time_sec_b\":" << std::get<1>(foundLoops[i]).toSec() << ",\"dotprodt\":" << std::get<2>(foundLoops[i]) << "}";
+    }
+    ss << "]";
+    return ss.str();
+  }
+  int processedLoops_count() const { return (int)processed_.size(); }
+
+  // ---- one pass of descriptor_computer_thread's loop body (src/Cerebro.cpp:169-298)
+  // Every keyframe without a descriptor and newer than the last processed stamp is sent through the
+  // descriptor handle (the reference does one blocking service call per keyframe, :263).
+  int descriptor_computer_step() {
+    if (!m_dataManager_available) return -1;
+    auto* data_map = dataManager->getDataMapRef();
+    int done = 0;
+    std::vector<float> out(descriptor_size);
+    for (auto& kv : *data_map) {
+      DataNode* node = kv.second;
+      if (!node->isKeyFrame() || node->isWholeImageDescriptorAvailable()) continue;  // :189
+      if (last_processed_set_ && !(last_processed_ < kv.first)) continue;
+      if (node->getNumberOfSuccessfullyTrackedFeatures() < 20) continue;  // :206-210
+      if ((int)node->left_image.size() != rows_ * cols_ * chnls_) continue;
+      const int rc = cb_descriptor_compute(desc_, 1, node->left_image.data(), 0, out.data());  // replaces client.call(srv), :263
+      if (rc != CB_OK) {
+        std::fprintf(stderr, "[descriptor_computer_thread] %s\n", cb_last_error());  // ROS_ERROR and continue, :288-290
+        continue;
+      }
+      std::vector<double> vec(out.begin(), out.end());  // float64[] desc -> VectorXd, :268-271
+      node->setWholeImageDescriptor(vec);               // :274
+      {
+        std::lock_guard<std::mutex> lk(m_wholeImageComputedList);
+        wholeImageComputedList.push_back(kv.first);  // :275
+      }
+      last_processed_ = kv.first;
+      last_processed_set_ = true;
+      ++done;
+    }
+    return done;
+  }
+
+  // ---- one wake-up of descrip_N__dot__descrip_0_N (src/Cerebro.cpp:956-1100)
+  bool run_step() {
+    auto* data_map = dataManager->getDataMapRef();
+    const int l = wholeImageComputedList_size();
+    if (l - last_l_ < 3) return false;  // :962
+    for (int s = last_l_; s < l; ++s) {  // "Fill descriptors [last_l, l) into M" :1005-1012 -> device DB
+      std::vector<double> v = data_map->at(wholeImageComputedList_at(s))->getWholeImageDescriptor();
+      if (cb_index_add_f64(index_, 1, v.data()) != CB_OK) return false;
+    }
+    int found = 0;
+    int64_t prev = -1, am[3];
+    double score = 0;
+    const int rc = cb_index_naive_candidate(index_, l, start_adding_descriptors_to_index_after, LOCALITY_THRESH,
+                                            DOT_PROD_THRESH, &found, &prev, &score, am);  // :1019-1056
+    last_l_ = l;
+    if (rc != CB_OK || !found) return false;
+    std::lock_guard<std::mutex> lk(m_foundLoops);
+    foundLoops.push_back(std::make_tuple(wholeImageComputedList_at(l - 1), wholeImageComputedList_at((int)prev), score));  // :1078-1081
+    return true;
+  }
+
+  // ---- the PnP part of process_loop_candidate_imagepair_consistent_pose_compute (src/Cerebro.cpp:1518)
+  float verify(const std::vector<double>& w_X, const std::vector<double>& uv, double* b_T_a, std::string& msg) {
+    const float g = StaticTheiaPoseCompute::PNP(pnp_, w_X, uv, b_T_a, msg);
+    processed_.push_back(g);
+    return g;
+  }
+
+  int descriptor_size = -1;
+  bool descriptor_size_available = false;
+
+ private:
+  cb_descriptor* desc_ = nullptr;
+  cb_index* index_ = nullptr;
+  cb_pnp* pnp_ = nullptr;
+  int rows_, cols_, chnls_;
+  bool ok_ = false;
+  DataManager* dataManager = nullptr;
+  std::atomic<bool> m_dataManager_available{false};
+  std::mutex m_wholeImageComputedList, m_foundLoops;
+  std::vector<Time> wholeImageComputedList;
+  std::vector<std::tuple<Time, Time, double>> foundLoops;
+  std::vector<float> processed_;
+  Time last_processed_;
+  bool last_processed_set_ = false;
+  int last_l_ = 0;
+};
+
+}  // namespace cerebro_b200

@@ -102,7 +102,7 @@ class IndexFlatIP:
         if n == 0:
             return D, I
         acc = np.float64 if accumulate == "float64" else np.float32
-        s = xq.astype(acc) @ self.x[:n].astype(acc).T
+        s = xq.astype(acc, copy=False) @ self.x[:n].astype(acc, copy=False).T
         kk = min(k, n)
         for q in range(xq.shape[0]):
             order = np.argsort(-s[q], kind="stable")[:kk]

@@ -1,0 +1,58 @@
+"""The C++ Cerebro shim (cerebro_b200/host) driven by the ROS-free harness, end to end on the GPU:
+keyframes -> descriptor_computer_step -> run_step (descrip_N__dot__descrip_0_N) -> foundLoops, plus one
+StaticTheiaPoseCompute::PNP call; compared with the CPU oracle on the same images and correspondences."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import golden_io, synth
+
+
+def test_harness_binary_links_on_cpu(native_lib):
+    from cerebro_b200 import build
+
+    assert os.path.exists(build.HARNESS)
+    r = subprocess.run([build.HARNESS], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_shim_stream_matches_oracle(native_lib, cuda_device, tmp_path):
+    from cerebro_b200 import build, keras_weights
+    from oracle import dls_pnp as D
+    from oracle import netvlad as NV
+    from oracle.search import naive_stream
+
+    raw = golden_io.raw_weights("gray_conv6")
+    wpath = str(tmp_path / "gray.cbw")
+    keras_weights.save_cbw(wpath, keras_weights.fold_mobilenet_netvlad(raw))
+    rows, cols, n = 96, 128, 90
+    places = synth.band_limited_images(60, rows, cols, 1, seed=50)
+    rng = np.random.default_rng(51)
+    imgs = np.empty((n, rows, cols, 1), dtype=np.uint8)
+    imgs[:60] = places
+    for i in range(30):  # frames 60..89 revisit places 5..34 with sensor noise
+        imgs[60 + i] = np.clip(places[5 + i].astype(np.int16) + rng.integers(-6, 7, places[0].shape), 0, 255).astype(np.uint8)
+    ipath = str(tmp_path / "images.raw")
+    imgs.tofile(ipath)
+    X, uv, T, _ = D.synth_candidate(np.random.default_rng(52), n=180, outlier_frac=0.1)
+    ppath = str(tmp_path / "pnp.raw")
+    with open(ppath, "wb") as f:
+        f.write(np.ascontiguousarray(X).tobytes())
+        f.write(np.ascontiguousarray(uv).tobytes())
+    r = subprocess.run([build.HARNESS, wpath, ipath, str(n), str(rows), str(cols), "1", ppath, "180"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["descriptor_size"] == 4096 and out["n_computed"] == n
+    desc = NV.describe(imgs, raw, dtype="float32").astype(np.float64)
+    expected = naive_stream(desc, list(range(3, n + 1, 3)))
+    assert len(expected) >= 5
+    assert [(a, b) for a, b, _ in out["found"]] == [(a, b) for a, b, _ in expected]
+    assert np.allclose([s for *_, s in out["found"]], [s for *_, s in expected], atol=5e-3)
+    o = D.ransac_pnp(X, uv, D.sample_table(0, 0, 50, 180))
+    assert abs(out["pnp"]["confidence"] - o["confidence"]) < 1e-6
+    e = D.pose_error(np.array(out["pnp"]["T"]).reshape(4, 4), o["T"])
+    assert e[0] < 1e-3 and e[1] < 1e-2
