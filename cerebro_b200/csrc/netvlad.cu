@@ -116,105 +116,157 @@ __device__ __forceinline__ float relu6(float x) { return fminf(fmaxf(x, 0.f), 6.
 
 // ---------------------------------------------------------------------------------------------
 // stem: u8 -> normalise -> 3x3 stride-2 conv (pad bottom/right) -> ReLU6 -> fp16 NHWC
-// thread = (output pixel, group of 8 output channels)
+// thread = (4 consecutive output pixels along x, group of 8 output channels): the 3 x 9 input patch is
+// converted once and every weight vector fetched from shared memory is reused for the 4 pixels.
 // ---------------------------------------------------------------------------------------------
+constexpr int kPX = 4;
+
 template <int CIN>
 __global__ void __launch_bounds__(256) conv1_kernel(const uint8_t* __restrict__ img, int n, int H, int W, int Ho, int Wo,
                                                    const float* __restrict__ w /*[3][3][CIN][32]*/,
                                                    const float* __restrict__ b, __half* __restrict__ out) {
-  __shared__ float sw[9 * CIN * 32];
+  __shared__ __align__(16) float sw[9 * CIN * 32];
   __shared__ float sb[32];
   for (int i = threadIdx.x; i < 9 * CIN * 32; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 32) sb[threadIdx.x] = b[threadIdx.x];
   __syncthreads();
+  const int Wg = (Wo + kPX - 1) / kPX;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)n * Ho * Wo * 4;
+  const long long total = (long long)n * Ho * Wg * 4;
   if (t >= total) return;
   const int cg = (int)(t & 3);
   long long p = t >> 2;
-  const int x = (int)(p % Wo);
-  p /= Wo;
+  const int xg = (int)(p % Wg);
+  p /= Wg;
   const int y = (int)(p % Ho);
   const int f = (int)(p / Ho);
-  float acc[8];
+  const int x0 = xg * kPX;
+  float acc[kPX][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = sb[cg * 8 + j];
+  for (int q = 0; q < kPX; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[q][j] = sb[cg * 8 + j];
   const uint8_t* base = img + (size_t)f * H * W * CIN;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = 2 * y + ky;
-    if (iy >= H) continue;
+    if (iy >= H) continue;  // ZeroPadding2D((0,1),(0,1)): the pad row contributes 0 AFTER normalisation
+    float v[2 * kPX + 1][CIN];
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = 2 * x + kx;
-      if (ix >= W) continue;
+    for (int cx = 0; cx < 2 * kPX + 1; ++cx) {
+      const int ix = 2 * x0 + cx;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci)
+        v[cx][ci] = ix < W ? ((float)base[((size_t)iy * W + ix) * CIN + ci] - 128.f) * 2.0f / 255.f : 0.f;  // server.py:629
+    }
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
-        const float v = ((float)base[((size_t)iy * W + ix) * CIN + ci] - 128.f) * 2.0f / 255.f;  // server.py:629
-        const float* wp = sw + ((ky * 3 + kx) * CIN + ci) * 32 + cg * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * CIN + ci) * 32 + cg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * CIN + ci) * 32 + cg * 8 + 4);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
+        for (int q = 0; q < kPX; ++q) {
+          const float xv = v[2 * q + kx][ci];
+          acc[q][0] = fmaf(xv, w0.x, acc[q][0]);
+          acc[q][1] = fmaf(xv, w0.y, acc[q][1]);
+          acc[q][2] = fmaf(xv, w0.z, acc[q][2]);
+          acc[q][3] = fmaf(xv, w0.w, acc[q][3]);
+          acc[q][4] = fmaf(xv, w1.x, acc[q][4]);
+          acc[q][5] = fmaf(xv, w1.y, acc[q][5]);
+          acc[q][6] = fmaf(xv, w1.z, acc[q][6]);
+          acc[q][7] = fmaf(xv, w1.w, acc[q][7]);
+        }
       }
-    }
   }
-  __half2 h[4];
+  __half* orow = out + (((size_t)f * Ho + y) * Wo + x0) * 32 + cg * 8;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(relu6(acc[2 * j]), relu6(acc[2 * j + 1]));
-  *reinterpret_cast<uint4*>(out + (size_t)(t >> 2) * 32 + cg * 8) = *reinterpret_cast<uint4*>(h);
+  for (int q = 0; q < kPX; ++q) {
+    if (x0 + q >= Wo) break;
+    __half2 h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(relu6(acc[q][2 * j]), relu6(acc[q][2 * j + 1]));
+    *reinterpret_cast<uint4*>(orow + (size_t)q * 32) = *reinterpret_cast<uint4*>(h);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
-// depthwise 3x3: thread = (output pixel, 8 channels)
+// depthwise 3x3: thread = (4 consecutive output pixels along x, 8 channels); the 72 weights live in
+// registers, input columns are shared between neighbouring outputs.
 // ---------------------------------------------------------------------------------------------
 template <int S>
 __global__ void __launch_bounds__(256) dw_kernel(const __half* __restrict__ in, int n, int H, int W, int C, int Ho, int Wo,
                                                 const float* __restrict__ w /*[3][3][C]*/, const float* __restrict__ b,
                                                 __half* __restrict__ out) {
   const int cgs = C >> 3;
+  const int Wg = (Wo + kPX - 1) / kPX;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)n * Ho * Wo * cgs;
+  const long long total = (long long)n * Ho * Wg * cgs;
   if (t >= total) return;
   const int cg = (int)(t % cgs);
   long long p = t / cgs;
-  const int x = (int)(p % Wo);
-  p /= Wo;
+  const int xg = (int)(p % Wg);
+  p /= Wg;
   const int y = (int)(p % Ho);
   const int f = (int)(p / Ho);
+  const int x0 = xg * kPX;
   constexpr int P = (S == 1) ? 1 : 0;  // 'same' for stride 1; ZeroPadding2D((0,1),(0,1)) + 'valid' for stride 2
-  float acc[8];
+  constexpr int NC = (kPX - 1) * S + 3;  // input columns feeding kPX outputs
+  float acc[kPX][8];
   {
-    const float4 b0 = *reinterpret_cast<const float4*>(b + cg * 8), b1 = *reinterpret_cast<const float4*>(b + cg * 8 + 4);
-    acc[0] = b0.x, acc[1] = b0.y, acc[2] = b0.z, acc[3] = b0.w, acc[4] = b1.x, acc[5] = b1.y, acc[6] = b1.z, acc[7] = b1.w;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + cg * 8)), b1 = __ldg(reinterpret_cast<const float4*>(b + cg * 8 + 4));
+#pragma unroll
+    for (int q = 0; q < kPX; ++q) {
+      acc[q][0] = b0.x, acc[q][1] = b0.y, acc[q][2] = b0.z, acc[q][3] = b0.w;
+      acc[q][4] = b1.x, acc[q][5] = b1.y, acc[q][6] = b1.z, acc[q][7] = b1.w;
+    }
   }
   const __half* base = in + (size_t)f * H * W * C + cg * 8;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = y * S + ky - P;
     if (iy < 0 || iy >= H) continue;
+    float wk[3][8];
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
-      const int ix = x * S + kx - P;
-      if (ix < 0 || ix >= W) continue;
-      const uint4 raw = *reinterpret_cast<const uint4*>(base + ((size_t)iy * W + ix) * C);
-      const __half2* hv = reinterpret_cast<const __half2*>(&raw);
       const float* wp = w + (ky * 3 + kx) * C + cg * 8;
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
-      const float2 v0 = __half22float2(hv[0]), v1 = __half22float2(hv[1]), v2 = __half22float2(hv[2]),
-                   v3 = __half22float2(hv[3]);
-      acc[0] = fmaf(v0.x, w0.x, acc[0]);
-      acc[1] = fmaf(v0.y, w0.y, acc[1]);
-      acc[2] = fmaf(v1.x, w0.z, acc[2]);
-      acc[3] = fmaf(v1.y, w0.w, acc[3]);
-      acc[4] = fmaf(v2.x, w1.x, acc[4]);
-      acc[5] = fmaf(v2.y, w1.y, acc[5]);
-      acc[6] = fmaf(v3.x, w1.z, acc[6]);
-      acc[7] = fmaf(v3.y, w1.w, acc[7]);
+      wk[kx][0] = w0.x, wk[kx][1] = w0.y, wk[kx][2] = w0.z, wk[kx][3] = w0.w;
+      wk[kx][4] = w1.x, wk[kx][5] = w1.y, wk[kx][6] = w1.z, wk[kx][7] = w1.w;
+    }
+    const __half* rowp = base + (size_t)iy * W * C;
+#pragma unroll
+    for (int cx = 0; cx < NC; ++cx) {
+      const int ix = x0 * S + cx - P;
+      if (ix < 0 || ix >= W) continue;
+      const uint4 raw = *reinterpret_cast<const uint4*>(rowp + (size_t)ix * C);
+      const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+      float xv[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f2 = __half22float2(hv[j]);
+        xv[2 * j] = f2.x;
+        xv[2 * j + 1] = f2.y;
+      }
+#pragma unroll
+      for (int q = 0; q < kPX; ++q) {
+        const int kx = cx - q * S;  // compile-time after unrolling
+        if (kx >= 0 && kx < 3) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(xv[j], wk[kx][j], acc[q][j]);
+        }
+      }
     }
   }
-  __half2 h[4];
+  __half* orow = out + (((size_t)f * Ho + y) * Wo + x0) * C + cg * 8;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(relu6(acc[2 * j]), relu6(acc[2 * j + 1]));
-  *reinterpret_cast<uint4*>(out + (size_t)(t / cgs) * C + cg * 8) = *reinterpret_cast<uint4*>(h);
+  for (int q = 0; q < kPX; ++q) {
+    if (x0 + q >= Wo) break;
+    __half2 h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(relu6(acc[q][2 * j]), relu6(acc[q][2 * j + 1]));
+    *reinterpret_cast<uint4*>(orow + (size_t)q * C) = *reinterpret_cast<uint4*>(h);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -597,7 +649,7 @@ int run_pw(cb_descriptor* d, const Block& b, long long M, const __half* in, __ha
 int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cudaStream_t st) {
   int cur = 0;
   {
-    const long long threads = (long long)n * d->H1 * d->W1 * 4;
+    const long long threads = (long long)n * d->H1 * ((d->W1 + kPX - 1) / kPX) * 4;
     const unsigned grid = (unsigned)((threads + 255) / 256);
     if (d->chnls == 1)
       conv1_kernel<1><<<grid, 256, 0, st>>>(img_dev, n, d->rows, d->cols, d->H1, d->W1, d->conv1_w, d->conv1_b, d->act[cur]);
@@ -608,7 +660,7 @@ int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cud
   int layer = 0;
   if (d->stop_layer == layer) return CB_OK;
   for (const Block& b : d->blocks) {
-    const long long threads = (long long)n * b.Ho * b.Wo * (b.C / 8);
+    const long long threads = (long long)n * b.Ho * ((b.Wo + kPX - 1) / kPX) * (b.C / 8);
     const unsigned grid = (unsigned)((threads + 255) / 256);
     if (b.stride == 1)
       dw_kernel<1><<<grid, 256, 0, st>>>(d->act[cur], n, b.Hin, b.Win, b.C, b.Ho, b.Wo, b.dw_w, b.dw_b, d->act[cur ^ 1]);

@@ -32,7 +32,6 @@ using cb::FULL;
 
 constexpr int kSample = 15;       // DlsPnpWithRansac::SampleSize (DlsPnpWithRansac.h:45)
 constexpr int kN = 27;            // quotient ring dimension / action matrix size
-constexpr int kAugStride = 65;    // odd stride (doubles) of the augmented [D | R] work matrix
 constexpr int kMaxSol = 27;
 
 // ---------------------------------------------------------------------------------------------
@@ -213,124 +212,212 @@ __global__ void __launch_bounds__(128) dls_setup_kernel(SetupArgs a) {
   double* To = a.T_out + (size_t)t * 27;
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 9; ++j) To[i * 9 + j] = T[i][j];
-  a.status[t] = isfinite(coef[0]) ? 0 : -1;
+  bool fin = true;
+  for (int i = 0; i < 60; ++i) fin = fin && isfinite(coef[i]);
+  a.status[t] = fin ? 0 : -1;
 }
 
 // ---------------------------------------------------------------------------------------------
-// stage 2: block-triangular elimination (warp per hypothesis, one warp per CTA)
+// stage 2: block-triangular elimination (one CTA of 4 warps per hypothesis)
 // ---------------------------------------------------------------------------------------------
-// shared memory per warp: N[93][27] | AUG[36][65] | coef[60]
-constexpr int kElimSmemDoubles = 93 * 27 + 36 * kAugStride + 60;
+// shared memory per CTA: N[60][27] (normal forms of degrees 3..6 + the 3 border monomials of degree 7)
+//                        | AUG[36][55] (work matrix) | coef[60] | part[4][3][27] | perm[36]
+// Blocks of degree 3..6: Gauss-Jordan on [D | R] (n x (n+27)).  Block of degree 7: only three rows of
+// D^-1 R are ever needed (the border monomials s_k*(2,2,2)), so solve D^T Y = E_J (36 x 3 right-hand
+// sides) and contract Y with R row by row without storing R.
+// Pivoting: partial, WITHOUT physical row swaps (a `used` mask + permutation), pivot-row scaling is
+// deferred to the read-out; every warp owns the rows i == warp (mod 4); one __syncthreads per pivot.
+constexpr int kElimWarps = 4;
+constexpr int kElimThreads = 32 * kElimWarps;
+constexpr int kAug = 55;  // odd stride (doubles) >= 27 + 27
+constexpr int kNRows = 60;
+constexpr int kElimSmemBytes = (kNRows * kN + 36 * kAug + 60 + kElimWarps * 3 * kN) * 8 + 36 * 4;
 
-__global__ void __launch_bounds__(32) dls_eliminate_kernel(const double* __restrict__ coef_in,
-                                                          const int* __restrict__ status, int count,
-                                                          double* __restrict__ S_out) {
-  extern __shared__ double sm[];
-  double* N = sm;                      // [93][27]
-  double* AUG = N + 93 * 27;           // [36][65]
-  double* coef = AUG + 36 * kAugStride;  // [60]
-  const int t = blockIdx.x;
-  const int lane = threadIdx.x;
-  if (t >= count || status[t] != 0) return;
-  for (int i = lane; i < 60; i += 32) coef[i] = coef_in[(size_t)t * 60 + i];
-  __syncwarp();
+// Build one row of the (reduced | same-degree | lower-degree) split of f_i * x^mult.
+//   direct scatter : reduced monomial cd -> dst_r[cd] -= c ; same-degree non-reduced -> (*put_d)(col, c)
+//   lower degree   : dst_r[0..26] -= c * N[cd-27][.]
+// Lanes 0..19 own the 20 terms; lanes 0..26 own the 27 right-hand-side columns.  Returns this lane's
+// right-hand-side accumulator (lower-degree part only); the direct terms are scattered by the caller.
+__device__ __forceinline__ double row_lower_part(const double* __restrict__ N, double c, int cd, int o0, int lane) {
+  const bool lower = lane < 20 && cd >= kN && (cd - kN) < o0;
+  unsigned m = __ballot_sync(FULL, lower);
+  double acc = 0.0;
+  while (m) {
+    const int b = __ffs(m) - 1;
+    m &= m - 1;
+    const double cc = __shfl_sync(FULL, c, b);
+    const int beta = __shfl_sync(FULL, cd, b) - kN;
+    if (lane < kN) acc = fma(-cc, N[beta * kN + lane], acc);
+  }
+  return acc;
+}
 
-  for (int blk = 0; blk < dls::kNumBlocks; ++blk) {
-    const int o0 = dls::kBlockOff[blk], n = dls::kBlockOff[blk + 1] - o0;
-    const int ncol = n + kN;  // augmented columns [D (n) | R (27)]
-    // ---- build the augmented rows: lane owns columns lane and lane+32
-    for (int r = 0; r < n; ++r) {
-      const int row = o0 + r;
-      const int pi = dls::kRowPoly[row];
-      double a0 = 0.0, a1 = 0.0;
-      const int c0 = lane, c1 = lane + 32;
-      for (int mu = 0; mu < 20; ++mu) {
-        const double c = coef[pi * 20 + mu];
-        const int cd = dls::kRowTerms[row][mu];
-        if (cd < kN) {  // reduced monomial -> right-hand side
-          if (c0 == n + cd) a0 -= c;
-          if (c1 == n + cd) a1 -= c;
-        } else if (cd - kN >= o0) {  // same-degree non-reduced -> D
-          const int col = cd - kN - o0;
-          if (c0 == col) a0 += c;
-          if (c1 == col) a1 += c;
-        } else {  // lower-degree non-reduced: substitute its normal form
-          const double* Nr = N + (cd - kN) * kN;
-          if (c0 >= n && c0 < ncol) a0 -= c * Nr[c0 - n];
-          if (c1 >= n && c1 < ncol) a1 -= c * Nr[c1 - n];
-        }
-      }
-      AUG[r * kAugStride + c0] = a0;
-      if (c1 < ncol) AUG[r * kAugStride + c1] = a1;
-    }
-    __syncwarp();
-    // ---- Gauss-Jordan with partial pivoting
-    for (int k = 0; k < n; ++k) {
-      double best = -1.0;
-      int bi = k;
-      for (int i = k + lane; i < n; i += 32) {
-        const double v = fabs(AUG[i * kAugStride + k]);
+// Gauss-Jordan elimination of the first n columns of AUG (n rows, ncol columns), partial pivoting by
+// permutation.  On return row perm[k] holds unknown k, still scaled by its pivot AUG[perm[k]][k].
+__device__ __forceinline__ void block_gauss_jordan(double* AUG, int* perm, int n, int ncol, int warp, int lane) {
+  unsigned long long used = 0ull;  // identical in every thread (deterministic arg-max)
+  for (int k = 0; k < n; ++k) {
+    // arg-max |AUG[i][k]| over unused rows (every warp computes it redundantly: no barrier needed)
+    double best = -1.0;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < n; i += 32) {
+      if (!((used >> i) & 1ull)) {
+        const double v = fabs(AUG[i * kAug + k]);
         if (v > best) {
           best = v;
           bi = i;
         }
       }
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
-        const double ob = __shfl_xor_sync(FULL, best, off);
-        const int oi = __shfl_xor_sync(FULL, bi, off);
-        if (ob > best || (ob == best && oi < bi)) {
-          best = ob;
-          bi = oi;
-        }
-      }
-      // columns still live: k .. ncol-1 ; lane owns k+lane and k+lane+32
-      const int ca = k + lane, cb_ = k + lane + 32;
-      const bool va = ca < ncol, vb = cb_ < ncol;
-      double pa = 0.0, pb = 0.0;
-      if (bi != k) {  // swap rows k <-> bi (uniform branch)
-        if (va) {
-          const double x = AUG[k * kAugStride + ca], y = AUG[bi * kAugStride + ca];
-          AUG[k * kAugStride + ca] = y;
-          AUG[bi * kAugStride + ca] = x;
-        }
-        if (vb) {
-          const double x = AUG[k * kAugStride + cb_], y = AUG[bi * kAugStride + cb_];
-          AUG[k * kAugStride + cb_] = y;
-          AUG[bi * kAugStride + cb_] = x;
-        }
-        __syncwarp();
-      }
-      const double inv = 1.0 / AUG[k * kAugStride + k];
-      __syncwarp();
-      if (va) {
-        pa = AUG[k * kAugStride + ca] * inv;
-        AUG[k * kAugStride + ca] = pa;
-      }
-      if (vb) {
-        pb = AUG[k * kAugStride + cb_] * inv;
-        AUG[k * kAugStride + cb_] = pb;
-      }
-      // eliminate column k from every other row (lane 0's column ca == k ends up 0: skip it)
-      const bool ua = va && lane > 0;
-#pragma unroll 4
-      for (int i = 0; i < n; ++i) {
-        if (i == k) continue;
-        const double f = AUG[i * kAugStride + k];
-        if (ua) AUG[i * kAugStride + ca] = fma(-f, pa, AUG[i * kAugStride + ca]);
-        if (vb) AUG[i * kAugStride + cb_] = fma(-f, pb, AUG[i * kAugStride + cb_]);
-      }
-      __syncwarp();
     }
-    // ---- normal forms of this block: N[o0 + r][b] = R[r][b]
-    for (int r = 0; r < n; ++r)
-      if (lane < kN) N[(o0 + r) * kN + lane] = AUG[r * kAugStride + n + lane];
-    __syncwarp();
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const double ob = __shfl_xor_sync(FULL, best, off);
+      const int oi = __shfl_xor_sync(FULL, bi, off);
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    int p = bi;
+    if (p >= n) {  // only NaNs left in the column: take the first unused row (the solve is lost anyway)
+      p = 0;
+      while ((used >> p) & 1ull) ++p;
+    }
+    used |= 1ull << p;
+    if (warp == 0 && lane == 0) perm[k] = p;
+    const double inv = 1.0 / AUG[p * kAug + k];
+    // live columns k+1 .. ncol-1 ; lane owns two of them, pivot-row values stay in registers
+    const int ca = k + 1 + lane, cb_ = k + 33 + lane;
+    const bool va = ca < ncol, vb = cb_ < ncol;
+    const double pa = va ? AUG[p * kAug + ca] : 0.0;
+    const double pb = vb ? AUG[p * kAug + cb_] : 0.0;
+#pragma unroll 3
+    for (int i = warp; i < n; i += kElimWarps) {
+      if (i == p) continue;
+      const double f = AUG[i * kAug + k] * inv;
+      if (va) AUG[i * kAug + ca] = fma(-f, pa, AUG[i * kAug + ca]);
+      if (vb) AUG[i * kAug + cb_] = fma(-f, pb, AUG[i * kAug + cb_]);
+    }
+    __syncthreads();
   }
-  // ---- action matrix of f0: S[b][:] = sum_k F0[k] * (e_cd  or  N[cd-27][:])
+}
+
+__global__ void __launch_bounds__(kElimThreads) dls_eliminate_kernel(const double* __restrict__ coef_in,
+                                                                    const int* __restrict__ status, int count,
+                                                                    double* __restrict__ S_out) {
+  extern __shared__ double sm[];
+  double* N = sm;                       // [60][27]
+  double* AUG = N + kNRows * kN;        // [36][55]
+  double* coef = AUG + 36 * kAug;       // [60]
+  double* part = coef + 60;             // [4][3][27]
+  int* perm = reinterpret_cast<int*>(part + kElimWarps * 3 * kN);  // [36]
+  const int t = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (t >= count || status[t] != 0) return;  // CTA-uniform
+  if (tid < 60) coef[tid] = coef_in[(size_t)t * 60 + tid];
+  __syncthreads();
+
+  // ---------------- blocks of degree 3..6 ----------------
+  for (int blk = 0; blk < 4; ++blk) {
+    const int o0 = dls::kBlockOff[blk], n = dls::kBlockOff[blk + 1] - o0;
+    const int ncol = n + kN;
+    for (int r = warp; r < n; r += kElimWarps) {
+      const int row = o0 + r;
+      const int pi = dls::kRowPoly[row];
+      double* arow = AUG + r * kAug;
+      arow[lane] = 0.0;
+      if (lane + 32 < kAug) arow[lane + 32] = 0.0;
+      double c = 0.0;
+      int cd = 0;
+      if (lane < 20) {
+        c = coef[pi * 20 + lane];
+        cd = dls::kRowTerms[row][lane];
+      }
+      const double acc = row_lower_part(N, c, cd, o0, lane);
+      __syncwarp();
+      if (lane < 20) {
+        if (cd < kN) arow[n + cd] = -c;                       // reduced monomial -> right-hand side
+        else if (cd - kN >= o0) arow[cd - kN - o0] = c;       // same-degree non-reduced -> D
+      }
+      __syncwarp();
+      if (lane < kN) arow[n + lane] += acc;
+    }
+    __syncthreads();
+    block_gauss_jordan(AUG, perm, n, ncol, warp, lane);
+    // normal forms: N[o0 + k][b] = R[perm[k]][b] / pivot_k
+    for (int k = warp; k < n; k += kElimWarps) {
+      const int p = perm[k];
+      const double inv = 1.0 / AUG[p * kAug + k];
+      if (lane < kN) N[(o0 + k) * kN + lane] = AUG[p * kAug + n + lane] * inv;
+    }
+    __syncthreads();
+  }
+
+  // ---------------- degree 7: three rows of D^-1 R via D^T Y = E_J ----------------
+  {
+    const int o0 = dls::kBlockOff[4], n = 36, ncol = 39;
+    for (int i = tid; i < 36 * kAug; i += kElimThreads) AUG[i] = 0.0;
+    __syncthreads();
+    for (int r = warp; r < n; r += kElimWarps) {  // row r of D -> column r of AUG
+      const int row = o0 + r;
+      const int pi = dls::kRowPoly[row];
+      if (lane < 20) {
+        const int cd = dls::kRowTerms[row][lane];
+        if (cd >= kN && cd - kN >= o0) AUG[(cd - kN - o0) * kAug + r] = coef[pi * 20 + lane];
+      }
+    }
+    if (tid < 3) AUG[dls::kBorder7[tid] * kAug + 36 + tid] = 1.0;
+    __syncthreads();
+    block_gauss_jordan(AUG, perm, n, ncol, warp, lane);
+    // contract: N7[j][b] = sum_r Y[r][j] * R[r][b],  Y[r][j] = AUG[perm[r]][36+j] / AUG[perm[r]][r]
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int r = warp; r < n; r += kElimWarps) {
+      const int row = o0 + r;
+      const int pi = dls::kRowPoly[row];
+      double c = 0.0;
+      int cd = 0;
+      if (lane < 20) {
+        c = coef[pi * 20 + lane];
+        cd = dls::kRowTerms[row][lane];
+      }
+      double rr = row_lower_part(N, c, cd, o0, lane);
+      // reduced terms of this row: lane b picks up -c of the term whose code is b
+      const unsigned red = __ballot_sync(FULL, lane < 20 && cd < kN);
+      unsigned m = red;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const double cc = __shfl_sync(FULL, c, b);
+        const int code = __shfl_sync(FULL, cd, b);
+        if (lane == code) rr -= cc;
+      }
+      const int p = perm[r];
+      const double inv = 1.0 / AUG[p * kAug + r];
+      const double y0 = AUG[p * kAug + 36] * inv, y1 = AUG[p * kAug + 37] * inv, y2 = AUG[p * kAug + 38] * inv;
+      a0 = fma(y0, rr, a0);
+      a1 = fma(y1, rr, a1);
+      a2 = fma(y2, rr, a2);
+    }
+    if (lane < kN) {
+      part[(warp * 3 + 0) * kN + lane] = a0;
+      part[(warp * 3 + 1) * kN + lane] = a1;
+      part[(warp * 3 + 2) * kN + lane] = a2;
+    }
+    __syncthreads();
+    if (warp < 3 && lane < kN) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kElimWarps; ++w) v += part[(w * 3 + warp) * kN + lane];
+      N[(57 + warp) * kN + lane] = v;
+    }
+    __syncthreads();
+  }
+
+  // ---------------- action matrix of f0: S[b][:] = sum_k F0[k] * (e_cd  or  N[cd-27][:]) ----------------
   double* So = S_out + (size_t)t * kN * kN;
-  for (int b = 0; b < kN; ++b) {
+  for (int b = warp; b < kN; b += kElimWarps) {
     double v = 0.0;
+#pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int cd = dls::kF0Terms[b][k];
       if (cd < kN) {
@@ -347,7 +434,7 @@ __global__ void __launch_bounds__(32) dls_eliminate_kernel(const double* __restr
 // stage 3: eigenvalues + roots + cheirality (warp per hypothesis)
 // ---------------------------------------------------------------------------------------------
 constexpr int kRootsWarps = 4;
-constexpr int kRootsSmemPerWarp = 3 * kN * kN + 64;  // A | H | LU | wr/wi/v scratch (doubles)
+constexpr int kRootsSmemPerWarp = kN * kN + 64;  // one 27x27 work matrix (H, then LU) | wr/wi/v scratch (doubles)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -638,19 +725,15 @@ __global__ void __launch_bounds__(32 * kRootsWarps) dls_roots_kernel(RootsArgs a
   const int t = blockIdx.x * kRootsWarps + warp;
   if (t >= a.count) return;
   if (a.status[t] != 0) return;
-  double* A = sm + (size_t)warp * kRootsSmemPerWarp;
-  double* H = A + kN * kN;
-  double* LU = H + kN * kN;
-  double* wr = LU + kN * kN;  // [27] (+ wi [27] share the 64-double scratch: wr at 0, wi at 32)
+  double* H = sm + (size_t)warp * kRootsSmemPerWarp;  // Hessenberg/QR work matrix, reused for the LU
+  double* LU = H;
+  double* wr = H + kN * kN;  // [27] (+ wi [27] share the 64-double scratch: wr at 0, wi at 32)
   double* wi = wr + 32;
   const double* Sg = a.S + (size_t)t * kN * kN;
-  for (int i = lane; i < kN * kN; i += 32) {
-    const double v = Sg[i];
-    A[i] = v;
-    H[i] = v;
-  }
+  const double* A = Sg;  // the action matrix itself stays in global memory (L2-resident)
+  for (int i = lane; i < kN * kN; i += 32) H[i] = Sg[i];
   __syncwarp();
-  warp_hessenberg(H, LU /*scratch for v*/, lane);
+  warp_hessenberg(H, wr /*scratch for v*/, lane);
   const bool conv = warp_hqr(H, wr, wi, lane);
   __syncwarp();
   if (!conv) {
@@ -923,7 +1006,7 @@ namespace {
 int run_chunks(cb_pnp* p, int n_cand, const int* offsets_dev, const double* X, const double* uv, int H,
                const cb_ransac_params& prm, const int* samples_dev, cudaStream_t st) {
   const long long total = (long long)n_cand * H;
-  const size_t elim_smem = kElimSmemDoubles * sizeof(double);
+  const size_t elim_smem = kElimSmemBytes;
   const size_t roots_smem = (size_t)kRootsWarps * kRootsSmemPerWarp * sizeof(double);
   CB_CUDA(cudaFuncSetAttribute(dls_eliminate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)elim_smem));
   CB_CUDA(cudaFuncSetAttribute(dls_roots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)roots_smem));
@@ -944,7 +1027,7 @@ int run_chunks(cb_pnp* p, int n_cand, const int* offsets_dev, const double* X, c
     sa.status = p->status;
     dls_setup_kernel<<<(count + 127) / 128, 128, 0, st>>>(sa);
     CB_LAUNCH_CHECK();
-    dls_eliminate_kernel<<<count, 32, elim_smem, st>>>(p->coef, p->status, count, p->S);
+    dls_eliminate_kernel<<<count, kElimThreads, elim_smem, st>>>(p->coef, p->status, count, p->S);
     CB_LAUNCH_CHECK();
     RootsArgs ra;
     ra.S = p->S;
@@ -1141,7 +1224,7 @@ int cb_pnp_dls_minimal(cb_pnp* p, int n_sets, int m, const double* X, const doub
   delete[] h_off;
   delete[] h_samples;
   if (total < 20) return cb::fail(CB_EINVAL, "need at least 2 sets");
-  const size_t elim_smem = kElimSmemDoubles * sizeof(double);
+  const size_t elim_smem = kElimSmemBytes;
   const size_t roots_smem = (size_t)kRootsWarps * kRootsSmemPerWarp * sizeof(double);
   CB_CUDA(cudaFuncSetAttribute(dls_eliminate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)elim_smem));
   CB_CUDA(cudaFuncSetAttribute(dls_roots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)roots_smem));
@@ -1160,7 +1243,7 @@ int cb_pnp_dls_minimal(cb_pnp* p, int n_sets, int m, const double* X, const doub
   sa.status = p->status;
   dls_setup_kernel<<<(n_sets + 127) / 128, 128, 0, st>>>(sa);
   CB_LAUNCH_CHECK();
-  dls_eliminate_kernel<<<n_sets, 32, elim_smem, st>>>(p->coef, p->status, n_sets, p->S);
+  dls_eliminate_kernel<<<n_sets, kElimThreads, elim_smem, st>>>(p->coef, p->status, n_sets, p->S);
   CB_LAUNCH_CHECK();
   RootsArgs ra;
   ra.S = p->S;

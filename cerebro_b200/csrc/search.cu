@@ -30,7 +30,7 @@ using cb::FULL;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kList = 32;          // candidates carried per list (one per lane)
-constexpr int kChunkRows = 8192;   // rows per top-k chunk CTA
+constexpr int kChunkRows = 2048;   // rows per top-k chunk CTA (8 rows per thread, loaded up front)
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 v;
@@ -235,13 +235,22 @@ topk_chunk_kernel(const float* __restrict__ partial, int n_slices, int qt_stride
   wl.init();
   const float* base = partial + (size_t)q * pstride;
   const size_t sstride = (size_t)qt_stride * pstride;
-  for (long long r = r_begin + tid; r < r_begin + kChunkRows; r += kThreads) {
-    const bool valid = r < r_end;
-    float v = 0.f;
-    if (valid) {
-      for (int s = 0; s < n_slices; ++s) v += base[s * sstride + r];
+  // all of this thread's rows are fetched before the (warp-collective, serialising) insertion loop
+  constexpr int kPer = kChunkRows / kThreads;
+  float v[kPer];
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const long long r = r_begin + tid + (long long)j * kThreads;
+    float a = 0.f;
+    if (r < r_end) {
+      for (int s = 0; s < n_slices; ++s) a += base[s * sstride + r];
     }
-    wl.offer(v, r * world + rank, valid, tie_high, lane);
+    v[j] = a;
+  }
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const long long r = r_begin + tid + (long long)j * kThreads;
+    wl.offer(v[j], r * world + rank, r < r_end, tie_high, lane);
   }
   ss[warp * kList + lane] = wl.s;
   sl[warp * kList + lane] = wl.id;
@@ -272,10 +281,17 @@ finalize_kernel(const float* __restrict__ cs, const long long* __restrict__ cl, 
     WarpList<float> wl;
     wl.init();
     const size_t o = (size_t)q * n_chunks * kList;
-    for (int i = 0; i < n_chunks; ++i) {
-      const float v = cs[o + i * kList + lane];
-      const long long id = cl[o + i * kList + lane];
-      wl.offer(v, id, id >= 0, tie_high, lane);
+    for (int i0 = 0; i0 < n_chunks; i0 += 8) {
+      float v[8];
+      long long id[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool in = i0 + j < n_chunks;
+        v[j] = in ? cs[o + (size_t)(i0 + j) * kList + lane] : 0.f;
+        id[j] = in ? cl[o + (size_t)(i0 + j) * kList + lane] : -1;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wl.offer(v[j], id[j], id[j] >= 0, tie_high, lane);
     }
     s_id[lane] = wl.id;
   }
@@ -288,12 +304,23 @@ finalize_kernel(const float* __restrict__ cs, const long long* __restrict__ cl, 
       const long long r = (id - rank) / world;
       const float4* pr = reinterpret_cast<const float4*>(rows + (size_t)r * d);
       const float4* pq = reinterpret_cast<const float4*>(xq + (size_t)q * d);
-      for (int c = lane; c < (d >> 2); c += 32) {
-        const float4 a = pr[c], b = pq[c];
-        acc += (double)a.x * (double)b.x;
-        acc += (double)a.y * (double)b.y;
-        acc += (double)a.z * (double)b.z;
-        acc += (double)a.w * (double)b.w;
+      const int nd4 = d >> 2;
+      for (int c0 = lane; c0 < nd4; c0 += 32 * 4) {  // 4 independent 16-byte loads per operand in flight
+        float4 a[4], b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + 32 * j;
+          const bool in = c < nd4;
+          a[j] = in ? pr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+          b[j] = in ? pq[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // same summation order as a plain lane-strided loop
+          acc += (double)a[j].x * (double)b[j].x;
+          acc += (double)a[j].y * (double)b[j].y;
+          acc += (double)a[j].z * (double)b[j].z;
+          acc += (double)a[j].w * (double)b[j].w;
+        }
       }
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
