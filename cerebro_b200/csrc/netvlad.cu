@@ -388,6 +388,245 @@ __global__ void __launch_bounds__(kGemmThreads) pw_gemm_kernel(const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused depthwise -> pointwise block.  One CTA = 128 output pixels x all COUT channels.
+//   warp 0    : TMA producer of the pointwise-weight (B) tiles, one 64-channel K block at a time
+//   warp 1    : TMEM allocator + tcgen05.mma issuer
+//   warps 2-5 : epilogue (TMEM -> +bias -> ReLU6 -> fp16 -> global)
+//   warps 6-13: depthwise producers: compute the 3x3 depthwise (+bias, ReLU6) for the tile straight from
+//               the previous layer's activation in global memory and write it, as fp16, into the
+//               128B/64B-swizzled K-major A tile in shared memory (the layout TMA would have produced);
+//               fence.proxy.async + mbarrier hand each K block to the MMA warp.
+// The depthwise output never touches HBM: per block the activation traffic drops from
+// (dw in + dw out + pw in + pw out) to (dw in + pw out).
+// ---------------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 448;
+constexpr int kProdThreads = 256;
+constexpr int kASlots = 2;
+constexpr int kBStages = 2;
+
+template <int CIN, int COUT>
+struct FusedSmem {
+  static constexpr int KB = CIN < 64 ? CIN : 64;  // channels per K block (32 only for the first block)
+  static constexpr int NKB = CIN / KB;
+  static constexpr int kABytes = 128 * KB * 2;
+  static constexpr int kBBytes = COUT * KB * 2;
+  static constexpr int kAS = NKB < kASlots ? NKB : kASlots;
+  static constexpr int kBS = NKB < kBStages ? NKB : kBStages;
+  static constexpr int kTotal = kAS * kABytes + kBS * kBBytes + 1024 /*align*/ + 128 /*barriers*/ + 1024 /*geometry*/;
+};
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int CIN, int COUT, int S>
+__global__ void __launch_bounds__(kFusedThreads, (COUT <= 256 ? 2 : 1)) dwpw_kernel(const __half* __restrict__ in, int n_frames, int H, int W, int Ho,
+                                                            int Wo, const float* __restrict__ dw_w /*[3][3][CIN]*/,
+                                                            const float* __restrict__ dw_b,
+                                                            const __grid_constant__ CUtensorMap tmB,
+                                                            const float* __restrict__ bias, __half* __restrict__ out,
+                                                            int M_total) {
+  using SM = FusedSmem<CIN, COUT>;
+  constexpr int KB = SM::KB, NKB = SM::NKB;
+  constexpr int SWZ = KB * 2;
+  constexpr int N_MMA = COUT > 256 ? 256 : COUT;  // columns per tcgen05.mma (two halves when COUT = 512)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + SM::kAS * SM::kABytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + SM::kBS * SM::kBBytes);
+  uint64_t* a_empty = a_full + kASlots;
+  uint64_t* b_full = a_empty + kASlots;
+  uint64_t* b_empty = b_full + kBStages;
+  uint64_t* tmem_full_bar = b_empty + kBStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  int2* geom = reinterpret_cast<int2*>(tmem_ptr + 2);  // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kASlots; ++s) {
+      mbar_init(&a_full[s], kProdThreads / 32);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, COUT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int s = kb % SM::kBS;
+        const uint32_t round = kb / SM::kBS;
+        mbar_wait(&b_empty[s], (round & 1) ^ 1);
+        mbar_expect_tx(&b_full[s], SM::kBBytes);
+        uint8_t* sb = smem_b + s * SM::kBBytes;
+        // the weight matrix is [COUT][CIN]; a TMA box holds at most 256 rows
+        tma_load_2d(&tmB, &b_full[s], sb, kb * KB, 0);
+        if (COUT > 256) tma_load_2d(&tmB, &b_full[s], sb + 256 * KB * 2, kb * KB, 256);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(N_MMA >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int sa = kb % SM::kAS, sb = kb % SM::kBS;
+        mbar_wait(&b_full[sb], (kb / SM::kBS) & 1);
+        mbar_wait(&a_full[sa], (kb / SM::kAS) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + sa * SM::kABytes);
+        const uint32_t b_addr = smem_u32(smem_b + sb * SM::kBBytes);
+#pragma unroll
+        for (int k = 0; k < KB / 16; ++k) {
+          const uint64_t ad = make_kmajor_desc<SWZ>(a_addr + k * 32);
+#pragma unroll
+          for (int h = 0; h < COUT / N_MMA; ++h) {
+            const uint64_t bd = make_kmajor_desc<SWZ>(b_addr + h * (256 * KB * 2) + k * 32);
+            umma_f16(tmem_base + h * 256, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          }
+        }
+        umma_commit(&a_empty[sa]);
+        umma_commit(&b_empty[sb]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else if (warp < 6) {
+    const int q = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < M_total;
+    __half* orow = out + (size_t)row * COUT;
+#pragma unroll 1
+    for (int c = 0; c < COUT; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c + j));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + j + 4));
+          __half2 h[4];
+          h[0] = __floats2half2_rn(relu6(__uint_as_float(v[j + 0]) + b0.x), relu6(__uint_as_float(v[j + 1]) + b0.y));
+          h[1] = __floats2half2_rn(relu6(__uint_as_float(v[j + 2]) + b0.z), relu6(__uint_as_float(v[j + 3]) + b0.w));
+          h[2] = __floats2half2_rn(relu6(__uint_as_float(v[j + 4]) + b1.x), relu6(__uint_as_float(v[j + 5]) + b1.y));
+          h[3] = __floats2half2_rn(relu6(__uint_as_float(v[j + 6]) + b1.z), relu6(__uint_as_float(v[j + 7]) + b1.w));
+          *reinterpret_cast<uint4*>(orow + c + j) = *reinterpret_cast<uint4*>(h);
+        }
+      }
+    }
+  } else {
+    // ---- depthwise producers: task = (pixel of the tile, group of 8 channels of the current K block)
+    const int pt = threadIdx.x - 192;        // 0..255
+    constexpr int CGB = KB / 8;              // channel groups per K block (8, or 4 for the 32-channel block)
+    constexpr int PIX_PER_PASS = kProdThreads / CGB;
+    constexpr int PASSES = 128 / PIX_PER_PASS;
+    constexpr int P = (S == 1) ? 1 : 0;
+    const int cgl = pt % CGB;
+    const int pl = pt / CGB;
+    // geometry of the tile's 128 pixels, computed once: {frame (or -1), (y << 16) | x}
+    if (pt < 128) {
+      const long long m = (long long)m0 + pt;
+      int2 g = make_int2(-1, 0);
+      if (m < M_total) {
+        const int x = (int)(m % Wo);
+        const long long t2 = m / Wo;
+        g.x = (int)(t2 / Ho);
+        g.y = ((int)(t2 % Ho) << 16) | x;
+      }
+      geom[pt] = g;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads) : "memory");
+    for (int kb = 0; kb < NKB; ++kb) {
+      const int sa = kb % SM::kAS;
+      mbar_wait(&a_empty[sa], ((kb / SM::kAS) & 1) ^ 1);
+      uint8_t* at = smem_a + sa * SM::kABytes;
+      const int ch0 = kb * KB + cgl * 8;
+      const float4 bb0 = __ldg(reinterpret_cast<const float4*>(dw_b + ch0));
+      const float4 bb1 = __ldg(reinterpret_cast<const float4*>(dw_b + ch0 + 4));
+#pragma unroll 1
+      for (int i0 = 0; i0 < PASSES; i0 += 2) {  // two pixels per round: their loads are independent
+        float acc[2][8];
+        int gy[2], gx[2];
+        const __half* gbase[2];
+        bool pok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int2 g = geom[(i0 + u) * PIX_PER_PASS + pl];
+          pok[u] = g.x >= 0;
+          gy[u] = g.y >> 16;
+          gx[u] = g.y & 0xffff;
+          gbase[u] = in + (size_t)(pok[u] ? g.x : 0) * H * W * CIN + ch0;
+          acc[u][0] = bb0.x, acc[u][1] = bb0.y, acc[u][2] = bb0.z, acc[u][3] = bb0.w;
+          acc[u][4] = bb1.x, acc[u][5] = bb1.y, acc[u][6] = bb1.z, acc[u][7] = bb1.w;
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(dw_w + (ky * 3 + kx) * CIN + ch0));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(dw_w + (ky * 3 + kx) * CIN + ch0 + 4));
+            uint4 raw[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int iy = gy[u] * S + ky - P, ix = gx[u] * S + kx - P;
+              const bool ok = pok[u] && iy >= 0 && iy < H && ix >= 0 && ix < W;
+              raw[u] = ok ? *reinterpret_cast<const uint4*>(gbase[u] + ((size_t)iy * W + ix) * CIN) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const __half2* hv = reinterpret_cast<const __half2*>(&raw[u]);
+              const float2 v0 = __half22float2(hv[0]), v1 = __half22float2(hv[1]), v2 = __half22float2(hv[2]),
+                           v3 = __half22float2(hv[3]);
+              acc[u][0] = fmaf(v0.x, w0.x, acc[u][0]);
+              acc[u][1] = fmaf(v0.y, w0.y, acc[u][1]);
+              acc[u][2] = fmaf(v1.x, w0.z, acc[u][2]);
+              acc[u][3] = fmaf(v1.y, w0.w, acc[u][3]);
+              acc[u][4] = fmaf(v2.x, w1.x, acc[u][4]);
+              acc[u][5] = fmaf(v2.y, w1.y, acc[u][5]);
+              acc[u][6] = fmaf(v3.x, w1.z, acc[u][6]);
+              acc[u][7] = fmaf(v3.y, w1.w, acc[u][7]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int r = (i0 + u) * PIX_PER_PASS + pl;
+          __half2 h[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            h[j] = pok[u] ? __floats2half2_rn(relu6(acc[u][2 * j]), relu6(acc[u][2 * j + 1])) : __floats2half2_rn(0.f, 0.f);
+          // K-major swizzled tile: row r, 16-byte chunk cgl -> chunk ^ (row bits), Swizzle<3,4,3> (128B) / <2,4,3> (64B)
+          const int chunk = (SWZ == 128) ? (cgl ^ (r & 7)) : (cgl ^ ((r >> 1) & 3));
+          *reinterpret_cast<uint4*>(at + r * SWZ + chunk * 16) = *reinterpret_cast<uint4*>(h);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[sa]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, COUT);
+  }
+}
+
 // CUDA-core version of the same contraction: thread = (pixel, 8 output channels)
 __global__ void __launch_bounds__(256) pw_simt_kernel(const __half* __restrict__ in, const __half* __restrict__ w /*[N][K]*/,
                                                      const float* __restrict__ bias, __half* __restrict__ out,
@@ -576,7 +815,9 @@ struct Block {
   float* pw_b = nullptr;
   bool use_tc = false;
   int n_tile = 0, kb = 0;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA[2], tmB;  // A map per ping-pong buffer (the GEMM input may live in either)
+  bool fused = false;  // depthwise folded into the tcgen05 GEMM producer
+  CUtensorMap tmBf;    // weight map with a <=256-row box for the fused kernel
 };
 
 }  // namespace
@@ -600,8 +841,9 @@ struct cb_descriptor {
   float* out_dev = nullptr;
   cudaStream_t stream = nullptr;
   bool force_simt = false;
+  bool no_fuse = false;  // CB_NO_FUSE=1: separate depthwise + GEMM kernels
   int stop_layer = -1;  // CB_DEBUG_STOP_LAYER: stop the forward pass after this layer (bring-up / parity tests)
-  std::vector<int> layer_buf;       // which act buffer holds layer l's output
+  int last_buf = 0;                 // ping-pong buffer holding the most recent layer output
   std::vector<size_t> layer_elems;  // per-frame elements of layer l's output
 };
 
@@ -614,29 +856,59 @@ int upload_f32(float** dst, const float* src, size_t n) {
 }
 
 template <int N_TILE, int KB>
-int launch_gemm(const Block& b, long long M, const __half* /*in*/, __half* out, cudaStream_t st) {
+int launch_gemm(const Block& b, long long M, int in_buf, __half* out, cudaStream_t st) {
   using SM = GemmSmem<N_TILE, KB>;
   auto kern = pw_gemm_kernel<N_TILE, KB>;
   CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
   dim3 grid((unsigned)((M + 127) / 128), (unsigned)(b.Cout / N_TILE));
-  kern<<<grid, kGemmThreads, SM::kTotal, st>>>(b.tmA, b.tmB, b.pw_b, out, (int)M, b.Cout, b.C);
+  kern<<<grid, kGemmThreads, SM::kTotal, st>>>(b.tmA[in_buf], b.tmB, b.pw_b, out, (int)M, b.Cout, b.C);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
 
-int run_pw(cb_descriptor* d, const Block& b, long long M, const __half* in, __half* out, cudaStream_t st) {
+bool fused_shape_supported(int cin, int cout, int stride) {
+  return (cin == 32 && cout == 64 && stride == 1) || (cin == 64 && cout == 128 && stride == 2) ||
+         (cin == 128 && cout == 128 && stride == 1) || (cin == 128 && cout == 256 && stride == 2) ||
+         (cin == 256 && cout == 256 && stride == 1) || (cin == 256 && cout == 512 && stride == 2) ||
+         (cin == 512 && cout == 512 && stride == 1);
+}
+
+template <int CIN, int COUT, int S>
+int launch_fused(const Block& b, int n, const __half* in, __half* out, cudaStream_t st) {
+  using SM = FusedSmem<CIN, COUT>;
+  auto kern = dwpw_kernel<CIN, COUT, S>;
+  CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+  const long long M = (long long)n * b.Ho * b.Wo;
+  kern<<<(unsigned)((M + 127) / 128), kFusedThreads, SM::kTotal, st>>>(in, n, b.Hin, b.Win, b.Ho, b.Wo, b.dw_w, b.dw_b, b.tmBf,
+                                                                     b.pw_b, out, (int)M);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+int run_fused(const Block& b, int n, const __half* in, __half* out, cudaStream_t st) {
+  if (b.C == 32) return launch_fused<32, 64, 1>(b, n, in, out, st);
+  if (b.C == 64) return launch_fused<64, 128, 2>(b, n, in, out, st);
+  if (b.C == 128 && b.Cout == 128) return launch_fused<128, 128, 1>(b, n, in, out, st);
+  if (b.C == 128) return launch_fused<128, 256, 2>(b, n, in, out, st);
+  if (b.C == 256 && b.Cout == 256) return launch_fused<256, 256, 1>(b, n, in, out, st);
+  if (b.C == 256) return launch_fused<256, 512, 2>(b, n, in, out, st);
+  return launch_fused<512, 512, 1>(b, n, in, out, st);
+}
+
+int run_pw(cb_descriptor* d, const Block& b, long long M, int in_buf, __half* out, cudaStream_t st) {
+  const __half* in = d->act[in_buf];
   if (b.use_tc && !d->force_simt) {
     if (b.kb == 64) {
       switch (b.n_tile) {
-        case 64: return launch_gemm<64, 64>(b, M, in, out, st);
-        case 128: return launch_gemm<128, 64>(b, M, in, out, st);
-        default: return launch_gemm<256, 64>(b, M, in, out, st);
+        case 64: return launch_gemm<64, 64>(b, M, in_buf, out, st);
+        case 128: return launch_gemm<128, 64>(b, M, in_buf, out, st);
+        default: return launch_gemm<256, 64>(b, M, in_buf, out, st);
       }
     } else {
       switch (b.n_tile) {
-        case 64: return launch_gemm<64, 32>(b, M, in, out, st);
-        case 128: return launch_gemm<128, 32>(b, M, in, out, st);
-        default: return launch_gemm<256, 32>(b, M, in, out, st);
+        case 64: return launch_gemm<64, 32>(b, M, in_buf, out, st);
+        case 128: return launch_gemm<128, 32>(b, M, in_buf, out, st);
+        default: return launch_gemm<256, 32>(b, M, in_buf, out, st);
       }
     }
   }
@@ -658,8 +930,20 @@ int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cud
     CB_LAUNCH_CHECK();
   }
   int layer = 0;
+  d->last_buf = cur;
   if (d->stop_layer == layer) return CB_OK;
   for (const Block& b : d->blocks) {
+    const int dw_layer = layer + 1, pw_layer = layer + 2;
+    if (b.has_pw && b.use_tc && b.fused && !d->no_fuse && !d->force_simt && d->stop_layer != dw_layer) {
+      // fused depthwise -> pointwise: one kernel, one ping-pong flip (the depthwise output never exists)
+      int rc = run_fused(b, n, d->act[cur], d->act[cur ^ 1], st);
+      if (rc) return rc;
+      cur ^= 1;
+      d->last_buf = cur;
+      layer = pw_layer;
+      if (d->stop_layer == layer) return CB_OK;
+      continue;
+    }
     const long long threads = (long long)n * b.Ho * ((b.Wo + kPX - 1) / kPX) * (b.C / 8);
     const unsigned grid = (unsigned)((threads + 255) / 256);
     if (b.stride == 1)
@@ -668,12 +952,14 @@ int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cud
       dw_kernel<2><<<grid, 256, 0, st>>>(d->act[cur], n, b.Hin, b.Win, b.C, b.Ho, b.Wo, b.dw_w, b.dw_b, d->act[cur ^ 1]);
     CB_LAUNCH_CHECK();
     cur ^= 1;
+    d->last_buf = cur;
     if (d->stop_layer == ++layer) return CB_OK;
     if (b.has_pw) {
       const long long M = (long long)n * b.Ho * b.Wo;
-      int rc = run_pw(d, b, M, d->act[cur], d->act[cur ^ 1], st);
+      int rc = run_pw(d, b, M, cur, d->act[cur ^ 1], st);
       if (rc) return rc;
       cur ^= 1;
+      d->last_buf = cur;
       if (d->stop_layer == ++layer) return CB_OK;
     }
   }
@@ -717,6 +1003,8 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
   d->max_batch = max_batch;
   const char* env = getenv("CB_PW_SIMT");
   d->force_simt = env && env[0] == '1';
+  const char* env3 = getenv("CB_NO_FUSE");
+  d->no_fuse = env3 && env3[0] == '1';
   const char* env2 = getenv("CB_DEBUG_STOP_LAYER");
   d->stop_layer = env2 ? atoi(env2) : -1;
   d->H1 = conv_out_s2(rows);
@@ -776,15 +1064,10 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
   if (!rc) rc = upload_f32(&d->vlad_w, w->vlad_w, (size_t)d->D * kK);
   if (!rc) rc = upload_f32(&d->vlad_b, w->vlad_b, kK);
   if (!rc) rc = upload_f32(&d->vlad_c, w->vlad_c, (size_t)d->D * kK);
-  // which ping-pong buffer each layer's output lands in (mirrors forward())
-  int cur = 0;
-  d->layer_buf.push_back(cur);
   for (size_t i = 0; i < d->blocks.size() && !rc; ++i) {
     Block& b = d->blocks[i];
     rc = upload_f32(&b.dw_w, w->dw_w[i], (size_t)9 * b.C);
     if (!rc) rc = upload_f32(&b.dw_b, w->dw_b[i], b.C);
-    cur ^= 1;
-    d->layer_buf.push_back(cur);
     if (b.has_pw && !rc) {
       // host: [C][Cout] fp32 -> device [Cout][C] fp16 (K-major B operand)
       std::vector<__half> tmp((size_t)b.C * b.Cout);
@@ -800,12 +1083,14 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
       b.use_tc = b.kb != 0 && b.n_tile != 0;
       if (b.use_tc && !rc) {
         const uint64_t Mmax = (uint64_t)max_batch * b.Ho * b.Wo;
-        // the GEMM reads the depthwise output (buffer `cur`) and writes the other buffer
-        rc = make_map_2d(&b.tmA, d->act[cur], Mmax, (uint64_t)b.C, 128, (uint32_t)b.kb);
+        rc = make_map_2d(&b.tmA[0], d->act[0], Mmax, (uint64_t)b.C, 128, (uint32_t)b.kb);
+        if (!rc) rc = make_map_2d(&b.tmA[1], d->act[1], Mmax, (uint64_t)b.C, 128, (uint32_t)b.kb);
         if (!rc) rc = make_map_2d(&b.tmB, b.pw_w, (uint64_t)b.Cout, (uint64_t)b.C, (uint32_t)b.n_tile, (uint32_t)b.kb);
+        b.fused = fused_shape_supported(b.C, b.Cout, b.stride);
+        if (b.fused && !rc)
+          rc = make_map_2d(&b.tmBf, b.pw_w, (uint64_t)b.Cout, (uint64_t)b.C, (uint32_t)(b.Cout > 256 ? 256 : b.Cout),
+                           (uint32_t)(b.C < 64 ? b.C : 64));
       }
-      cur ^= 1;
-      d->layer_buf.push_back(cur);
     }
   }
   if (rc) {
@@ -863,15 +1148,15 @@ int cb_descriptor_compute(cb_descriptor* d, int n, const uint8_t* images, int64_
 
 int64_t cb_descriptor_get_activation(cb_descriptor* d, int layer, float* out, int64_t max_floats) {
   if (!d || !out) return cb::fail(CB_EINVAL, "NULL argument to cb_descriptor_get_activation");
-  if (layer < 0 || layer >= (int)d->layer_buf.size()) return cb::fail(CB_EINVAL, "layer %d out of range", layer);
-  // only the LAST layer written into each ping-pong buffer survives a forward pass; callers use
-  // this right after a 1-layer-at-a-time debugging run or for the final feature map
+  if (layer < 0 || layer >= (int)d->layer_elems.size()) return cb::fail(CB_EINVAL, "layer %d out of range", layer);
+  // returns the MOST RECENT layer output (the forward pass stops after `CB_DEBUG_STOP_LAYER`, or runs to the
+  // final feature map); `layer` only selects the element count
   const size_t ne = d->layer_elems[layer];
   if ((int64_t)ne > max_floats) return cb::fail(CB_EINVAL, "buffer too small: need %zu floats", ne);
   cb::DeviceGuard g(d->device);
   std::vector<__half> tmp(ne);
   CB_CUDA(cudaStreamSynchronize(d->stream));
-  CB_CUDA(cudaMemcpy(tmp.data(), d->act[d->layer_buf[layer]], ne * sizeof(__half), cudaMemcpyDeviceToHost));
+  CB_CUDA(cudaMemcpy(tmp.data(), d->act[d->last_buf], ne * sizeof(__half), cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < ne; ++i) out[i] = __half2float(tmp[i]);
   return (int64_t)ne;
 }

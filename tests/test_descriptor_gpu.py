@@ -93,6 +93,30 @@ def test_tcgen05_path_agrees_with_cuda_core_path(native_lib, cuda_device):
     finally:
         os.environ.pop("CB_PW_SIMT", None)
     assert np.linalg.norm(a - b, axis=1).max() < 2e-3
+    # the fused depthwise->pointwise kernel (default) vs separate depthwise + TMA-fed GEMM kernels
+    os.environ["CB_NO_FUSE"] = "1"
+    try:
+        nd = NetvladDescriptor(net, h, w, c, max_batch=3)
+        c_ = nd.compute(imgs)
+        nd.close()
+    finally:
+        os.environ.pop("CB_NO_FUSE", None)
+    assert np.linalg.norm(a - c_, axis=1).max() < 2e-3
+
+
+def test_odd_image_size_tail_tiles(native_lib, cuda_device):
+    """480x752 (EuRoC) gives feature maps whose pixel counts are not multiples of the 128-pixel tile
+    and widths not multiples of 4: exercises every tail path against the oracle."""
+    from cerebro_b200.descriptor import NetvladDescriptor
+    from oracle import netvlad as NV
+
+    raw = golden_io.raw_weights("mobilenet_conv7")
+    imgs = synth.band_limited_images(1, 120, 188, 3, seed=77)
+    nd = NetvladDescriptor(_net("mobilenet_conv7"), 120, 188, 3, max_batch=1)
+    d = nd.compute(imgs)
+    ref = NV.describe(imgs, raw, dtype="float64")
+    assert np.linalg.norm(d - ref, axis=1).max() < L2_TOL
+    nd.close()
 
 
 def test_reference_server_call_shape(native_lib, cuda_device, tmp_path):
