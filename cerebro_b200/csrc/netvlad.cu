@@ -389,31 +389,34 @@ __global__ void __launch_bounds__(kGemmThreads) pw_gemm_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
-// fused depthwise -> pointwise block.  One CTA = 128 output pixels x all COUT channels.
-//   warp 0    : TMA producer of the pointwise-weight (B) tiles, one 64-channel K block at a time
-//   warp 1    : TMEM allocator + tcgen05.mma issuer
-//   warps 2-5 : epilogue (TMEM -> +bias -> ReLU6 -> fp16 -> global)
-//   warps 6-13: depthwise producers: compute the 3x3 depthwise (+bias, ReLU6) for the tile straight from
-//               the previous layer's activation in global memory and write it, as fp16, into the
-//               128B/64B-swizzled K-major A tile in shared memory (the layout TMA would have produced);
-//               fence.proxy.async + mbarrier hand each K block to the MMA warp.
+// fused depthwise -> pointwise block, persistent: one CTA per SM loops over 128-pixel output tiles.
+//   warp 0     : TMA producer of the pointwise-weight (B) tiles; the whole weight matrix stays resident in
+//                shared memory when it fits (blocks 1-5), else a 2-stage ring of 64-channel K blocks
+//   warp 1     : TMEM allocator + tcgen05.mma issuer (two TMEM accumulator stages when COUT <= 256, so the
+//                epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 2-5  : epilogue (TMEM -> +bias -> ReLU6 -> fp16 -> global)
+//   warps 6-21 : depthwise producers: compute the 3x3 depthwise (+bias, ReLU6) for the tile straight from the
+//                previous layer's activation in global memory and write it, as fp16, into the 128B/64B-swizzled
+//                K-major A tile in shared memory (the layout TMA would have produced); fence.proxy.async +
+//                mbarrier hand each K block to the MMA warp; a ring of A slots lets them run ahead.
 // The depthwise output never touches HBM: per block the activation traffic drops from
 // (dw in + dw out + pw in + pw out) to (dw in + pw out).
 // ---------------------------------------------------------------------------------------------
-constexpr int kFusedThreads = 448;
-constexpr int kProdThreads = 256;
-constexpr int kASlots = 2;
-constexpr int kBStages = 2;
+constexpr int kProdWarps = 16;
+constexpr int kProdThreads = 32 * kProdWarps;
+constexpr int kFusedThreads = 192 + kProdThreads;  // 704
+constexpr int kASlots = 3;
 
 template <int CIN, int COUT>
 struct FusedSmem {
   static constexpr int KB = CIN < 64 ? CIN : 64;  // channels per K block (32 only for the first block)
   static constexpr int NKB = CIN / KB;
   static constexpr int kABytes = 128 * KB * 2;
-  static constexpr int kBBytes = COUT * KB * 2;
-  static constexpr int kAS = NKB < kASlots ? NKB : kASlots;
-  static constexpr int kBS = NKB < kBStages ? NKB : kBStages;
-  static constexpr int kTotal = kAS * kABytes + kBS * kBBytes + 1024 /*align*/ + 128 /*barriers*/ + 1024 /*geometry*/;
+  static constexpr int kBBytes = COUT * KB * 2;                    // one K block of the weights
+  static constexpr bool kResident = NKB * kBBytes <= 128 * 1024;   // whole [COUT][CIN] matrix in smem
+  static constexpr int kBS = kResident ? NKB : 2;                  // B slots
+  static constexpr int kAcc = COUT <= 256 ? 2 : 1;                 // TMEM accumulator stages
+  static constexpr int kTotal = kASlots * kABytes + kBS * kBBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -422,45 +425,46 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <int CIN, int COUT, int S>
-__global__ void __launch_bounds__(kFusedThreads, (COUT <= 256 ? 2 : 1)) dwpw_kernel(const __half* __restrict__ in, int n_frames, int H, int W, int Ho,
-                                                            int Wo, const float* __restrict__ dw_w /*[3][3][CIN]*/,
-                                                            const float* __restrict__ dw_b,
-                                                            const __grid_constant__ CUtensorMap tmB,
-                                                            const float* __restrict__ bias, __half* __restrict__ out,
-                                                            int M_total) {
+__global__ void __launch_bounds__(kFusedThreads, 1) dwpw_kernel(const __half* __restrict__ in, int H, int W, int Ho, int Wo,
+                                                               const float* __restrict__ dw_w /*[3][3][CIN]*/,
+                                                               const float* __restrict__ dw_b,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const float* __restrict__ bias, __half* __restrict__ out,
+                                                               int M_total, int n_tiles) {
   using SM = FusedSmem<CIN, COUT>;
   constexpr int KB = SM::KB, NKB = SM::NKB;
   constexpr int SWZ = KB * 2;
   constexpr int N_MMA = COUT > 256 ? 256 : COUT;  // columns per tcgen05.mma (two halves when COUT = 512)
+  constexpr int kAcc = SM::kAcc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + SM::kAS * SM::kABytes;
+  uint8_t* smem_b = smem + kASlots * SM::kABytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + SM::kBS * SM::kBBytes);
   uint64_t* a_empty = a_full + kASlots;
-  uint64_t* b_full = a_empty + kASlots;
-  uint64_t* b_empty = b_full + kBStages;
-  uint64_t* tmem_full_bar = b_empty + kBStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  int2* geom = reinterpret_cast<int2*>(tmem_ptr + 2);  // [128]
+  uint64_t* b_full = a_empty + kASlots;   // [2] (ring) or [1] (resident)
+  uint64_t* b_empty = b_full + 2;
+  uint64_t* tmem_full_bar = b_empty + 2;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kASlots; ++s) {
-      mbar_init(&a_full[s], kProdThreads / 32);
+      mbar_init(&a_full[s], kProdWarps);
       mbar_init(&a_empty[s], 1);
     }
-    for (int s = 0; s < kBStages; ++s) {
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);
     }
-    mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, COUT);
+  if (warp == 1) tmem_alloc(tmem_ptr, kAcc * COUT);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -468,110 +472,130 @@ __global__ void __launch_bounds__(kFusedThreads, (COUT <= 256 ? 2 : 1)) dwpw_ker
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < NKB; ++kb) {
-        const int s = kb % SM::kBS;
-        const uint32_t round = kb / SM::kBS;
-        mbar_wait(&b_empty[s], (round & 1) ^ 1);
-        mbar_expect_tx(&b_full[s], SM::kBBytes);
-        uint8_t* sb = smem_b + s * SM::kBBytes;
-        // the weight matrix is [COUT][CIN]; a TMA box holds at most 256 rows
-        tma_load_2d(&tmB, &b_full[s], sb, kb * KB, 0);
-        if (COUT > 256) tma_load_2d(&tmB, &b_full[s], sb + 256 * KB * 2, kb * KB, 256);
+      if (SM::kResident) {
+        mbar_expect_tx(&b_full[0], NKB * SM::kBBytes);
+        for (int kb = 0; kb < NKB; ++kb) {
+          uint8_t* sb = smem_b + kb * SM::kBBytes;
+          tma_load_2d(&tmB, &b_full[0], sb, kb * KB, 0);
+          if (COUT > 256) tma_load_2d(&tmB, &b_full[0], sb + 256 * KB * 2, kb * KB, 256);
+        }
+      } else {
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+          for (int kb = 0; kb < NKB; ++kb, ++g) {
+            const int s = g & 1;
+            mbar_wait(&b_empty[s], ((g >> 1) & 1) ^ 1);
+            mbar_expect_tx(&b_full[s], SM::kBBytes);
+            uint8_t* sb = smem_b + s * SM::kBBytes;
+            tma_load_2d(&tmB, &b_full[s], sb, kb * KB, 0);
+            if (COUT > 256) tma_load_2d(&tmB, &b_full[s], sb + 256 * KB * 2, kb * KB, 256);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(N_MMA >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      for (int kb = 0; kb < NKB; ++kb) {
-        const int sa = kb % SM::kAS, sb = kb % SM::kBS;
-        mbar_wait(&b_full[sb], (kb / SM::kBS) & 1);
-        mbar_wait(&a_full[sa], (kb / SM::kAS) & 1);
+      uint32_t g = 0, ti = 0;
+      if (SM::kResident) mbar_wait(&b_full[0], 0);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        const int acc = ti % kAcc;
+        mbar_wait(&tmem_empty_bar[acc], ((ti / kAcc) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem_a + sa * SM::kABytes);
-        const uint32_t b_addr = smem_u32(smem_b + sb * SM::kBBytes);
+        const uint32_t d_tmem = tmem_base + acc * COUT;
+        for (int kb = 0; kb < NKB; ++kb, ++g) {
+          const int sa = g % kASlots;
+          const int sb = SM::kResident ? kb : (int)(g & 1);
+          if (!SM::kResident) mbar_wait(&b_full[sb], (g >> 1) & 1);
+          mbar_wait(&a_full[sa], (g / kASlots) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + sa * SM::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + sb * SM::kBBytes);
 #pragma unroll
-        for (int k = 0; k < KB / 16; ++k) {
-          const uint64_t ad = make_kmajor_desc<SWZ>(a_addr + k * 32);
+          for (int k = 0; k < KB / 16; ++k) {
+            const uint64_t ad = make_kmajor_desc<SWZ>(a_addr + k * 32);
 #pragma unroll
-          for (int h = 0; h < COUT / N_MMA; ++h) {
-            const uint64_t bd = make_kmajor_desc<SWZ>(b_addr + h * (256 * KB * 2) + k * 32);
-            umma_f16(tmem_base + h * 256, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            for (int h = 0; h < COUT / N_MMA; ++h) {
+              const uint64_t bd = make_kmajor_desc<SWZ>(b_addr + h * (256 * KB * 2) + k * 32);
+              umma_f16(d_tmem + h * 256, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            }
           }
+          umma_commit(&a_empty[sa]);
+          if (!SM::kResident) umma_commit(&b_empty[sb]);
         }
-        umma_commit(&a_empty[sa]);
-        umma_commit(&b_empty[sb]);
+        umma_commit(&tmem_full_bar[acc]);
       }
-      umma_commit(tmem_full_bar);
     }
   } else if (warp < 6) {
     const int q = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < M_total;
-    __half* orow = out + (size_t)row * COUT;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int acc = ti % kAcc;
+      mbar_wait(&tmem_full_bar[acc], (ti / kAcc) & 1);
+      tc_fence_after();
+      const long long row = (long long)tile * 128 + q * 32 + lane;
+      const bool row_ok = row < M_total;
+      __half* orow = out + (size_t)row * COUT;
 #pragma unroll 1
-    for (int c = 0; c < COUT; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      if (row_ok) {
+      for (int c = 0; c < COUT; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + acc * COUT + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c + j));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + j + 4));
-          __half2 h[4];
-          h[0] = __floats2half2_rn(relu6(__uint_as_float(v[j + 0]) + b0.x), relu6(__uint_as_float(v[j + 1]) + b0.y));
-          h[1] = __floats2half2_rn(relu6(__uint_as_float(v[j + 2]) + b0.z), relu6(__uint_as_float(v[j + 3]) + b0.w));
-          h[2] = __floats2half2_rn(relu6(__uint_as_float(v[j + 4]) + b1.x), relu6(__uint_as_float(v[j + 5]) + b1.y));
-          h[3] = __floats2half2_rn(relu6(__uint_as_float(v[j + 6]) + b1.z), relu6(__uint_as_float(v[j + 7]) + b1.w));
-          *reinterpret_cast<uint4*>(orow + c + j) = *reinterpret_cast<uint4*>(h);
+          for (int j = 0; j < 32; j += 8) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c + j));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + j + 4));
+            __half2 h[4];
+            h[0] = __floats2half2_rn(relu6(__uint_as_float(v[j + 0]) + b0.x), relu6(__uint_as_float(v[j + 1]) + b0.y));
+            h[1] = __floats2half2_rn(relu6(__uint_as_float(v[j + 2]) + b0.z), relu6(__uint_as_float(v[j + 3]) + b0.w));
+            h[2] = __floats2half2_rn(relu6(__uint_as_float(v[j + 4]) + b1.x), relu6(__uint_as_float(v[j + 5]) + b1.y));
+            h[3] = __floats2half2_rn(relu6(__uint_as_float(v[j + 6]) + b1.z), relu6(__uint_as_float(v[j + 7]) + b1.w));
+            *reinterpret_cast<uint4*>(orow + c + j) = *reinterpret_cast<uint4*>(h);
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
   } else {
     // ---- depthwise producers: task = (pixel of the tile, group of 8 channels of the current K block)
-    const int pt = threadIdx.x - 192;        // 0..255
+    const int pt = threadIdx.x - 192;        // 0..511
     constexpr int CGB = KB / 8;              // channel groups per K block (8, or 4 for the 32-channel block)
     constexpr int PIX_PER_PASS = kProdThreads / CGB;
-    constexpr int PASSES = 128 / PIX_PER_PASS;
+    constexpr int PASSES = 128 / PIX_PER_PASS;  // 2 (1 for the 32-channel block)
     constexpr int P = (S == 1) ? 1 : 0;
     const int cgl = pt % CGB;
     const int pl = pt / CGB;
-    // geometry of the tile's 128 pixels, computed once: {frame (or -1), (y << 16) | x}
-    if (pt < 128) {
-      const long long m = (long long)m0 + pt;
-      int2 g = make_int2(-1, 0);
-      if (m < M_total) {
-        const int x = (int)(m % Wo);
-        const long long t2 = m / Wo;
-        g.x = (int)(t2 / Ho);
-        g.y = ((int)(t2 % Ho) << 16) | x;
-      }
-      geom[pt] = g;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads) : "memory");
-    for (int kb = 0; kb < NKB; ++kb) {
-      const int sa = kb % SM::kAS;
-      mbar_wait(&a_empty[sa], ((kb / SM::kAS) & 1) ^ 1);
-      uint8_t* at = smem_a + sa * SM::kABytes;
-      const int ch0 = kb * KB + cgl * 8;
-      const float4 bb0 = __ldg(reinterpret_cast<const float4*>(dw_b + ch0));
-      const float4 bb1 = __ldg(reinterpret_cast<const float4*>(dw_b + ch0 + 4));
-#pragma unroll 1
-      for (int i0 = 0; i0 < PASSES; i0 += 2) {  // two pixels per round: their loads are independent
-        float acc[2][8];
-        int gy[2], gx[2];
-        const __half* gbase[2];
-        bool pok[2];
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int gy[PASSES], gx[PASSES];
+      const __half* gbase[PASSES];
+      bool pok[PASSES];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int2 g = geom[(i0 + u) * PIX_PER_PASS + pl];
-          pok[u] = g.x >= 0;
-          gy[u] = g.y >> 16;
-          gx[u] = g.y & 0xffff;
-          gbase[u] = in + (size_t)(pok[u] ? g.x : 0) * H * W * CIN + ch0;
-          acc[u][0] = bb0.x, acc[u][1] = bb0.y, acc[u][2] = bb0.z, acc[u][3] = bb0.w;
-          acc[u][4] = bb1.x, acc[u][5] = bb1.y, acc[u][6] = bb1.z, acc[u][7] = bb1.w;
+      for (int u = 0; u < PASSES; ++u) {
+        const long long m = (long long)tile * 128 + u * PIX_PER_PASS + pl;
+        pok[u] = m < M_total;
+        const long long mm = pok[u] ? m : 0;
+        gx[u] = (int)(mm % Wo);
+        const long long t2 = mm / Wo;
+        gy[u] = (int)(t2 % Ho);
+        gbase[u] = in + (size_t)(t2 / Ho) * H * W * CIN;
+      }
+      for (int kb = 0; kb < NKB; ++kb, ++g) {
+        const int sa = g % kASlots;
+        mbar_wait(&a_empty[sa], ((g / kASlots) & 1) ^ 1);
+        uint8_t* at = smem_a + sa * SM::kABytes;
+        const int ch0 = kb * KB + cgl * 8;
+        float acc[PASSES][8];
+        {
+          const float4 bb0 = __ldg(reinterpret_cast<const float4*>(dw_b + ch0));
+          const float4 bb1 = __ldg(reinterpret_cast<const float4*>(dw_b + ch0 + 4));
+#pragma unroll
+          for (int u = 0; u < PASSES; ++u) {
+            acc[u][0] = bb0.x, acc[u][1] = bb0.y, acc[u][2] = bb0.z, acc[u][3] = bb0.w;
+            acc[u][4] = bb1.x, acc[u][5] = bb1.y, acc[u][6] = bb1.z, acc[u][7] = bb1.w;
+          }
         }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -579,15 +603,16 @@ __global__ void __launch_bounds__(kFusedThreads, (COUT <= 256 ? 2 : 1)) dwpw_ker
           for (int kx = 0; kx < 3; ++kx) {
             const float4 w0 = __ldg(reinterpret_cast<const float4*>(dw_w + (ky * 3 + kx) * CIN + ch0));
             const float4 w1 = __ldg(reinterpret_cast<const float4*>(dw_w + (ky * 3 + kx) * CIN + ch0 + 4));
-            uint4 raw[2];
+            uint4 raw[PASSES];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < PASSES; ++u) {
               const int iy = gy[u] * S + ky - P, ix = gx[u] * S + kx - P;
               const bool ok = pok[u] && iy >= 0 && iy < H && ix >= 0 && ix < W;
-              raw[u] = ok ? *reinterpret_cast<const uint4*>(gbase[u] + ((size_t)iy * W + ix) * CIN) : make_uint4(0u, 0u, 0u, 0u);
+              raw[u] = ok ? *reinterpret_cast<const uint4*>(gbase[u] + ((size_t)iy * W + ix) * CIN + ch0)
+                          : make_uint4(0u, 0u, 0u, 0u);
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < PASSES; ++u) {
               const __half2* hv = reinterpret_cast<const __half2*>(&raw[u]);
               const float2 v0 = __half22float2(hv[0]), v1 = __half22float2(hv[1]), v2 = __half22float2(hv[2]),
                            v3 = __half22float2(hv[3]);
@@ -603,8 +628,8 @@ __global__ void __launch_bounds__(kFusedThreads, (COUT <= 256 ? 2 : 1)) dwpw_ker
           }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int r = (i0 + u) * PIX_PER_PASS + pl;
+        for (int u = 0; u < PASSES; ++u) {
+          const int r = u * PIX_PER_PASS + pl;
           __half2 h[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -613,17 +638,141 @@ __global__ void __launch_bounds__(kFusedThreads, (COUT <= 256 ? 2 : 1)) dwpw_ker
           const int chunk = (SWZ == 128) ? (cgl ^ (r & 7)) : (cgl ^ ((r >> 1) & 3));
           *reinterpret_cast<uint4*>(at + r * SWZ + chunk * 16) = *reinterpret_cast<uint4*>(h);
         }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[sa]);
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[sa]);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, COUT);
+    tmem_dealloc(tmem_base, kAcc * COUT);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stem on tcgen05: implicit GEMM  [pixels x 32 (27 taps, zero padded)] x [32 x 32 output channels].
+//   warp 0    : TMEM allocator + tcgen05.mma issuer
+//   warps 1-4 : im2col producers (one output pixel per thread: 27 byte loads -> exact fp16 integers x-128
+//               -> 64B-swizzled K-major row), then the epilogue of the same tile
+// The 2/255 input scale is folded into the weights, which are split hi + lo (two accumulating MMAs) so the
+// only rounding left is the fp16 store of the result.  kConvTiles tiles per CTA amortise the set-up.
+// ---------------------------------------------------------------------------------------------
+constexpr int kConvThreads = 160;
+constexpr int kConvTiles = 4;
+
+template <int CIN>
+__global__ void __launch_bounds__(kConvThreads) conv1_tc_kernel(const uint8_t* __restrict__ img, int n, int H, int W, int Ho, int Wo,
+                                                               const __half* __restrict__ w_hi /*[32][32] K-major*/,
+                                                               const __half* __restrict__ w_lo, const float* __restrict__ bias,
+                                                               __half* __restrict__ out, int M_total) {
+  __shared__ __align__(1024) uint8_t sA[128 * 64];
+  __shared__ __align__(1024) uint8_t sB[2][32 * 64];
+  __shared__ uint64_t a_full, tmem_full;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&a_full, 4);
+    mbar_init(&tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 32);
+  if (threadIdx.x >= 32) {  // weights: 32 rows x 4 chunks of 16 B per matrix, 64B-swizzled like the A tile
+    const int t = threadIdx.x - 32, r = t >> 2, c = t & 3;
+    const int cs = c ^ ((r >> 1) & 3);
+    *reinterpret_cast<uint4*>(sB[0] + r * 64 + cs * 16) = *reinterpret_cast<const uint4*>(w_hi + r * 32 + c * 8);
+    *reinterpret_cast<uint4*>(sB[1] + r * 64 + cs * 16) = *reinterpret_cast<const uint4*>(w_lo + r * 32 + c * 8);
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  for (int it = 0; it < kConvTiles; ++it) {
+    const long long m0 = ((long long)blockIdx.x * kConvTiles + it) * 128;
+    if (m0 >= M_total) break;  // CTA-uniform
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_wait(&a_full, it & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA);
+#pragma unroll
+        for (int hl = 0; hl < 2; ++hl) {
+          const uint32_t b_addr = smem_u32(sB[hl]);
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_f16(tmem_base, make_kmajor_desc<64>(a_addr + k * 32), make_kmajor_desc<64>(b_addr + k * 32), idesc,
+                     (hl | k) ? 1u : 0u);
+        }
+        umma_commit(&tmem_full);
+      }
+    } else {
+      const int r = threadIdx.x - 32;  // row of the tile = TMEM lane
+      const long long m = m0 + r;
+      const bool ok = m < M_total;
+      __half hv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) hv[i] = __ushort_as_half((unsigned short)0);
+      if (ok) {
+        const int x = (int)(m % Wo);
+        const long long t2 = m / Wo;
+        const int y = (int)(t2 % Ho);
+        const uint8_t* base = img + (size_t)(t2 / Ho) * H * W * CIN;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int iy = 2 * y + ky;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int ix = 2 * x + kx;
+            if (iy < H && ix < W) {
+#pragma unroll
+              for (int ci = 0; ci < CIN; ++ci)
+                hv[(ky * 3 + kx) * CIN + ci] = __int2half_rn((int)__ldg(base + ((size_t)iy * W + ix) * CIN + ci) - 128);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int cs = c ^ ((r >> 1) & 3);
+        *reinterpret_cast<uint4*>(sA + r * 64 + cs * 16) = *reinterpret_cast<uint4*>(&hv[c * 8]);
+      }
+      fence_proxy_async();
+      tc_fence_before();  // orders the previous tile's tcgen05.ld before the next MMA overwrites TMEM
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full);
+      // ---- epilogue of this tile
+      mbar_wait(&tmem_full, it & 1);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16), v);
+      // TMEM lane quarter of this warp is (warp & 3); its rows are 32*(warp&3)+lane
+      const long long mr = m0 + (warp & 3) * 32 + lane;
+      if (mr < M_total) {
+        __half* orow = out + (size_t)mr * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + j));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + j + 4));
+          __half2 h[4];
+          h[0] = __floats2half2_rn(relu6(__uint_as_float(v[j + 0]) + b0.x), relu6(__uint_as_float(v[j + 1]) + b0.y));
+          h[1] = __floats2half2_rn(relu6(__uint_as_float(v[j + 2]) + b0.z), relu6(__uint_as_float(v[j + 3]) + b0.w));
+          h[2] = __floats2half2_rn(relu6(__uint_as_float(v[j + 4]) + b1.x), relu6(__uint_as_float(v[j + 5]) + b1.y));
+          h[3] = __floats2half2_rn(relu6(__uint_as_float(v[j + 6]) + b1.z), relu6(__uint_as_float(v[j + 7]) + b1.w));
+          *reinterpret_cast<uint4*>(orow + j) = *reinterpret_cast<uint4*>(h);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
   }
 }
 
@@ -828,6 +977,8 @@ struct cb_descriptor {
   int H1 = 0, W1 = 0;
   float* conv1_w = nullptr;
   float* conv1_b = nullptr;
+  __half* conv1_hi = nullptr;  // [32][32] K-major, scale 2/255 folded in, hi/lo split (tcgen05 stem)
+  __half* conv1_lo = nullptr;
   std::vector<Block> blocks;
   int K = 16, D = 0, Hf = 0, Wf = 0;
   float* vlad_w = nullptr;
@@ -874,25 +1025,26 @@ bool fused_shape_supported(int cin, int cout, int stride) {
 }
 
 template <int CIN, int COUT, int S>
-int launch_fused(const Block& b, int n, const __half* in, __half* out, cudaStream_t st) {
+int launch_fused(const Block& b, int n, int sm_count, const __half* in, __half* out, cudaStream_t st) {
   using SM = FusedSmem<CIN, COUT>;
   auto kern = dwpw_kernel<CIN, COUT, S>;
   CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
   const long long M = (long long)n * b.Ho * b.Wo;
-  kern<<<(unsigned)((M + 127) / 128), kFusedThreads, SM::kTotal, st>>>(in, n, b.Hin, b.Win, b.Ho, b.Wo, b.dw_w, b.dw_b, b.tmBf,
-                                                                     b.pw_b, out, (int)M);
+  const int n_tiles = (int)((M + 127) / 128);
+  const int grid = n_tiles < sm_count ? n_tiles : sm_count;  // persistent: one CTA per SM
+  kern<<<grid, kFusedThreads, SM::kTotal, st>>>(in, b.Hin, b.Win, b.Ho, b.Wo, b.dw_w, b.dw_b, b.tmBf, b.pw_b, out, (int)M, n_tiles);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
 
-int run_fused(const Block& b, int n, const __half* in, __half* out, cudaStream_t st) {
-  if (b.C == 32) return launch_fused<32, 64, 1>(b, n, in, out, st);
-  if (b.C == 64) return launch_fused<64, 128, 2>(b, n, in, out, st);
-  if (b.C == 128 && b.Cout == 128) return launch_fused<128, 128, 1>(b, n, in, out, st);
-  if (b.C == 128) return launch_fused<128, 256, 2>(b, n, in, out, st);
-  if (b.C == 256 && b.Cout == 256) return launch_fused<256, 256, 1>(b, n, in, out, st);
-  if (b.C == 256) return launch_fused<256, 512, 2>(b, n, in, out, st);
-  return launch_fused<512, 512, 1>(b, n, in, out, st);
+int run_fused(const Block& b, int n, int sm, const __half* in, __half* out, cudaStream_t st) {
+  if (b.C == 32) return launch_fused<32, 64, 1>(b, n, sm, in, out, st);
+  if (b.C == 64) return launch_fused<64, 128, 2>(b, n, sm, in, out, st);
+  if (b.C == 128 && b.Cout == 128) return launch_fused<128, 128, 1>(b, n, sm, in, out, st);
+  if (b.C == 128) return launch_fused<128, 256, 2>(b, n, sm, in, out, st);
+  if (b.C == 256 && b.Cout == 256) return launch_fused<256, 256, 1>(b, n, sm, in, out, st);
+  if (b.C == 256) return launch_fused<256, 512, 2>(b, n, sm, in, out, st);
+  return launch_fused<512, 512, 1>(b, n, sm, in, out, st);
 }
 
 int run_pw(cb_descriptor* d, const Block& b, long long M, int in_buf, __half* out, cudaStream_t st) {
@@ -920,7 +1072,17 @@ int run_pw(cb_descriptor* d, const Block& b, long long M, int in_buf, __half* ou
 
 int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cudaStream_t st) {
   int cur = 0;
-  {
+  if (!d->force_simt && !d->no_fuse) {
+    const long long M = (long long)n * d->H1 * d->W1;
+    const unsigned grid = (unsigned)((M + 128 * kConvTiles - 1) / (128 * kConvTiles));
+    if (d->chnls == 1)
+      conv1_tc_kernel<1><<<grid, kConvThreads, 0, st>>>(img_dev, n, d->rows, d->cols, d->H1, d->W1, d->conv1_hi, d->conv1_lo,
+                                                        d->conv1_b, d->act[cur], (int)M);
+    else
+      conv1_tc_kernel<3><<<grid, kConvThreads, 0, st>>>(img_dev, n, d->rows, d->cols, d->H1, d->W1, d->conv1_hi, d->conv1_lo,
+                                                        d->conv1_b, d->act[cur], (int)M);
+    CB_LAUNCH_CHECK();
+  } else {
     const long long threads = (long long)n * d->H1 * ((d->W1 + kPX - 1) / kPX) * 4;
     const unsigned grid = (unsigned)((threads + 255) / 256);
     if (d->chnls == 1)
@@ -936,7 +1098,7 @@ int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cud
     const int dw_layer = layer + 1, pw_layer = layer + 2;
     if (b.has_pw && b.use_tc && b.fused && !d->no_fuse && !d->force_simt && d->stop_layer != dw_layer) {
       // fused depthwise -> pointwise: one kernel, one ping-pong flip (the depthwise output never exists)
-      int rc = run_fused(b, n, d->act[cur], d->act[cur ^ 1], st);
+      int rc = run_fused(b, n, d->sm_count, d->act[cur], d->act[cur ^ 1], st);
       if (rc) return rc;
       cur ^= 1;
       d->last_buf = cur;
@@ -1060,6 +1222,21 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
     return cb::fail(CB_ENOMEM, "descriptor allocation failed: %s", cudaGetErrorString(e));
   }
   rc = upload_f32(&d->conv1_w, w->conv1_w, (size_t)9 * chnls * 32);
+  if (!rc) {
+    std::vector<__half> hi(32 * 32, __float2half_rn(0.f)), lo(32 * 32, __float2half_rn(0.f));
+    for (int k = 0; k < 9 * chnls; ++k)
+      for (int nn = 0; nn < 32; ++nn) {
+        const float v = w->conv1_w[(size_t)k * 32 + nn] * (2.0f / 255.0f);  // server.py:629 folded into the weights
+        const __half h = __float2half_rn(v);
+        hi[nn * 32 + k] = h;
+        lo[nn * 32 + k] = __float2half_rn(v - __half2float(h));
+      }
+    cudaError_t e2 = cudaMalloc((void**)&d->conv1_hi, hi.size() * sizeof(__half));
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&d->conv1_lo, lo.size() * sizeof(__half));
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(d->conv1_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(d->conv1_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e2 != cudaSuccess) rc = cb::fail(CB_ENOMEM, "stem weight upload failed: %s", cudaGetErrorString(e2));
+  }
   if (!rc) rc = upload_f32(&d->conv1_b, w->conv1_b, 32);
   if (!rc) rc = upload_f32(&d->vlad_w, w->vlad_w, (size_t)d->D * kK);
   if (!rc) rc = upload_f32(&d->vlad_b, w->vlad_b, kK);
@@ -1111,7 +1288,7 @@ int cb_descriptor_destroy(cb_descriptor* d) {
     cudaFree(b.pw_w);
     cudaFree(b.pw_b);
   }
-  void* ptrs[] = {d->conv1_w, d->conv1_b, d->vlad_w, d->vlad_b, d->vlad_c, d->act[0], d->act[1],
+  void* ptrs[] = {d->conv1_hi, d->conv1_lo, d->conv1_w, d->conv1_b, d->vlad_w, d->vlad_b, d->vlad_c, d->act[0], d->act[1],
                   d->assign,  d->Vraw,    d->img_dev, d->out_dev};
   for (void* p : ptrs)
     if (p) cudaFree(p);
