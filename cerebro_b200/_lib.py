@@ -92,6 +92,11 @@ _SIGNATURES = {
         C.c_int,
         [_vp, C.c_int, _vp, C.c_int, _vp, _vp, C.POINTER(RansacParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     ),
+    "cb_pnp_icp_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.POINTER(RansacParams), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cb_pnp_icp_batch_device": (
+        C.c_int,
+        [_vp, C.c_int, _vp, _vp, _vp, C.POINTER(RansacParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    ),
     "cb_pnp_dls_minimal": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -567,20 +567,37 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dwpw_kernel(const __half* __
     constexpr int P = (S == 1) ? 1 : 0;
     const int cgl = pt % CGB;
     const int pl = pt / CGB;
+    // tap offsets (in elements) relative to the pixel's top-left tap; identical for every thread
+    int tap_off[9];
+#pragma unroll
+    for (int t9 = 0; t9 < 9; ++t9) tap_off[t9] = ((t9 / 3) * W + (t9 % 3)) * CIN;
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      int gy[PASSES], gx[PASSES];
-      const __half* gbase[PASSES];
-      bool pok[PASSES];
+      // geometry once per tile (not per K block): pointer to the top-left tap and a 9-bit validity mask
+      const __half* pb[PASSES];
+      uint32_t vmask[PASSES];
 #pragma unroll
       for (int u = 0; u < PASSES; ++u) {
-        const long long m = (long long)tile * 128 + u * PIX_PER_PASS + pl;
-        pok[u] = m < M_total;
-        const long long mm = pok[u] ? m : 0;
-        gx[u] = (int)(mm % Wo);
-        const long long t2 = mm / Wo;
-        gy[u] = (int)(t2 % Ho);
-        gbase[u] = in + (size_t)(t2 / Ho) * H * W * CIN;
+        const int m = tile * 128 + u * PIX_PER_PASS + pl;
+        const bool ok = m < M_total;
+        const int mm = ok ? m : 0;
+        const int x = mm % Wo;
+        const int t2 = mm / Wo;
+        const int y = t2 % Ho;
+        const int f = t2 / Ho;
+        const int iy0 = y * S - P, ix0 = x * S - P;
+        uint32_t rmask = 0, cmask = 0;
+#pragma unroll
+        for (int k3 = 0; k3 < 3; ++k3) {
+          rmask |= (uint32_t)(iy0 + k3 >= 0 && iy0 + k3 < H) << k3;
+          cmask |= (uint32_t)(ix0 + k3 >= 0 && ix0 + k3 < W) << k3;
+        }
+        uint32_t vm = 0;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+          if ((rmask >> ky) & 1u) vm |= cmask << (3 * ky);
+        vmask[u] = ok ? vm : 0u;
+        pb[u] = in + ((long long)(f * H + iy0) * W + ix0) * CIN;  // may point before the frame: only valid taps are read
       }
       for (int kb = 0; kb < NKB; ++kb, ++g) {
         const int sa = g % kASlots;
@@ -598,35 +615,32 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dwpw_kernel(const __half* __
           }
         }
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(dw_w + t9 * CIN + ch0));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(dw_w + t9 * CIN + ch0 + 4));
+          uint4 raw[PASSES];
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(dw_w + (ky * 3 + kx) * CIN + ch0));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(dw_w + (ky * 3 + kx) * CIN + ch0 + 4));
-            uint4 raw[PASSES];
+          for (int u = 0; u < PASSES; ++u)
+            raw[u] = ((vmask[u] >> t9) & 1u) ? *reinterpret_cast<const uint4*>(pb[u] + tap_off[t9] + ch0)
+                                              : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int u = 0; u < PASSES; ++u) {
-              const int iy = gy[u] * S + ky - P, ix = gx[u] * S + kx - P;
-              const bool ok = pok[u] && iy >= 0 && iy < H && ix >= 0 && ix < W;
-              raw[u] = ok ? *reinterpret_cast<const uint4*>(gbase[u] + ((size_t)iy * W + ix) * CIN + ch0)
-                          : make_uint4(0u, 0u, 0u, 0u);
-            }
-#pragma unroll
-            for (int u = 0; u < PASSES; ++u) {
-              const __half2* hv = reinterpret_cast<const __half2*>(&raw[u]);
-              const float2 v0 = __half22float2(hv[0]), v1 = __half22float2(hv[1]), v2 = __half22float2(hv[2]),
-                           v3 = __half22float2(hv[3]);
-              acc[u][0] = fmaf(v0.x, w0.x, acc[u][0]);
-              acc[u][1] = fmaf(v0.y, w0.y, acc[u][1]);
-              acc[u][2] = fmaf(v1.x, w0.z, acc[u][2]);
-              acc[u][3] = fmaf(v1.y, w0.w, acc[u][3]);
-              acc[u][4] = fmaf(v2.x, w1.x, acc[u][4]);
-              acc[u][5] = fmaf(v2.y, w1.y, acc[u][5]);
-              acc[u][6] = fmaf(v3.x, w1.z, acc[u][6]);
-              acc[u][7] = fmaf(v3.y, w1.w, acc[u][7]);
-            }
+          for (int u = 0; u < PASSES; ++u) {
+            const __half2* hv = reinterpret_cast<const __half2*>(&raw[u]);
+            const float2 v0 = __half22float2(hv[0]), v1 = __half22float2(hv[1]), v2 = __half22float2(hv[2]),
+                         v3 = __half22float2(hv[3]);
+            acc[u][0] = fmaf(v0.x, w0.x, acc[u][0]);
+            acc[u][1] = fmaf(v0.y, w0.y, acc[u][1]);
+            acc[u][2] = fmaf(v1.x, w0.z, acc[u][2]);
+            acc[u][3] = fmaf(v1.y, w0.w, acc[u][3]);
+            acc[u][4] = fmaf(v2.x, w1.x, acc[u][4]);
+            acc[u][5] = fmaf(v2.y, w1.y, acc[u][5]);
+            acc[u][6] = fmaf(v3.x, w1.z, acc[u][6]);
+            acc[u][7] = fmaf(v3.y, w1.w, acc[u][7]);
           }
         }
+        bool pok[PASSES];
+#pragma unroll
+        for (int u = 0; u < PASSES; ++u) pok[u] = tile * 128 + u * PIX_PER_PASS + pl < M_total;
 #pragma unroll
         for (int u = 0; u < PASSES; ++u) {
           const int r = u * PIX_PER_PASS + pl;
@@ -678,6 +692,7 @@ __global__ void __launch_bounds__(kConvThreads) conv1_tc_kernel(const uint8_t* _
     mbar_init(&tmem_full, 1);
     fence_barrier_init();
   }
+  __syncwarp();  // warp 0 must be converged for the .sync.aligned allocation
   if (warp == 0) tmem_alloc(&tmem_slot, 32);
   if (threadIdx.x >= 32) {  // weights: 32 rows x 4 chunks of 16 B per matrix, 64B-swizzled like the A tile
     const int t = threadIdx.x - 32, r = t >> 2, c = t & 3;

@@ -44,12 +44,12 @@ __host__ __device__ inline unsigned long long mix64(unsigned long long z) {
 }
 constexpr unsigned long long kGold = 0x9E3779B97F4A7C15ULL;
 
-__device__ inline void sample_indices(unsigned long long seed, int cand, int hyp, int n, int* out) {
+__device__ inline void sample_indices(unsigned long long seed, int cand, int hyp, int n, int* out, int k = kSample) {
   unsigned long long key = mix64(seed + kGold * (unsigned long long)(cand + 1));
   key = mix64(key + kGold * (unsigned long long)(hyp + 1));
   int cnt = 0;
   unsigned long long ctr = 0;
-  while (cnt < kSample) {
+  while (cnt < k) {
     ++ctr;
     const unsigned long long r = mix64(key + kGold * ctr);
     const int idx = (int)(((r >> 32) * (unsigned long long)n) >> 32);
@@ -856,6 +856,7 @@ struct SelectArgs {
   const int* ninl;      // [n_cand*H]  (-1: hypothesis produced no model)
   const double* model;  // [n_cand*H][12]
   cb_ransac_params p;
+  int sample_size;      // 15 (DLS-PnP) or 10 (Umeyama)
   double* c_T_w;        // [n_cand][16]
   float* confidence;
   int* num_iterations;
@@ -919,7 +920,7 @@ __global__ void __launch_bounds__(32) pnp_select_kernel(SelectArgs a) {
     const double log_fail = log(a.p.failure_probability);
     int max_it = a.p.max_iterations;
     if (a.p.min_inlier_ratio > 0.0) {
-      const int m = max_iterations_for((double)kSample, a.p.min_inlier_ratio, log_fail, a.p);
+      const int m = max_iterations_for((double)a.sample_size, a.p.min_inlier_ratio, log_fail, a.p);
       max_it = m < max_it ? m : max_it;
     }
     int it = 0;
@@ -930,8 +931,8 @@ __global__ void __launch_bounds__(32) pnp_select_kernel(SelectArgs a) {
           best = it;
           best_cost = c;
           const double ratio = (double)ninl[it] / (double)n;
-          if (ratio >= (double)kSample / (double)n) {
-            const int m = max_iterations_for((double)kSample, ratio, log_fail, a.p);
+          if (ratio >= (double)a.sample_size / (double)n) {
+            const int m = max_iterations_for((double)a.sample_size, ratio, log_fail, a.p);
             max_it = m < max_it ? m : max_it;
           }
         }
@@ -953,10 +954,195 @@ __global__ void __launch_bounds__(32) pnp_select_kernel(SelectArgs a) {
         To[i * 4 + 3] = m[9 + i];
       }
       const double ratio = (double)ninl[best] / (double)n;
-      const double conf = 1.0 - pow(1.0 - pow(ratio, (double)kSample), (double)iters);
+      const double conf = 1.0 - pow(1.0 - pow(ratio, (double)a.sample_size), (double)iters);
       a.confidence[cand] = (float)conf;
       if (a.n_inliers) a.n_inliers[cand] = ninl[best];
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Option C: AlignPointCloudsUmeyamaWithRansac (src/DlsPnpWithRansac.h:117-166), thread per hypothesis.
+// Sample 10 pairs -> similarity b ~ s R a + t (Umeyama 1991).  R comes from Horn's quaternion form of the
+// same optimum (largest eigenvector of the 4x4 symmetric N built from the cross-covariance, cyclic Jacobi),
+// which yields a proper rotation in the reflection case exactly like Umeyama's S = diag(1,1,-1);
+// s = trace(R^T Sigma) / var(a); the model keeps R and t and is accepted iff min(s, 1/s) > 0.9 (:139).
+// ---------------------------------------------------------------------------------------------
+constexpr int kIcpSample = 10;
+
+struct IcpArgs {
+  const int* offsets;
+  const double* A;   // [total][3] points in frame a
+  const double* B;   // [total][3] the same points in frame b
+  const int* samples;  // optional [n_cand][H][10]
+  unsigned long long seed;
+  int H;
+  long long g0;
+  int count;
+  int* status;       // out: 1 model, 0 rejected, -1 refused
+  double* model;     // [count][12]
+};
+
+__device__ inline void jacobi4(double N[4][4], double V[4][4]) {
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < 4; ++i)
+      for (int j = i + 1; j < 4; ++j) off += N[i][j] * N[i][j];
+    if (off < 1e-300) break;
+    for (int pi = 0; pi < 3; ++pi)
+      for (int qi = pi + 1; qi < 4; ++qi) {
+        const double apq = N[pi][qi];
+        if (apq == 0.0) continue;
+        const double theta = (N[qi][qi] - N[pi][pi]) / (2.0 * apq);
+        const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(tt * tt + 1.0), sn = tt * c;
+        for (int k = 0; k < 4; ++k) {  // N <- N J
+          const double nkp = N[k][pi], nkq = N[k][qi];
+          N[k][pi] = c * nkp - sn * nkq;
+          N[k][qi] = sn * nkp + c * nkq;
+        }
+        for (int k = 0; k < 4; ++k) {  // N <- J^T N
+          const double npk = N[pi][k], nqk = N[qi][k];
+          N[pi][k] = c * npk - sn * nqk;
+          N[qi][k] = sn * npk + c * nqk;
+        }
+        for (int k = 0; k < 4; ++k) {
+          const double vkp = V[k][pi], vkq = V[k][qi];
+          V[k][pi] = c * vkp - sn * vkq;
+          V[k][qi] = sn * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+__global__ void __launch_bounds__(128) icp_model_kernel(IcpArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.count) return;
+  const long long g = a.g0 + t;
+  const int cand = (int)(g / a.H), hyp = (int)(g % a.H);
+  const int p0 = a.offsets[cand], n = a.offsets[cand + 1] - p0;
+  if (n < 20) {  // DlsPnpWithRansac.cpp:18-21
+    a.status[t] = -1;
+    return;
+  }
+  int idx[kIcpSample];
+  if (a.samples) {
+    const int* sp = a.samples + ((size_t)cand * a.H + hyp) * kIcpSample;
+    for (int i = 0; i < kIcpSample; ++i) idx[i] = sp[i];
+  } else {
+    sample_indices(a.seed, cand, hyp, n, idx, kIcpSample);
+  }
+  double ma[3] = {0, 0, 0}, mb[3] = {0, 0, 0};
+  for (int i = 0; i < kIcpSample; ++i) {
+    if (idx[i] < 0 || idx[i] >= n) {
+      a.status[t] = -1;
+      return;
+    }
+    idx[i] += p0;
+    for (int c = 0; c < 3; ++c) {
+      ma[c] += a.A[3 * (size_t)idx[i] + c];
+      mb[c] += a.B[3 * (size_t)idx[i] + c];
+    }
+  }
+  for (int c = 0; c < 3; ++c) {
+    ma[c] /= kIcpSample;
+    mb[c] /= kIcpSample;
+  }
+  double Sg[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // Sigma = (1/n) sum (b - mb)(a - ma)^T
+  double var_a = 0.0;
+  for (int i = 0; i < kIcpSample; ++i) {
+    double da[3], db[3];
+    for (int c = 0; c < 3; ++c) {
+      da[c] = a.A[3 * (size_t)idx[i] + c] - ma[c];
+      db[c] = a.B[3 * (size_t)idx[i] + c] - mb[c];
+      var_a += da[c] * da[c];
+    }
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) Sg[r][c] += db[r] * da[c];
+  }
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Sg[r][c] /= kIcpSample;
+  var_a /= kIcpSample;
+  // Horn: S_xy = sum a_x b_y = Sigma^T entries
+  const double Sxx = Sg[0][0], Sxy = Sg[1][0], Sxz = Sg[2][0];
+  const double Syx = Sg[0][1], Syy = Sg[1][1], Syz = Sg[2][1];
+  const double Szx = Sg[0][2], Szy = Sg[1][2], Szz = Sg[2][2];
+  double N[4][4] = {{Sxx + Syy + Szz, Syz - Szy, Szx - Sxz, Sxy - Syx},
+                    {Syz - Szy, Sxx - Syy - Szz, Sxy + Syx, Szx + Sxz},
+                    {Szx - Sxz, Sxy + Syx, -Sxx + Syy - Szz, Syz + Szy},
+                    {Sxy - Syx, Szx + Sxz, Syz + Szy, -Sxx - Syy + Szz}};
+  double V[4][4];
+  jacobi4(N, V);
+  int best = 0;
+  for (int i = 1; i < 4; ++i)
+    if (N[i][i] > N[best][best]) best = i;
+  double qw = V[0][best], qx = V[1][best], qy = V[2][best], qz = V[3][best];
+  const double qn = 1.0 / sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
+  qw *= qn, qx *= qn, qy *= qn, qz *= qn;
+  double R[9];
+  R[0] = 1 - 2 * (qy * qy + qz * qz);
+  R[1] = 2 * (qx * qy - qw * qz);
+  R[2] = 2 * (qx * qz + qw * qy);
+  R[3] = 2 * (qx * qy + qw * qz);
+  R[4] = 1 - 2 * (qx * qx + qz * qz);
+  R[5] = 2 * (qy * qz - qw * qx);
+  R[6] = 2 * (qx * qz - qw * qy);
+  R[7] = 2 * (qy * qz + qw * qx);
+  R[8] = 1 - 2 * (qx * qx + qy * qy);
+  double tr = 0.0;  // trace(R^T Sigma)
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) tr += R[r * 3 + c] * Sg[r][c];
+  const double sc = tr / var_a;
+  double* mo = a.model + (size_t)t * 12;
+  for (int i = 0; i < 9; ++i) mo[i] = R[i];
+  for (int r = 0; r < 3; ++r) mo[9 + r] = mb[r] - sc * (R[r * 3] * ma[0] + R[r * 3 + 1] * ma[1] + R[r * 3 + 2] * ma[2]);
+  const bool okm = isfinite(sc) && sc > 0.0 && fmin(sc, 1.0 / sc) > 0.9;  // DlsPnpWithRansac.h:139
+  a.status[t] = okm ? 1 : 0;
+}
+
+// residual || R a + t - b || over all pairs (DlsPnpWithRansac.h:152-164), MLE cost, inliers
+__global__ void __launch_bounds__(128) icp_score_kernel(const int* __restrict__ offsets, const double* __restrict__ A,
+                                                       const double* __restrict__ B, int H, long long g0, int count,
+                                                       const int* __restrict__ status, const double* __restrict__ model,
+                                                       double thresh, double* __restrict__ cost, int* __restrict__ ninl) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 4 + warp;
+  if (t >= count) return;
+  const long long g = g0 + t;
+  if (status[t] != 1) {
+    if (lane == 0) {
+      cost[g] = CUDART_INF;
+      ninl[g] = -1;
+    }
+    return;
+  }
+  const int cand = (int)(g / H);
+  const int p0 = offsets[cand], n = offsets[cand + 1] - p0;
+  const double* m = model + (size_t)t * 12;
+  double c = 0.0;
+  int ni = 0;
+  for (int i = lane; i < n; i += 32) {
+    const size_t id = (size_t)(p0 + i);
+    const double x = A[3 * id], y = A[3 * id + 1], z = A[3 * id + 2];
+    const double ex = m[0] * x + m[1] * y + m[2] * z + m[9] - B[3 * id];
+    const double ey = m[3] * x + m[4] * y + m[5] * z + m[10] - B[3 * id + 1];
+    const double ez = m[6] * x + m[7] * y + m[8] * z + m[11] - B[3 * id + 2];
+    const double e = sqrt(ex * ex + ey * ey + ez * ez);
+    if (e < thresh) {
+      c += e;
+      ++ni;
+    } else {
+      c += thresh;
+    }
+  }
+  c = warp_sum(c);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) ni += __shfl_xor_sync(FULL, ni, off);
+  if (lane == 0) {
+    cost[g] = c;
+    ninl[g] = ni;
   }
 }
 
@@ -1076,7 +1262,7 @@ int cb_pnp_create(cb_pnp** out, int max_candidates, int max_points_total, int ma
   if (e == cudaSuccess) e = cudaMalloc((void**)&(ptr), (bytes))
   CB_ALLOC(p->offsets, (size_t)(max_candidates + 1) * sizeof(int));
   CB_ALLOC(p->X, (size_t)max_points_total * 3 * sizeof(double));
-  CB_ALLOC(p->uv, (size_t)max_points_total * 2 * sizeof(double));
+  CB_ALLOC(p->uv, (size_t)max_points_total * 3 * sizeof(double));  // 2 per point for PnP, 3 for the 3D-3D variant
   CB_ALLOC(p->cost, all * sizeof(double));
   CB_ALLOC(p->ninl, all * sizeof(int));
   CB_ALLOC(p->model, all * 12 * sizeof(double));
@@ -1136,6 +1322,7 @@ int cb_pnp_solve_batch_device(cb_pnp* p, int n_cand, const int32_t* offsets_dev,
   sa.ninl = p->ninl;
   sa.model = p->model;
   sa.p = *params;
+  sa.sample_size = kSample;
   sa.c_T_w = c_T_w_dev;
   sa.confidence = confidence_dev;
   sa.num_iterations = num_iterations_dev;
@@ -1184,6 +1371,97 @@ int cb_pnp_solve_batch(cb_pnp* p, int n_cand, const int32_t* offsets, const doub
     CB_CUDA(cudaMemcpyAsync(n_inliers, oi + p->max_cand, (size_t)n_cand * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (best_hyp)
     CB_CUDA(cudaMemcpyAsync(best_hyp, oi + 2 * p->max_cand, (size_t)n_cand * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  return CB_OK;
+}
+
+int cb_pnp_icp_batch_device(cb_pnp* p, int n_cand, const int32_t* offsets_dev, const double* A_dev, const double* B_dev,
+                            const cb_ransac_params* params, const int32_t* samples_dev, double* b_T_a_dev,
+                            float* confidence_dev, int32_t* num_iterations_dev, int32_t* n_inliers_dev,
+                            int32_t* best_hyp_dev, void* stream) {
+  if (!p || !offsets_dev || !A_dev || !B_dev || !params || !b_T_a_dev || !confidence_dev)
+    return cb::fail(CB_EINVAL, "NULL argument to cb_pnp_icp_batch_device");
+  if (n_cand < 1 || n_cand > p->max_cand) return cb::fail(CB_EINVAL, "n_cand %d outside [1,%d]", n_cand, p->max_cand);
+  const int H = params->max_iterations;
+  if (H < 1 || H > p->max_hyp) return cb::fail(CB_EINVAL, "max_iterations %d outside [1,%d]", H, p->max_hyp);
+  if (!params->use_mle) return cb::fail(CB_EINVAL, "only use_mle=1 (the reference's setting) is implemented");
+  cb::DeviceGuard g(p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)n_cand * H;
+  for (long long g0 = 0; g0 < total; g0 += p->chunk) {
+    const int count = (int)((total - g0) < p->chunk ? (total - g0) : p->chunk);
+    IcpArgs ia;
+    ia.offsets = offsets_dev;
+    ia.A = A_dev;
+    ia.B = B_dev;
+    ia.samples = samples_dev;
+    ia.seed = params->seed;
+    ia.H = H;
+    ia.g0 = g0;
+    ia.count = count;
+    ia.status = p->status;
+    ia.model = p->cmodel;
+    icp_model_kernel<<<(count + 127) / 128, 128, 0, st>>>(ia);
+    CB_LAUNCH_CHECK();
+    icp_score_kernel<<<(count + 3) / 4, 128, 0, st>>>(offsets_dev, A_dev, B_dev, H, g0, count, p->status, p->cmodel,
+                                                      params->error_thresh, p->cost, p->ninl);
+    CB_LAUNCH_CHECK();
+    copy_models_kernel<<<(count * 12 + 255) / 256, 256, 0, st>>>(p->cmodel, p->status, g0, count, p->model);
+    CB_LAUNCH_CHECK();
+  }
+  SelectArgs sa;
+  sa.offsets = offsets_dev;
+  sa.n_cand = n_cand;
+  sa.H = H;
+  sa.cost = p->cost;
+  sa.ninl = p->ninl;
+  sa.model = p->model;
+  sa.p = *params;
+  sa.sample_size = kIcpSample;
+  sa.c_T_w = b_T_a_dev;
+  sa.confidence = confidence_dev;
+  sa.num_iterations = num_iterations_dev;
+  sa.n_inliers = n_inliers_dev;
+  sa.best_hyp = best_hyp_dev;
+  pnp_select_kernel<<<n_cand, 32, 0, st>>>(sa);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+int cb_pnp_icp_batch(cb_pnp* p, int n_cand, const int32_t* offsets, const double* A, const double* B,
+                     const cb_ransac_params* params, const int32_t* samples, double* b_T_a, float* confidence,
+                     int32_t* num_iterations, int32_t* n_inliers, int32_t* best_hyp) {
+  if (!p || !offsets || !A || !B || !params || !b_T_a || !confidence) return cb::fail(CB_EINVAL, "NULL argument to cb_pnp_icp_batch");
+  if (n_cand < 1 || n_cand > p->max_cand) return cb::fail(CB_EINVAL, "n_cand %d outside [1,%d]", n_cand, p->max_cand);
+  const int total = offsets[n_cand];
+  if (total < 0 || total > p->max_points) return cb::fail(CB_EINVAL, "total points %d outside [0,%d]", total, p->max_points);
+  cb::DeviceGuard g(p->device);
+  cudaStream_t st = p->stream;
+  CB_CUDA(cudaMemcpyAsync(p->offsets, offsets, (size_t)(n_cand + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(p->X, A, (size_t)total * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(p->uv, B, (size_t)total * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+  const int* samples_dev = nullptr;
+  if (samples) {
+    const size_t ne = (size_t)n_cand * params->max_iterations * kIcpSample;
+    if (p->samples_elems < ne) {
+      if (p->samples) cudaFree(p->samples);
+      p->samples = nullptr;
+      p->samples_elems = 0;
+      CB_CUDA(cudaMalloc((void**)&p->samples, ne * sizeof(int)));
+      p->samples_elems = ne;
+    }
+    CB_CUDA(cudaMemcpyAsync(p->samples, samples, ne * sizeof(int), cudaMemcpyHostToDevice, st));
+    samples_dev = p->samples;
+  }
+  int* oi = p->out_i;
+  int rc = cb_pnp_icp_batch_device(p, n_cand, p->offsets, p->X, p->uv, params, samples_dev, p->out_T, p->out_conf, oi,
+                                   oi + p->max_cand, oi + 2 * p->max_cand, st);
+  if (rc) return rc;
+  CB_CUDA(cudaMemcpyAsync(b_T_a, p->out_T, (size_t)n_cand * 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(confidence, p->out_conf, (size_t)n_cand * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (num_iterations) CB_CUDA(cudaMemcpyAsync(num_iterations, oi, (size_t)n_cand * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (n_inliers) CB_CUDA(cudaMemcpyAsync(n_inliers, oi + p->max_cand, (size_t)n_cand * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (best_hyp) CB_CUDA(cudaMemcpyAsync(best_hyp, oi + 2 * p->max_cand, (size_t)n_cand * sizeof(int), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
   return CB_OK;
 }

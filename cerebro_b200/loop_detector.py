@@ -34,6 +34,64 @@ class LoopEdge:
         self.description = description
 
 
+def R2ypr(R: np.ndarray) -> np.ndarray:
+    """PoseManipUtils::R2ypr (src/utils/PoseManipUtils.cpp:148-163): yaw, pitch, roll in DEGREES."""
+    import math
+
+    n, o, a = R[:, 0], R[:, 1], R[:, 2]
+    y = math.atan2(n[1], n[0])
+    p = math.atan2(-n[2], n[0] * math.cos(y) + n[1] * math.sin(y))
+    r = math.atan2(a[0] * math.sin(y) - a[1] * math.cos(y), -o[0] * math.sin(y) + o[1] * math.cos(y))
+    return np.array([y, p, r]) * (180.0 / math.pi)
+
+
+class ProcessedLoopCandidate:
+    """The slice of src/ProcessedLoopCandidate.{h,cpp} that consumes the verifier's output: the three poses
+    (Option A PnP, Option B PnP with roles swapped and inverted, Option C 3D-3D ICP), their goodness values
+    and the decision whether a LoopEdge is published."""
+
+    def __init__(self, idx_from_raw_candidates_list, t_1, t_2, idx_1=-1, idx_2=-1):
+        self.idx_from_raw_candidates_list = idx_from_raw_candidates_list
+        self.t_1, self.t_2 = t_1, t_2  # node_1->getT(), node_2->getT() in seconds
+        self.idx_from_datamanager_1, self.idx_from_datamanager_2 = idx_1, idx_2
+        self.opX_b_T_a = []
+        self.opX_goodness = []
+        self.pf_matches = 0
+        self.isSet_3d2d__2T1 = False
+        self._3d2d__2T1 = None
+        self._3d2d__2T1__ransac_confidence = 0.0
+
+    def makeLoopEdgeMsg(self):  # ProcessedLoopCandidate.cpp:16-36
+        if not self.isSet_3d2d__2T1:
+            return None
+        desc = "%d<=>%d    this pose is: %d_T_%d" % (
+            self.idx_from_datamanager_1, self.idx_from_datamanager_2, self.idx_from_datamanager_2, self.idx_from_datamanager_1)
+        return LoopEdge(self.t_1, self.t_2, self._3d2d__2T1, self._3d2d__2T1__ransac_confidence, desc)
+
+    def makeLoopEdgeMsgWithConsistencyCheck(self):  # ProcessedLoopCandidate.cpp:40-125
+        if len(self.opX_b_T_a) != 3:
+            return None
+        if abs(int(self.t_1 - self.t_2)) < 10:  # :49-56, ros::Duration::sec
+            return None
+        op1, op2, icp = self.opX_b_T_a
+        op1_m_op2 = np.linalg.inv(op1) @ op2
+        op1_m_icp = np.linalg.inv(op1) @ icp
+        op2_m_icp = np.linalg.inv(op2) @ icp
+        is_consistent_ypr = (
+            np.abs(R2ypr(op1_m_op2[:3, :3])).max() < 5.0
+            and np.abs(R2ypr(op1_m_icp[:3, :3])).max() < 5.0
+            and np.abs(R2ypr(op2_m_icp[:3, :3])).max() < 5.0
+        )  # :77-81
+        # :83-87 -- the reference tests op1-icp twice and never the op1-op2 translation; kept as is
+        is_consistent_tr = np.abs(op1_m_icp[:3, 3]).max() < 0.2 and np.abs(op1_m_icp[:3, 3]).max() < 0.2 and np.abs(op2_m_icp[:3, 3]).max() < 0.2
+        if self.pf_matches > 800 and is_consistent_ypr and is_consistent_tr:  # :110
+            self._3d2d__2T1 = self.opX_b_T_a[0]
+            self.isSet_3d2d__2T1 = True
+            self._3d2d__2T1__ransac_confidence = max(self.opX_goodness)
+            return self.makeLoopEdgeMsg()
+        return None
+
+
 class Cerebro:
     LOCALITY_THRESH = 12  # Cerebro.cpp:912
     DOT_PROD_THRESH = 0.85  # Cerebro.cpp:913

@@ -92,6 +92,31 @@ class PnpBatch:
         )
         return out
 
+    def icp(self, A_list, B_list, params: RansacParams | None = None, samples=None):
+        """Batched StaticTheiaPoseCompute::P3P_ICP: A_list[c], B_list[c] are [n_c,3] float64 (the same
+        points in frames a and b).  Returns the same dict as ``solve`` (T = b_T_a)."""
+        params = params or default_params(error_thresh=0.1)  # DlsPnpWithRansac.cpp:89
+        n_cand = len(A_list)
+        offsets = np.zeros(n_cand + 1, dtype=np.int32)
+        offsets[1:] = np.cumsum([len(x) for x in A_list])
+        A = np.ascontiguousarray(np.concatenate(A_list, axis=0), dtype=np.float64).reshape(-1, 3)
+        B = np.ascontiguousarray(np.concatenate(B_list, axis=0), dtype=np.float64).reshape(-1, 3)
+        if samples is not None:
+            samples = np.ascontiguousarray(samples, dtype=np.int32)
+            assert samples.shape == (n_cand, params.max_iterations, 10)
+        T = np.empty((n_cand, 4, 4), dtype=np.float64)
+        conf = np.empty(n_cand, dtype=np.float32)
+        nit = np.empty(n_cand, dtype=np.int32)
+        ninl = np.empty(n_cand, dtype=np.int32)
+        bh = np.empty(n_cand, dtype=np.int32)
+        check(
+            self._lib.cb_pnp_icp_batch(
+                self._h, n_cand, ptr(offsets), ptr(A), ptr(B), C.byref(params), ptr(samples), ptr(T), ptr(conf), ptr(nit),
+                ptr(ninl), ptr(bh),
+            )
+        )
+        return dict(T=T, confidence=conf, num_iterations=nit, n_inliers=ninl, best_hyp=bh)
+
     def dls_minimal(self, X_sets: np.ndarray, uv_sets: np.ndarray):
         """theia::DlsPnp on sets of exactly 15 points: X_sets [s,15,3], uv_sets [s,15,2].
         Returns (n_solutions [s], R [s,27,3,3], t [s,27,3])."""
@@ -128,4 +153,20 @@ class StaticTheiaPoseCompute:
                 "DlsPnpWithRansac (best_rel_pose.b_T_a): %s;    num_iterations=%d  confidence=%f"
                 % (np.array2string(r["T"][0], precision=6), int(r["num_iterations"][0]), float(r["confidence"][0]))
             )
+        return float(r["confidence"][0])
+
+    @classmethod
+    def P3P_ICP(cls, uv_X, uvd_Y, uvd_T_uv: np.ndarray, p3p__msg: list | None = None, params=None, samples=None) -> float:
+        """src/DlsPnpWithRansac.cpp:16-122: 3D-3D alignment (Umeyama) with RANSAC.  uv_X, uvd_Y: n x 3; the
+        4x4 ``uvd_T_uv`` is overwritten; returns summary.confidence, or -1 for fewer than 20 points (:18-21)."""
+        a = np.asarray(uv_X, dtype=np.float64).reshape(-1, 3)
+        b = np.asarray(uvd_Y, dtype=np.float64).reshape(-1, 3)
+        if a.shape[0] < 20:
+            return -1.0
+        if cls._batch is None:
+            cls._batch = PnpBatch(max_candidates=1, max_points_total=20000, max_hypotheses=4096)
+        r = cls._batch.icp([a], [b], params, None if samples is None else np.asarray(samples)[None])
+        uvd_T_uv[...] = r["T"][0]
+        if p3p__msg is not None:
+            p3p__msg.append("ICP Ransac;     #iterations=%d    confidence=%f" % (int(r["num_iterations"][0]), float(r["confidence"][0])))
         return float(r["confidence"][0])

@@ -213,6 +213,19 @@ CB_API int cb_pnp_solve_batch_device(cb_pnp* p, int n_cand, const int32_t* offse
                               int32_t* num_iterations_dev, int32_t* n_inliers_dev,
                               int32_t* best_hyp_dev, void* stream);
 
+/* StaticTheiaPoseCompute::P3P_ICP (src/DlsPnpWithRansac.cpp:16-122): RANSAC over
+ * AlignPointCloudsUmeyamaWithRansac (src/DlsPnpWithRansac.h:117-166; SampleSize 10, model accepted iff
+ * min(s,1/s) > 0.9, Error = ||R a + t - b||).  A, B [total][3] fp64: the same points in frames a and b.
+ * The caller sets params->error_thresh = 0.1 (DlsPnpWithRansac.cpp:89).  samples: NULL or
+ * int32 [n_cand][max_iterations][10].  Outputs as cb_pnp_solve_batch (b_T_a row-major 4x4). */
+CB_API int cb_pnp_icp_batch(cb_pnp* p, int n_cand, const int32_t* offsets, const double* A, const double* B,
+                     const cb_ransac_params* params, const int32_t* samples, double* b_T_a,
+                     float* confidence, int32_t* num_iterations, int32_t* n_inliers, int32_t* best_hyp);
+CB_API int cb_pnp_icp_batch_device(cb_pnp* p, int n_cand, const int32_t* offsets_dev, const double* A_dev,
+                            const double* B_dev, const cb_ransac_params* params, const int32_t* samples_dev,
+                            double* b_T_a_dev, float* confidence_dev, int32_t* num_iterations_dev,
+                            int32_t* n_inliers_dev, int32_t* best_hyp_dev, void* stream);
+
 /* Minimal solver only (theia::DlsPnp as called at DlsPnpWithRansac.h:61) for n_sets sets of
  * exactly `m` points: up to 27 solutions per set.  n_solutions [n_sets]; R [n_sets][27][9]
  * row-major, t [n_sets][27][3].  For parity tests of the solver. */
