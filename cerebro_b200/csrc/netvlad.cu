@@ -888,6 +888,106 @@ __global__ void __launch_bounds__(256) vlad_assign_kernel(const __half* __restri
   }
 }
 
+// soft-assignment on tcgen05: s = x W + b as a GEMM [pixels x D] x [D x 16] (W split hi + lo, two accumulating
+// MMAs per K step), epilogue = bias + softmax over the 16 clusters straight out of TMEM.
+__global__ void __launch_bounds__(kGemmThreads) vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                     const __grid_constant__ CUtensorMap tmWhi,
+                                                                     const __grid_constant__ CUtensorMap tmWlo,
+                                                                     const float* __restrict__ bvec, float* __restrict__ a_out,
+                                                                     int P_total, int D) {
+  constexpr int kA = 128 * 64 * 2, kB = 16 * 64 * 2, kStage = kA + 2 * kB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStage);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  const int nkb = D / 64;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmWhi);
+    tma_prefetch_desc(&tmWlo);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1);
+        mbar_expect_tx(&full_bar[s], kStage);
+        uint8_t* sa = smem + s * kStage;
+        tma_load_2d(&tmX, &full_bar[s], sa, kb * 64, m0);
+        tma_load_2d(&tmWhi, &full_bar[s], sa + kA, kb * 64, 0);
+        tma_load_2d(&tmWlo, &full_bar[s], sa + kA + kB, kb * 64, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(&full_bar[s], (kb / kStages) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * kStage);
+#pragma unroll
+        for (int hl = 0; hl < 2; ++hl) {
+          const uint32_t b_addr = a_addr + kA + hl * kB;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base, make_kmajor_desc<128>(a_addr + k * 32), make_kmajor_desc<128>(b_addr + k * 32), idesc,
+                     (kb | hl | k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = m0 + q * 32 + lane;
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v);
+    if (row < P_total) {
+      float sv[kK];
+      float mx = -3.0e38f;
+#pragma unroll
+      for (int k = 0; k < kK; ++k) {
+        sv[k] = __uint_as_float(v[k]) + __ldg(bvec + k);
+        mx = fmaxf(mx, sv[k]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < kK; ++k) {
+        sv[k] = expf(sv[k] - mx);
+        sum += sv[k];
+      }
+      const float inv = 1.f / sum;
+      float4* o = reinterpret_cast<float4*>(a_out + (size_t)row * kK);
+#pragma unroll
+      for (int k = 0; k < kK; k += 4) o[k / 4] = make_float4(sv[k] * inv, sv[k + 1] * inv, sv[k + 2] * inv, sv[k + 3] * inv);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
 // grid (D/64, frames): V[k][d] = sum_p a[p][k] (x[p][d] + C[d][k]) for a 64-wide d slice
 __global__ void __launch_bounds__(256) vlad_aggregate_kernel(const __half* __restrict__ x, const float* __restrict__ a,
                                                             int P, int D, const float* __restrict__ Cc /*[D][16]*/,
@@ -999,6 +1099,10 @@ struct cb_descriptor {
   float* vlad_w = nullptr;
   float* vlad_b = nullptr;
   float* vlad_c = nullptr;
+  __half* vlad_whi = nullptr;  // [16][D] K-major hi/lo split of the soft-assignment weights (tcgen05 path)
+  __half* vlad_wlo = nullptr;
+  CUtensorMap tmX[2], tmWhi, tmWlo;
+  bool vlad_tc = false;
   __half* act[2] = {nullptr, nullptr};
   size_t act_elems = 0;
   float* assign = nullptr;
@@ -1142,9 +1246,17 @@ int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cud
   }
   const int P = d->Hf * d->Wf;
   const long long Ptot = (long long)n * P;
-  vlad_assign_kernel<<<(unsigned)((Ptot + 7) / 8), 256, (size_t)d->D * kK * sizeof(float), st>>>(
-      d->act[cur], Ptot, d->D, d->vlad_w, d->vlad_b, d->assign);
-  CB_LAUNCH_CHECK();
+  if (d->vlad_tc && !d->force_simt && !d->no_fuse) {
+    constexpr int kSm = kStages * (128 * 64 * 2 + 2 * 16 * 64 * 2) + 1024 + 64;
+    CB_CUDA(cudaFuncSetAttribute(vlad_assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));
+    vlad_assign_tc_kernel<<<(unsigned)((Ptot + 127) / 128), kGemmThreads, kSm, st>>>(d->tmX[cur], d->tmWhi, d->tmWlo, d->vlad_b,
+                                                                                  d->assign, (int)Ptot, d->D);
+    CB_LAUNCH_CHECK();
+  } else {
+    vlad_assign_kernel<<<(unsigned)((Ptot + 7) / 8), 256, (size_t)d->D * kK * sizeof(float), st>>>(
+        d->act[cur], Ptot, d->D, d->vlad_w, d->vlad_b, d->assign);
+    CB_LAUNCH_CHECK();
+  }
   vlad_aggregate_kernel<<<dim3(d->D / 64, n), 256, 0, st>>>(d->act[cur], d->assign, P, d->D, d->vlad_c, d->Vraw);
   CB_LAUNCH_CHECK();
   vlad_norm_kernel<<<n, 512, 0, st>>>(d->Vraw, d->D, out_dev);
@@ -1256,6 +1368,27 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
   if (!rc) rc = upload_f32(&d->vlad_w, w->vlad_w, (size_t)d->D * kK);
   if (!rc) rc = upload_f32(&d->vlad_b, w->vlad_b, kK);
   if (!rc) rc = upload_f32(&d->vlad_c, w->vlad_c, (size_t)d->D * kK);
+  if (!rc && d->D % 64 == 0) {
+    std::vector<__half> hi((size_t)kK * d->D), lo((size_t)kK * d->D);
+    for (int dd = 0; dd < d->D; ++dd)
+      for (int k = 0; k < kK; ++k) {
+        const float v = w->vlad_w[(size_t)dd * kK + k];
+        const __half h = __float2half_rn(v);
+        hi[(size_t)k * d->D + dd] = h;
+        lo[(size_t)k * d->D + dd] = __float2half_rn(v - __half2float(h));
+      }
+    cudaError_t e3 = cudaMalloc((void**)&d->vlad_whi, hi.size() * sizeof(__half));
+    if (e3 == cudaSuccess) e3 = cudaMalloc((void**)&d->vlad_wlo, lo.size() * sizeof(__half));
+    if (e3 == cudaSuccess) e3 = cudaMemcpy(d->vlad_whi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e3 == cudaSuccess) e3 = cudaMemcpy(d->vlad_wlo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e3 != cudaSuccess) rc = cb::fail(CB_ENOMEM, "VLAD weight upload failed: %s", cudaGetErrorString(e3));
+    const uint64_t Pmax = (uint64_t)max_batch * d->Hf * d->Wf;
+    if (!rc) rc = make_map_2d(&d->tmX[0], d->act[0], Pmax, (uint64_t)d->D, 128, 64);
+    if (!rc) rc = make_map_2d(&d->tmX[1], d->act[1], Pmax, (uint64_t)d->D, 128, 64);
+    if (!rc) rc = make_map_2d(&d->tmWhi, d->vlad_whi, (uint64_t)kK, (uint64_t)d->D, kK, 64);
+    if (!rc) rc = make_map_2d(&d->tmWlo, d->vlad_wlo, (uint64_t)kK, (uint64_t)d->D, kK, 64);
+    d->vlad_tc = !rc;
+  }
   for (size_t i = 0; i < d->blocks.size() && !rc; ++i) {
     Block& b = d->blocks[i];
     rc = upload_f32(&b.dw_w, w->dw_w[i], (size_t)9 * b.C);
@@ -1303,7 +1436,7 @@ int cb_descriptor_destroy(cb_descriptor* d) {
     cudaFree(b.pw_w);
     cudaFree(b.pw_b);
   }
-  void* ptrs[] = {d->conv1_hi, d->conv1_lo, d->conv1_w, d->conv1_b, d->vlad_w, d->vlad_b, d->vlad_c, d->act[0], d->act[1],
+  void* ptrs[] = {d->vlad_whi, d->vlad_wlo, d->conv1_hi, d->conv1_lo, d->conv1_w, d->conv1_b, d->vlad_w, d->vlad_b, d->vlad_c, d->act[0], d->act[1],
                   d->assign,  d->Vraw,    d->img_dev, d->out_dev};
   for (void* p : ptrs)
     if (p) cudaFree(p);

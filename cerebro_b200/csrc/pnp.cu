@@ -558,10 +558,7 @@ __device__ bool warp_hqr(double* a, double* wr, double* wi, int lane) {
         p = (rr * ss - w) / a[(m + 1) * n + m] + a[m * n + m + 1];
         q = a[(m + 1) * n + m + 1] - z - rr - ss;
         r = a[(m + 2) * n + m + 1];
-        const double s = fabs(p) + fabs(q) + fabs(r);
-        p /= s;
-        q /= s;
-        r /= s;
+        // the deflation test below is invariant to a common scale of (p,q,r): normalise after selection
         if (m == l) {
           ok = true;
         } else {
@@ -575,6 +572,12 @@ __device__ bool warp_hqr(double* a, double* wr, double* wi, int lane) {
       p = __shfl_sync(FULL, p, m);
       q = __shfl_sync(FULL, q, m);
       r = __shfl_sync(FULL, r, m);
+      {
+        const double inv = 1.0 / (fabs(p) + fabs(q) + fabs(r));
+        p *= inv;
+        q *= inv;
+        r *= inv;
+      }
       // clear the entries below the sub-diagonal in the active window
       if (lane >= m + 2 && lane <= nn) {
         a[lane * n + lane - 2] = 0.0;
@@ -589,9 +592,10 @@ __device__ bool warp_hqr(double* a, double* wr, double* wi, int lane) {
           r = (k != nn - 1) ? a[(k + 2) * n + k - 1] : 0.0;
           x = fabs(p) + fabs(q) + fabs(r);
           if (x != 0.0) {
-            p /= x;
-            q /= x;
-            r /= x;
+            const double ix = 1.0 / x;
+            p *= ix;
+            q *= ix;
+            r *= ix;
           }
         }
         double s = sqrt(p * p + q * q + r * r);
@@ -606,11 +610,12 @@ __device__ bool warp_hqr(double* a, double* wr, double* wi, int lane) {
             }
           }
           p += s;
-          x = p / s;
-          y = q / s;
-          const double z = r / s;
-          q /= p;
-          r /= p;
+          const double is = 1.0 / s, ip = 1.0 / p;
+          x = p * is;
+          y = q * is;
+          const double z = r * is;
+          q *= ip;
+          r *= ip;
           const bool three = (k != nn - 1);
           // row modification: lane = column j in [k, nn]
           if (lane >= k && lane <= nn) {
@@ -688,8 +693,9 @@ __device__ double warp_null_vector(const double* A, double* B, double lam, int l
     }
     __syncwarp();
     // lane = row i > k
+    const double ipiv = 1.0 / piv;
     if (lane > k && lane < n) {
-      const double f = B[lane * n + k] / piv;
+      const double f = B[lane * n + k] * ipiv;
       for (int c = k + 1; c < n; ++c) B[lane * n + c] = fma(-f, B[k * n + c], B[lane * n + c]);
     }
     __syncwarp();
