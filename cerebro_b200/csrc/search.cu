@@ -30,7 +30,7 @@ using cb::FULL;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kList = 32;          // candidates carried per list (one per lane)
-constexpr int kChunkRows = 2048;   // rows per top-k chunk CTA (8 rows per thread, loaded up front)
+constexpr int kChunkRows = 8192;   // rows per top-k chunk CTA (32 rows per thread, fetched 8 at a time)
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 v;
@@ -68,7 +68,7 @@ template <int QT, int R>
 __global__ void __launch_bounds__(kThreads, (QT * R >= 64 ? 1 : 2))
 scores_kernel(const float* __restrict__ rows, long long n_rows, int d, int ds, int n_slices,
               const float* __restrict__ xq, int nq_valid, float* __restrict__ partial,
-              long long pstride) {
+              long long pstride, int* __restrict__ work_counter) {
   extern __shared__ float4 sq[];  // [QT][ds/4]
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -90,9 +90,25 @@ scores_kernel(const float* __restrict__ rows, long long n_rows, int d, int ds, i
   const long long n_blocks = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
   const int nj = ds >> 7;  // 128-float segments per slice
 
-  for (long long rb = group; rb < n_blocks; rb += n_groups) {
-    const long long r0 = rb * kRowsPerCta + (long long)warp * R;
-    if (r0 >= n_rows) continue;  // warp-uniform
+  // Row groups of R rows are handed to warps either statically (strided over the grid) or, when a work counter is
+  // given (small query tiles: pure streaming, where a ragged last wave costs up to 1/n_waves), dynamically by
+  // atomic ticket so that every warp stays busy until the database is exhausted.
+  const long long n_items = (n_rows + R - 1) / R;
+  long long rb = group;
+  for (;;) {
+    long long r0;
+    if (work_counter) {
+      long long it = 0;
+      if (lane == 0) it = atomicAdd(&work_counter[slice], 1);
+      it = __shfl_sync(FULL, it, 0);
+      if (it >= n_items) break;
+      r0 = it * R;
+    } else {
+      if (rb >= n_blocks) break;
+      r0 = rb * kRowsPerCta + (long long)warp * R;
+      rb += n_groups;
+      if (r0 >= n_rows) continue;  // warp-uniform
+    }
     float acc[R * QT];
 #pragma unroll
     for (int i = 0; i < R * QT; ++i) acc[i] = 0.f;
@@ -192,28 +208,57 @@ struct WarpList {
     s = neg_inf<S>();
     id = -1;
   }
-  // every lane offers one candidate (cs, cid); `valid` false lanes are skipped
+  // every lane offers one candidate (cs, cid); `valid` false lanes are skipped.
+  // Data-independent cost: if any candidate beats the current 32nd best, the batch of 32 is sorted with a
+  // bitonic network across the lanes (15 compare-exchange steps), merged with the sorted list (element-wise
+  // best of list[i] and batch[31-i] is the top 32 of the union, as a bitonic sequence) and re-sorted (5 steps).
   __device__ __forceinline__ void offer(S cs, long long cid, bool valid, int tie_high, int lane) {
-    S ts = __shfl_sync(FULL, s, 31);
-    long long tid_ = __shfl_sync(FULL, id, 31);
-    unsigned m = __ballot_sync(FULL, valid && better<S>(cs, cid, ts, tid_, tie_high));
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const S bs = __shfl_sync(FULL, cs, src);
-      const long long bid = __shfl_sync(FULL, cid, src);
-      const bool b = better<S>(bs, bid, s, id, tie_high);
-      const unsigned bm = __ballot_sync(FULL, b);
-      const S us = __shfl_up_sync(FULL, s, 1);
-      const long long uid = __shfl_up_sync(FULL, id, 1);
-      if (b) {
-        if (lane == __ffs(bm) - 1) {
-          s = bs;
-          id = bid;
-        } else {
-          s = us;
-          id = uid;
+    const S ts = __shfl_sync(FULL, s, 31);
+    const long long tid_ = __shfl_sync(FULL, id, 31);
+    const bool cand = valid && better<S>(cs, cid, ts, tid_, tie_high);
+    if (!__ballot_sync(FULL, cand)) return;
+    if (!cand) {
+      cs = neg_inf<S>();
+      cid = -1;
+    }
+    // bitonic sort of the batch, descending by `better`
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j >= 1; j >>= 1) {
+        const S os = __shfl_xor_sync(FULL, cs, j);
+        const long long oid = __shfl_xor_sync(FULL, cid, j);
+        const bool lower = (lane & j) == 0;          // this lane holds the lower index of the pair
+        const bool desc = (lane & k) == 0;           // direction of this sub-sequence
+        const bool ob = better<S>(os, oid, cs, cid, tie_high);  // partner beats mine
+        // lower index keeps the better element when descending, the worse one when ascending
+        const bool take = (lower == desc) ? ob : (!ob && !(os == cs && oid == cid));
+        if (take) {
+          cs = os;
+          cid = oid;
         }
+      }
+    }
+    // merge: top 32 of (list, batch) = element-wise best of list[i] and batch[31 - i]
+    {
+      const S rs = __shfl_sync(FULL, cs, 31 - lane);
+      const long long rid = __shfl_sync(FULL, cid, 31 - lane);
+      if (better<S>(rs, rid, s, id, tie_high)) {
+        s = rs;
+        id = rid;
+      }
+    }
+    // the result is bitonic: one merge pass sorts it descending
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+      const S os = __shfl_xor_sync(FULL, s, j);
+      const long long oid = __shfl_xor_sync(FULL, id, j);
+      const bool lower = (lane & j) == 0;
+      const bool ob = better<S>(os, oid, s, id, tie_high);
+      const bool take = lower ? ob : (!ob && !(os == s && oid == id));
+      if (take) {
+        s = os;
+        id = oid;
       }
     }
   }
@@ -235,22 +280,25 @@ topk_chunk_kernel(const float* __restrict__ partial, int n_slices, int qt_stride
   wl.init();
   const float* base = partial + (size_t)q * pstride;
   const size_t sstride = (size_t)qt_stride * pstride;
-  // all of this thread's rows are fetched before the (warp-collective, serialising) insertion loop
+  // this thread's rows are fetched 8 at a time ahead of the warp-collective merges
   constexpr int kPer = kChunkRows / kThreads;
-  float v[kPer];
+#pragma unroll 1
+  for (int j0 = 0; j0 < kPer; j0 += 8) {
+    float v[8];
 #pragma unroll
-  for (int j = 0; j < kPer; ++j) {
-    const long long r = r_begin + tid + (long long)j * kThreads;
-    float a = 0.f;
-    if (r < r_end) {
-      for (int s = 0; s < n_slices; ++s) a += base[s * sstride + r];
+    for (int j = 0; j < 8; ++j) {
+      const long long r = r_begin + tid + (long long)(j0 + j) * kThreads;
+      float a = 0.f;
+      if (r < r_end) {
+        for (int s = 0; s < n_slices; ++s) a += base[s * sstride + r];
+      }
+      v[j] = a;
     }
-    v[j] = a;
-  }
 #pragma unroll
-  for (int j = 0; j < kPer; ++j) {
-    const long long r = r_begin + tid + (long long)j * kThreads;
-    wl.offer(v[j], r * world + rank, r < r_end, tie_high, lane);
+    for (int j = 0; j < 8; ++j) {
+      const long long r = r_begin + tid + (long long)(j0 + j) * kThreads;
+      wl.offer(v[j], r * world + rank, r < r_end, tie_high, lane);
+    }
   }
   ss[warp * kList + lane] = wl.s;
   sl[warp * kList + lane] = wl.id;
@@ -385,11 +433,11 @@ __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restri
 template <int QT, int R>
 cudaError_t launch_scores(int grid, size_t smem, cudaStream_t st, const float* rows, long long n_rows,
                           int d, int ds, int n_slices, const float* xq, int nq_valid, float* partial,
-                          long long pstride) {
+                          long long pstride, int* work_counter) {
   auto kern = scores_kernel<QT, R>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kThreads, smem, st>>>(rows, n_rows, d, ds, n_slices, xq, nq_valid, partial, pstride);
+  kern<<<grid, kThreads, smem, st>>>(rows, n_rows, d, ds, n_slices, xq, nq_valid, partial, pstride, work_counter);
   return cudaGetLastError();
 }
 
@@ -419,6 +467,7 @@ struct cb_index {
   void* stage = nullptr;  // add staging
   size_t stage_bytes = 0;
   int max_qt = 16;
+  int* work_counter = nullptr;
   // optional device-side timing of the sweep kernel (bench.py roofline)
   bool timing = false;
   cudaEvent_t ev[2 * 64] = {};
@@ -510,11 +559,17 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
     }
     const float* xq = xq_dev + (size_t)q0 * ix->d;
     cudaError_t e = cudaSuccess;
+    int* wc = nullptr;
+    if (p.qt <= 4) {  // streaming regime: dynamic row-group tickets (one counter per d-slice)
+      if (!ix->work_counter) CB_CUDA(cudaMalloc((void**)&ix->work_counter, 16 * sizeof(int)));
+      CB_CUDA(cudaMemsetAsync(ix->work_counter, 0, 16 * sizeof(int), st));
+      wc = ix->work_counter;
+    }
     const bool rec = ix->timing && ix->ev_used < 64;
     if (rec) cudaEventRecord(ix->ev[2 * ix->ev_used], st);
 #define CB_SWEEP(QT, R)                                                                          \
   e = launch_scores<QT, R>(p.grid, p.smem, st, ix->rows, n_rows, ix->d, p.ds, p.n_slices, xq,    \
-                           nq_valid, ix->partial, pstride)
+                           nq_valid, ix->partial, pstride, wc)
     switch (p.qt) {
       case 1: CB_SWEEP(1, 8); break;
       case 2: CB_SWEEP(2, 8); break;
@@ -589,6 +644,7 @@ int cb_index_destroy(cb_index* ix) {
   cudaFree(ix->out_s);
   cudaFree(ix->out_l);
   cudaFree(ix->stage);
+  cudaFree(ix->work_counter);
   for (cudaEvent_t ev : ix->ev)
     if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ix->stream);
