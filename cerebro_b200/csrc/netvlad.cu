@@ -615,18 +615,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dwpw_kernel(const __half* __
           }
         }
 #pragma unroll
-        for (int u = 0; u < PASSES; ++u) {
-          // all nine taps of this pixel are requested before any of them is consumed (9 loads in flight)
-          uint4 raw[9];
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(dw_w + t9 * CIN + ch0));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(dw_w + t9 * CIN + ch0 + 4));
+          uint4 raw[PASSES];
 #pragma unroll
-          for (int t9 = 0; t9 < 9; ++t9)
-            raw[t9] = ((vmask[u] >> t9) & 1u) ? *reinterpret_cast<const uint4*>(pb[u] + tap_off[t9] + ch0)
+          for (int u = 0; u < PASSES; ++u)
+            raw[u] = ((vmask[u] >> t9) & 1u) ? *reinterpret_cast<const uint4*>(pb[u] + tap_off[t9] + ch0)
                                               : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-          for (int t9 = 0; t9 < 9; ++t9) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(dw_w + t9 * CIN + ch0));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(dw_w + t9 * CIN + ch0 + 4));
-            const __half2* hv = reinterpret_cast<const __half2*>(&raw[t9]);
+          for (int u = 0; u < PASSES; ++u) {
+            const __half2* hv = reinterpret_cast<const __half2*>(&raw[u]);
             const float2 v0 = __half22float2(hv[0]), v1 = __half22float2(hv[1]), v2 = __half22float2(hv[2]),
                          v3 = __half22float2(hv[3]);
             acc[u][0] = fmaf(v0.x, w0.x, acc[u][0]);
@@ -989,21 +988,17 @@ __global__ void __launch_bounds__(kGemmThreads) vlad_assign_tc_kernel(const __gr
   }
 }
 
-// grid (D/64, frames), 1024 threads = 4 pixel groups x (16 clusters x 16 channel quads):
-// V[k][d] = sum_p a[p][k] (x[p][d] + C[d][k]) for a 64-wide d slice; the pixel groups keep 4x more loads in flight
-// and are summed in a fixed order through shared memory.
-__global__ void __launch_bounds__(1024) vlad_aggregate_kernel(const __half* __restrict__ x, const float* __restrict__ a,
-                                                             int P, int D, const float* __restrict__ Cc /*[D][16]*/,
-                                                             float* __restrict__ V /*[frames][16][D]*/) {
-  __shared__ float red[3][256][5];
+// grid (D/64, frames): V[k][d] = sum_p a[p][k] (x[p][d] + C[d][k]) for a 64-wide d slice
+__global__ void __launch_bounds__(256) vlad_aggregate_kernel(const __half* __restrict__ x, const float* __restrict__ a,
+                                                            int P, int D, const float* __restrict__ Cc /*[D][16]*/,
+                                                            float* __restrict__ V /*[frames][16][D]*/) {
   const int f = blockIdx.y, d0 = blockIdx.x * 64;
-  const int grp = threadIdx.x >> 8, t = threadIdx.x & 255;
-  const int k = t >> 4, dq = t & 15;
+  const int k = threadIdx.x >> 4, dq = threadIdx.x & 15;
   const __half* xf = x + (size_t)f * P * D + d0 + dq * 4;
   const float* af = a + (size_t)f * P * kK + k;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, asum = 0.f;
 #pragma unroll 4
-  for (int p = grp; p < P; p += 4) {
+  for (int p = 0; p < P; ++p) {
     const float av = af[(size_t)p * kK];
     const uint2 raw = *reinterpret_cast<const uint2*>(xf + (size_t)p * D);
     const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
@@ -1014,24 +1009,12 @@ __global__ void __launch_bounds__(1024) vlad_aggregate_kernel(const __half* __re
     acc3 = fmaf(av, f1.y, acc3);
     asum += av;
   }
-  if (grp > 0) {
-    float* r = red[grp - 1][t];
-    r[0] = acc0, r[1] = acc1, r[2] = acc2, r[3] = acc3, r[4] = asum;
-  }
-  __syncthreads();
-  if (grp == 0) {
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      const float* r = red[g][t];
-      acc0 += r[0], acc1 += r[1], acc2 += r[2], acc3 += r[3], asum += r[4];
-    }
-    const int d = d0 + dq * 4;
-    float* vo = V + ((size_t)f * kK + k) * D + d;
-    vo[0] = acc0 + asum * Cc[(size_t)(d + 0) * kK + k];
-    vo[1] = acc1 + asum * Cc[(size_t)(d + 1) * kK + k];
-    vo[2] = acc2 + asum * Cc[(size_t)(d + 2) * kK + k];
-    vo[3] = acc3 + asum * Cc[(size_t)(d + 3) * kK + k];
-  }
+  const int d = d0 + dq * 4;
+  float* vo = V + ((size_t)f * kK + k) * D + d;
+  vo[0] = acc0 + asum * Cc[(size_t)(d + 0) * kK + k];
+  vo[1] = acc1 + asum * Cc[(size_t)(d + 1) * kK + k];
+  vo[2] = acc2 + asum * Cc[(size_t)(d + 2) * kK + k];
+  vo[3] = acc3 + asum * Cc[(size_t)(d + 3) * kK + k];
 }
 
 // CTA per frame: intra-normalise each cluster over D, flatten K-major, L2-normalise (eps 1e-12 on the
@@ -1274,7 +1257,7 @@ int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cud
         d->act[cur], Ptot, d->D, d->vlad_w, d->vlad_b, d->assign);
     CB_LAUNCH_CHECK();
   }
-  vlad_aggregate_kernel<<<dim3(d->D / 64, n), 1024, 0, st>>>(d->act[cur], d->assign, P, d->D, d->vlad_c, d->Vraw);
+  vlad_aggregate_kernel<<<dim3(d->D / 64, n), 256, 0, st>>>(d->act[cur], d->assign, P, d->D, d->vlad_c, d->Vraw);
   CB_LAUNCH_CHECK();
   vlad_norm_kernel<<<n, 512, 0, st>>>(d->Vraw, d->D, out_dev);
   CB_LAUNCH_CHECK();

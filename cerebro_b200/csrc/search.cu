@@ -208,82 +208,99 @@ struct WarpList {
     s = neg_inf<S>();
     id = -1;
   }
-  // every lane offers one candidate (cs, cid); `valid` false lanes are skipped.
-  // Data-independent cost: if any candidate beats the current 32nd best, the batch of 32 is sorted with a
-  // bitonic network across the lanes (15 compare-exchange steps), merged with the sorted list (element-wise
-  // best of list[i] and batch[31-i] is the top 32 of the union, as a bitonic sequence) and re-sorted (5 steps).
+  // every lane offers one candidate (cs, cid); `valid` false lanes are skipped
   __device__ __forceinline__ void offer(S cs, long long cid, bool valid, int tie_high, int lane) {
-    const S ts = __shfl_sync(FULL, s, 31);
-    const long long tid_ = __shfl_sync(FULL, id, 31);
-    const bool cand = valid && better<S>(cs, cid, ts, tid_, tie_high);
-    if (!__ballot_sync(FULL, cand)) return;
-    if (!cand) {
-      cs = neg_inf<S>();
-      cid = -1;
-    }
-    // bitonic sort of the batch, descending by `better`
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-      for (int j = k >> 1; j >= 1; j >>= 1) {
-        const S os = __shfl_xor_sync(FULL, cs, j);
-        const long long oid = __shfl_xor_sync(FULL, cid, j);
-        const bool lower = (lane & j) == 0;          // this lane holds the lower index of the pair
-        const bool desc = (lane & k) == 0;           // direction of this sub-sequence
-        const bool ob = better<S>(os, oid, cs, cid, tie_high);  // partner beats mine
-        // lower index keeps the better element when descending, the worse one when ascending
-        const bool take = (lower == desc) ? ob : (!ob && !(os == cs && oid == cid));
-        if (take) {
-          cs = os;
-          cid = oid;
+    S ts = __shfl_sync(FULL, s, 31);
+    long long tid_ = __shfl_sync(FULL, id, 31);
+    unsigned m = __ballot_sync(FULL, valid && better<S>(cs, cid, ts, tid_, tie_high));
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const S bs = __shfl_sync(FULL, cs, src);
+      const long long bid = __shfl_sync(FULL, cid, src);
+      const bool b = better<S>(bs, bid, s, id, tie_high);
+      const unsigned bm = __ballot_sync(FULL, b);
+      const S us = __shfl_up_sync(FULL, s, 1);
+      const long long uid = __shfl_up_sync(FULL, id, 1);
+      if (b) {
+        if (lane == __ffs(bm) - 1) {
+          s = bs;
+          id = bid;
+        } else {
+          s = us;
+          id = uid;
         }
-      }
-    }
-    // merge: top 32 of (list, batch) = element-wise best of list[i] and batch[31 - i]
-    {
-      const S rs = __shfl_sync(FULL, cs, 31 - lane);
-      const long long rid = __shfl_sync(FULL, cid, 31 - lane);
-      if (better<S>(rs, rid, s, id, tie_high)) {
-        s = rs;
-        id = rid;
-      }
-    }
-    // the result is bitonic: one merge pass sorts it descending
-#pragma unroll
-    for (int j = 16; j >= 1; j >>= 1) {
-      const S os = __shfl_xor_sync(FULL, s, j);
-      const long long oid = __shfl_xor_sync(FULL, id, j);
-      const bool lower = (lane & j) == 0;
-      const bool ob = better<S>(os, oid, s, id, tie_high);
-      const bool take = lower ? ob : (!ob && !(os == s && oid == id));
-      if (take) {
-        s = os;
-        id = oid;
       }
     }
   }
 };
 
-// partial[slice][q][row] -> chunk lists [q][chunk][32]
+// ---------------------------------------------------------------------------------------------
+// fp32 top-32 selection on packed 64-bit keys: key = orderable(score) << 32 | tie-ordered local row,
+// larger key = better candidate, 0 = empty.  A warp keeps a descending sorted list (lane i = i-th best).
+//   offer_batch : 32 unsorted keys; skipped when none beats the current 32nd best, else bitonic-sorted
+//                 (15 compare-exchange steps) and merged
+//   merge_sorted: merge with another descending sorted list: best-of(list[i], other[31-i]) is the top 32 of
+//                 the union as a bitonic sequence; 5 more steps sort it
+// Data-independent cost per step (one 64-bit shuffle + min/max): no serial insertion chains.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack_key(float s, unsigned int row, int tie_high) {
+  unsigned int u = __float_as_uint(s);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // monotone map of IEEE-754 floats to unsigned
+  return ((unsigned long long)u << 32) | (unsigned long long)(tie_high ? row : ~row);
+}
+__device__ __forceinline__ unsigned int key_row(unsigned long long key, int tie_high) {
+  const unsigned int lo = (unsigned int)key;
+  return tie_high ? lo : ~lo;
+}
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+__device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+
+struct KeyList {
+  unsigned long long key;
+  __device__ __forceinline__ void init() { key = 0ull; }
+  __device__ __forceinline__ void merge_sorted(unsigned long long other, int lane) {
+    const unsigned long long r = __shfl_sync(FULL, other, 31 - lane);
+    key = umax64(key, r);
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(FULL, key, j);
+      key = ((lane & j) == 0) ? umax64(key, o) : umin64(key, o);
+    }
+  }
+  __device__ __forceinline__ void offer_batch(unsigned long long ck, int lane) {
+    const unsigned long long thr = __shfl_sync(FULL, key, 31);
+    if (!__ballot_sync(FULL, ck > thr)) return;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j >= 1; j >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(FULL, ck, j);
+        const bool up = ((lane & j) == 0) == ((lane & k) == 0);  // keep the larger of the pair
+        ck = up ? umax64(ck, o) : umin64(ck, o);
+      }
+    }
+    merge_sorted(ck, lane);
+  }
+};
+
+// partial[slice][q][row] -> chunk key lists [q][chunk][32]
 __global__ void __launch_bounds__(kThreads)
 topk_chunk_kernel(const float* __restrict__ partial, int n_slices, int qt_stride, long long pstride,
-                  long long n_rows, int rank, int world, int tie_high, float* __restrict__ cs,
-                  long long* __restrict__ cl, int n_chunks) {
-  __shared__ float ss[kWarps * kList];
-  __shared__ long long sl[kWarps * kList];
+                  long long n_rows, int tie_high, unsigned long long* __restrict__ ckeys, int n_chunks) {
+  __shared__ unsigned long long sk[kWarps * kList];
   const int q = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long r_begin = (long long)chunk * kChunkRows;
   long long r_end = r_begin + kChunkRows;
   if (r_end > n_rows) r_end = n_rows;
-  WarpList<float> wl;
-  wl.init();
+  KeyList kl;
+  kl.init();
   const float* base = partial + (size_t)q * pstride;
   const size_t sstride = (size_t)qt_stride * pstride;
-  // this thread's rows are fetched 8 at a time ahead of the warp-collective merges
   constexpr int kPer = kChunkRows / kThreads;
 #pragma unroll 1
-  for (int j0 = 0; j0 < kPer; j0 += 8) {
+  for (int j0 = 0; j0 < kPer; j0 += 8) {  // rows fetched 8 at a time ahead of the warp-collective merges
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -297,73 +314,71 @@ topk_chunk_kernel(const float* __restrict__ partial, int n_slices, int qt_stride
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const long long r = r_begin + tid + (long long)(j0 + j) * kThreads;
-      wl.offer(v[j], r * world + rank, r < r_end, tie_high, lane);
+      const bool ok = r < r_end && v[j] == v[j];  // NaN never competes
+      kl.offer_batch(ok ? pack_key(v[j], (unsigned int)r, tie_high) : 0ull, lane);
     }
   }
-  ss[warp * kList + lane] = wl.s;
-  sl[warp * kList + lane] = wl.id;
+  // tree merge of the 8 sorted warp lists
+  sk[warp * kList + lane] = kl.key;
   __syncthreads();
-  if (warp == 0) {
-    for (int w = 1; w < kWarps; ++w) {
-      const float v = ss[w * kList + lane];
-      const long long id = sl[w * kList + lane];
-      wl.offer(v, id, id >= 0, tie_high, lane);
+#pragma unroll
+  for (int half = kWarps / 2; half >= 1; half >>= 1) {
+    if (warp < half) {
+      kl.merge_sorted(sk[(warp + half) * kList + lane], lane);
+      sk[warp * kList + lane] = kl.key;
     }
-    const size_t o = ((size_t)q * n_chunks + chunk) * kList + lane;
-    cs[o] = wl.s;
-    cl[o] = wl.id;
+    __syncthreads();
   }
+  if (warp == 0) ckeys[((size_t)q * n_chunks + chunk) * kList + lane] = kl.key;
 }
 
 // one CTA (32 warps) per query: merge chunk lists -> 32 survivors, fp64 re-score, rank, write top k
 __global__ void __launch_bounds__(1024)
-finalize_kernel(const float* __restrict__ cs, const long long* __restrict__ cl, int n_chunks,
-                const float* __restrict__ rows, int d, int rank, int world,
-                const float* __restrict__ xq, int k, int tie_high, double* __restrict__ out_s,
+finalize_kernel(const unsigned long long* __restrict__ ckeys, int n_chunks, const float* __restrict__ rows, int d,
+                int rank, int world, const float* __restrict__ xq, int k, int tie_high, double* __restrict__ out_s,
                 long long* __restrict__ out_l) {
+  __shared__ unsigned long long sk[32 * kList];
   __shared__ long long s_id[kList];
   __shared__ double s_sc[kList];
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (warp == 0) {
-    WarpList<float> wl;
-    wl.init();
-    const size_t o = (size_t)q * n_chunks * kList;
-    for (int i0 = 0; i0 < n_chunks; i0 += 8) {
-      float v[8];
-      long long id[8];
+  {
+    KeyList kl;
+    kl.init();
+    const unsigned long long* base = ckeys + (size_t)q * n_chunks * kList;
+    for (int i = warp; i < n_chunks; i += 32) kl.merge_sorted(base[(size_t)i * kList + lane], lane);
+    sk[warp * kList + lane] = kl.key;
+    __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool in = i0 + j < n_chunks;
-        v[j] = in ? cs[o + (size_t)(i0 + j) * kList + lane] : 0.f;
-        id[j] = in ? cl[o + (size_t)(i0 + j) * kList + lane] : -1;
+    for (int half = 16; half >= 1; half >>= 1) {
+      if (warp < half) {
+        kl.merge_sorted(sk[(warp + half) * kList + lane], lane);
+        sk[warp * kList + lane] = kl.key;
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) wl.offer(v[j], id[j], id[j] >= 0, tie_high, lane);
+      __syncthreads();
     }
-    s_id[lane] = wl.id;
+    if (warp == 0) s_id[lane] = kl.key ? (long long)key_row(kl.key, tie_high) : -1;  // local row or -1
   }
   __syncthreads();
   // warp w re-scores survivor w in fp64 (fixed order: lane-strided, then butterfly)
   {
-    const long long id = s_id[warp];
+    const long long r = s_id[warp];
     double acc = 0.0;
-    if (id >= 0) {
-      const long long r = (id - rank) / world;
+    if (r >= 0) {
       const float4* pr = reinterpret_cast<const float4*>(rows + (size_t)r * d);
       const float4* pq = reinterpret_cast<const float4*>(xq + (size_t)q * d);
       const int nd4 = d >> 2;
-      for (int c0 = lane; c0 < nd4; c0 += 32 * 4) {  // 4 independent 16-byte loads per operand in flight
-        float4 a[4], b[4];
+      for (int c0 = lane; c0 < nd4; c0 += 32 * 8) {  // 8 independent 16-byte loads per operand in flight
+        float4 a[8], b[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const int c = c0 + 32 * j;
           const bool in = c < nd4;
           a[j] = in ? pr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
           b[j] = in ? pq[c] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {  // same summation order as a plain lane-strided loop
+        for (int j = 0; j < 8; ++j) {  // same summation order as a plain lane-strided loop
           acc += (double)a[j].x * (double)b[j].x;
           acc += (double)a[j].y * (double)b[j].y;
           acc += (double)a[j].z * (double)b[j].z;
@@ -380,7 +395,8 @@ finalize_kernel(const float* __restrict__ cs, const long long* __restrict__ cl, 
   __syncthreads();
   if (warp == 0) {
     const double ms = s_sc[lane];
-    const long long mid = s_id[lane];
+    const long long lr = s_id[lane];
+    const long long mid = lr >= 0 ? lr * world + rank : -1;  // global label
     int rnk = 0;
     for (int j = 0; j < kList; ++j) {
       const double os = __shfl_sync(FULL, ms, j);
@@ -456,8 +472,7 @@ struct cb_index {
   // scratch (grown on demand)
   float* partial = nullptr;
   size_t partial_bytes = 0;
-  float* chunk_s = nullptr;
-  long long* chunk_l = nullptr;
+  unsigned long long* chunk_k = nullptr;  // [qt][n_chunks][32] packed keys
   size_t chunk_elems = 0;
   float* q_dev = nullptr;  // host-API staging
   size_t q_bytes = 0;
@@ -548,13 +563,10 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
     if (rc) return rc;
     const size_t ce = (size_t)p.qt * n_chunks * kList;
     if (ix->chunk_elems < ce) {
-      if (ix->chunk_s) cudaFree(ix->chunk_s);
-      if (ix->chunk_l) cudaFree(ix->chunk_l);
-      ix->chunk_s = nullptr;
-      ix->chunk_l = nullptr;
+      if (ix->chunk_k) cudaFree(ix->chunk_k);
+      ix->chunk_k = nullptr;
       ix->chunk_elems = 0;
-      CB_CUDA(cudaMalloc(&ix->chunk_s, ce * sizeof(float)));
-      CB_CUDA(cudaMalloc(&ix->chunk_l, ce * sizeof(long long)));
+      CB_CUDA(cudaMalloc(&ix->chunk_k, ce * sizeof(unsigned long long)));
       ix->chunk_elems = ce;
     }
     const float* xq = xq_dev + (size_t)q0 * ix->d;
@@ -583,12 +595,10 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
       ++ix->ev_used;
     }
     if (e != cudaSuccess) return cb::fail(CB_ECUDA, "scores_kernel launch failed: %s", cudaGetErrorString(e));
-    topk_chunk_kernel<<<dim3(n_chunks, nq_valid), kThreads, 0, st>>>(
-        ix->partial, p.n_slices, p.qt, pstride, n_rows, ix->rank, ix->world, tie_high, ix->chunk_s,
-        ix->chunk_l, n_chunks);
+    topk_chunk_kernel<<<dim3(n_chunks, nq_valid), kThreads, 0, st>>>(ix->partial, p.n_slices, p.qt, pstride, n_rows, tie_high,
+                                                                     ix->chunk_k, n_chunks);
     CB_LAUNCH_CHECK();
-    finalize_kernel<<<nq_valid, 1024, 0, st>>>(ix->chunk_s, ix->chunk_l, n_chunks, ix->rows, ix->d,
-                                               ix->rank, ix->world, xq, k, tie_high,
+    finalize_kernel<<<nq_valid, 1024, 0, st>>>(ix->chunk_k, n_chunks, ix->rows, ix->d, ix->rank, ix->world, xq, k, tie_high,
                                                scores_dev + (size_t)q0 * k, labels_dev + (size_t)q0 * k);
     CB_LAUNCH_CHECK();
     q0 += nq_valid;
@@ -604,7 +614,7 @@ int cb_index_create(cb_index** out, int d, int64_t capacity, int device, int ran
   if (!out) return cb::fail(CB_EINVAL, "out is NULL");
   *out = nullptr;
   if (d <= 0 || d % 128 != 0) return cb::fail(CB_EINVAL, "descriptor dim must be a positive multiple of 128, got %d", d);
-  if (capacity <= 0) return cb::fail(CB_EINVAL, "capacity must be > 0");
+  if (capacity <= 0 || capacity >= (1ll << 32)) return cb::fail(CB_EINVAL, "capacity must be in (0, 2^32) rows per shard");
   if (world < 1 || rank < 0 || rank >= world) return cb::fail(CB_EINVAL, "bad shard %d/%d", rank, world);
   int sm = 0;
   int rc = cb::select_device(device, &sm);
@@ -638,8 +648,7 @@ int cb_index_destroy(cb_index* ix) {
   cudaStreamSynchronize(ix->stream);
   cudaFree(ix->rows);
   cudaFree(ix->partial);
-  cudaFree(ix->chunk_s);
-  cudaFree(ix->chunk_l);
+  cudaFree(ix->chunk_k);
   cudaFree(ix->q_dev);
   cudaFree(ix->out_s);
   cudaFree(ix->out_l);
