@@ -305,7 +305,16 @@ def main():
     achieved = alg_bytes / (sweep_ms / max(n_sw, 1) * 1e-3) / 1e9 if n_sw else None
 
     # ---- end to end through the host C-ABI calls (pinned host buffers in, host results out)
+    from concurrent.futures import ThreadPoolExecutor
+
+    pool = ThreadPoolExecutor(max_workers=1)
+    Xs = [X_host.numpy()[i * N_CORR : (i + 1) * N_CORR] for i in range(B)]
+    uvs = [uv_host.numpy()[i * N_CORR : (i + 1) * N_CORR] for i in range(B)]
+
     def step_host():
+        # the reference drives the verifier from its own thread (loopcandidate_consumer_th); so does this:
+        # ctypes releases the GIL inside the C-ABI calls, each handle owns its stream
+        fut = pool.submit(pipe.pnp.solve, Xs, uvs, pipe.params)
         d = pipe.desc.compute(imgs_host.numpy())
         if world > 1:
             dd = torch.from_numpy(d).to(dev)
@@ -314,9 +323,7 @@ def main():
             res = (s.cpu(), l.cpu())
         else:
             res = pipe.index.search(d, 5)
-        r = pipe.pnp.solve([X_host.numpy()[i * N_CORR : (i + 1) * N_CORR] for i in range(B)],
-                           [uv_host.numpy()[i * N_CORR : (i + 1) * N_CORR] for i in range(B)], pipe.params)
-        return res, r
+        return res, fut.result()
 
     for _ in range(2):
         step_host()

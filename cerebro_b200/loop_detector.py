@@ -198,10 +198,21 @@ class LoopPipeline:
         self.pnp = PnpBatch(max_candidates=batch, max_points_total=batch * n_corr, max_hypotheses=hypotheses, device=device)
         self.params = default_params(max_iterations=hypotheses, seed=7)
         self.k = 5  # FAISS path searches top-5 (Cerebro.cpp:460)
+        self._side = None  # second CUDA stream for the verifier
 
     def step_device(self, images_dev, offsets_dev, X_dev, uv_dev, bufs):
-        """All inputs already in HBM.  Returns (labels [B*world,k], scores, pnp outputs)."""
+        """All inputs already in HBM.  Returns (labels [B*world,k], scores, pnp outputs).
+
+        The verifier does not depend on the descriptor/search chain of the same step (the reference runs them
+        in different threads, cerebro_node.cpp:487-509), so it is issued on a second CUDA stream: its
+        latency-bound warp-per-hypothesis kernels fill the SMs' idle issue slots while the HBM-bound sweep runs."""
         torch = self.torch
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            out = self.pnp.solve_device(offsets_dev, X_dev, uv_dev, self.params, out=bufs["pnp"])
         d = self.desc.compute_device(images_dev, out=bufs["desc"])
         if self.sharded and self.world > 1:
             q = bufs["queries"]
@@ -209,5 +220,5 @@ class LoopPipeline:
         else:
             q = d
         s, l = self.index.search_device(q, self.k)
-        out = self.pnp.solve_device(offsets_dev, X_dev, uv_dev, self.params, out=bufs["pnp"])
+        main.wait_stream(self._side)
         return l, s, out
