@@ -22,6 +22,7 @@
 #include "common.cuh"
 
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -446,6 +447,113 @@ __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restri
   if (i < n) out[i] = (float)in[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// 16-query sweep with the database staged through shared memory: every lane streams its own 16-byte chunks
+// of R rows into a private 3-deep cp.async ring (no cross-lane sharing, hence no barriers: a lane only ever
+// reads back what it copied itself), so two 128-float segments per row are always in flight while the
+// current one is multiplied against the 16 resident query slices.  Same arithmetic, same summation order
+// and same output as scores_kernel<16,8>; only the load pipeline differs.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRingStages = 3;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+scores_ring_kernel(const float* __restrict__ rows, long long n_rows, int d, int ds, int n_slices,
+                   const float* __restrict__ xq, int nq_valid, float* __restrict__ partial, long long pstride) {
+  constexpr int QT = 16, R = 8;
+  extern __shared__ float4 sq[];  // [QT][ds/4] queries | ring [warps][stages][R][32] float4
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int slice = blockIdx.x % n_slices;
+  const int group = blockIdx.x / n_slices;
+  const int n_groups = gridDim.x / n_slices;
+  const int d0 = slice * ds;
+  const int ds4 = ds >> 2;
+  float4* ring = sq + QT * ds4 + (size_t)warp * kRingStages * R * 32 + lane;
+
+  for (int i = tid; i < QT * ds4; i += kThreads) {
+    const int t = i / ds4, c = i - t * ds4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < nq_valid) v = reinterpret_cast<const float4*>(xq + (size_t)t * d + d0)[c];
+    sq[i] = v;
+  }
+  __syncthreads();
+
+  constexpr int kRowsPerCta = kWarps * R;
+  const long long n_blocks = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
+  const int nj = ds >> 7;
+
+  for (long long rb = group; rb < n_blocks; rb += n_groups) {
+    const long long r0 = rb * kRowsPerCta + (long long)warp * R;
+    if (r0 >= n_rows) continue;  // warp-uniform
+    float acc[R * QT];
+#pragma unroll
+    for (int i = 0; i < R * QT; ++i) acc[i] = 0.f;
+    const float4* p[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      long long rr = r0 + r;
+      if (rr >= n_rows) rr = n_rows - 1;  // tail rows: computed, never written
+      p[r] = reinterpret_cast<const float4*>(rows + (size_t)rr * d + d0) + lane;
+    }
+    // prologue: segments 0 .. stages-2 in flight
+#pragma unroll
+    for (int st = 0; st < kRingStages - 1; ++st) {
+      if (st < nj) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) cp_async16(ring + (st * R + r) * 32, p[r] + st * 32);
+      }
+      cp_async_commit();
+    }
+    for (int j = 0; j < nj; ++j) {
+      const int jn = j + kRingStages - 1;
+      if (jn < nj) {
+        const int stn = jn % kRingStages;
+#pragma unroll
+        for (int r = 0; r < R; ++r) cp_async16(ring + (stn * R + r) * 32, p[r] + jn * 32);
+      }
+      cp_async_commit();
+      cp_async_wait<kRingStages - 1>();  // segment j has landed (for this lane's own chunks)
+      const int stc = j % kRingStages;
+      float4 cur[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) cur[r] = ring[(stc * R + r) * 32];
+      const float4* q = sq + j * 32 + lane;
+#pragma unroll
+      for (int t = 0; t < QT; ++t) {
+        const float4 q4 = q[t * ds4];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float a = acc[r * QT + t];
+          a = fmaf(cur[r].x, q4.x, a);
+          a = fmaf(cur[r].y, q4.y, a);
+          a = fmaf(cur[r].z, q4.z, a);
+          a = fmaf(cur[r].w, q4.w, a);
+          acc[r * QT + t] = a;
+        }
+      }
+    }
+    cp_async_wait<0>();
+    float* out = partial + (size_t)slice * QT * pstride;
+    warp_reduce_scatter<R * QT>(acc, lane);
+#pragma unroll
+    for (int g = 0; g < (R * QT) / 32; ++g) {
+      const int id = g * 32 + lane;
+      const int r = id / QT, t = id % QT;
+      if (r0 + r < n_rows && t < nq_valid) out[(size_t)t * pstride + r0 + r] = acc[g];
+    }
+  }
+}
+
 template <int QT, int R>
 cudaError_t launch_scores(int grid, size_t smem, cudaStream_t st, const float* rows, long long n_rows,
                           int d, int ds, int n_slices, const float* xq, int nq_valid, float* partial,
@@ -483,6 +591,7 @@ struct cb_index {
   size_t stage_bytes = 0;
   int max_qt = 16;
   int* work_counter = nullptr;
+  bool no_ring = false;  // CB_NO_RING=1: register-prefetch sweep for the 16-query tile as well
   // optional device-side timing of the sweep kernel (bench.py roofline)
   bool timing = false;
   cudaEvent_t ev[2 * 64] = {};
@@ -524,7 +633,7 @@ SweepPlan plan_sweep(const cb_index* ix, int nq_left) {
   while (qt < nq_left && qt < ix->max_qt) qt <<= 1;
   for (;; qt >>= 1) {
     // shared memory budget: one resident CTA for the 8/16-query tiles, two otherwise
-    const size_t cap = (qt >= 8 ? 200 : 100) * 1024;
+    const size_t cap = (qt >= 16 ? 128 : (qt >= 8 ? 200 : 100)) * 1024;  // the 16-query tile shares smem with the 96 KB ring
     int n_slices = 1;
     while ((size_t)qt * (ix->d / n_slices) * 4 > cap && (ix->d / (n_slices * 2)) % 128 == 0 &&
            ix->d % (n_slices * 2) == 0)
@@ -587,7 +696,20 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
       case 2: CB_SWEEP(2, 8); break;
       case 4: CB_SWEEP(4, 8); break;
       case 8: CB_SWEEP(8, 8); break;
-      default: CB_SWEEP(16, 8); break;
+      default: {
+        const size_t ring_bytes = (size_t)kWarps * kRingStages * 8 * 32 * sizeof(float4);
+        if (p.smem + ring_bytes <= 227 * 1024 && !ix->no_ring) {
+          e = cudaFuncSetAttribute(scores_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.smem + ring_bytes));
+          if (e == cudaSuccess) {
+            scores_ring_kernel<<<p.grid, kThreads, p.smem + ring_bytes, st>>>(ix->rows, n_rows, ix->d, p.ds, p.n_slices, xq,
+                                                                              nq_valid, ix->partial, pstride);
+            e = cudaGetLastError();
+          }
+        } else {
+          CB_SWEEP(16, 8);
+        }
+        break;
+      }
     }
 #undef CB_SWEEP
     if (rec) {
@@ -627,6 +749,10 @@ int cb_index_create(cb_index** out, int d, int64_t capacity, int device, int ran
   ix->rank = rank;
   ix->world = world;
   ix->sm_count = sm;
+  {
+    const char* env = getenv("CB_NO_RING");
+    ix->no_ring = env && env[0] == '1';
+  }
   cudaError_t e = cudaMalloc(&ix->rows, (size_t)capacity * d * sizeof(float));
   if (e != cudaSuccess) {
     delete ix;
