@@ -295,6 +295,7 @@ def main():
     nq = q_all.shape[0]
     sweeps = (nq + 15) // 16
     sweep_ms, n_sw = _sweep_timing(local_index, q_all)
+    sweep3_ms, n_sw3 = _sweep_timing(local_index, q_all, nq=3)  # the reference's natural batch: v, vm, vmm
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
@@ -368,9 +369,14 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": launches,
             "stages_ms": {"descriptor": st_desc, "search": st_search, "pnp": st_pnp},
-            "roofline": {"kernel": "scores_kernel (search sweep)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+            "roofline": {"kernel": "scores_ring_kernel (16-query search sweep, 4 launches per step)", "bound": "hbm", "achieved": achieved,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
+                         "traffic": _traffic_from_profile(world), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": sweep_ms / max(n_sw, 1)},
+            "roofline_streaming": {"kernel": "scores_kernel<4,8> (3-query sweep: the reference's v, vm, vmm batch)", "bound": "hbm",
+                                   "achieved": alg_bytes / (sweep3_ms / max(n_sw3, 1) * 1e-3) / 1e9 if n_sw3 else None,
+                                   "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": (alg_bytes / (sweep3_ms / max(n_sw3, 1) * 1e-3) / 1e9 / hbm_peak) if n_sw3 else None},
             "cpu_baseline": cpu_base,
             "clocks": clocks,
         }
@@ -379,12 +385,24 @@ def main():
         dist.destroy_process_group()
 
 
-def _sweep_timing(index, q):
-    """Summed duration and count of scores_kernel launches over 10 searches of <= 16 queries, from
+def _traffic_from_profile(world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep kernel, from the committed ncu --set full
+    capture of this same workload (profiles/r1_traffic.json); only valid for the single-GPU 100k x 8192 DB."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if world != 1 or not os.path.exists(path):
+        return None
+    try:
+        return json.load(open(path)).get("scores_ring_kernel_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def _sweep_timing(index, q, nq=16):
+    """Summed duration and count of sweep-kernel launches over 10 searches of <= nq queries, from
     the library's CUDA events recorded on the launching stream around exactly that kernel."""
     import torch
 
-    q16 = q[:16].contiguous() if q.shape[0] >= 16 else q
+    q16 = q[:nq].contiguous() if q.shape[0] >= nq else q
     out = index.search_device(q16, 5)
     torch.cuda.synchronize()
     index.set_timing(True)
