@@ -590,27 +590,28 @@ __device__ bool warp_hqr(double* a, double* wr, double* wi, int lane) {
           p = a[k * n + k - 1];
           q = a[(k + 1) * n + k - 1];
           r = (k != nn - 1) ? a[(k + 2) * n + k - 1] : 0.0;
-          x = fabs(p) + fabs(q) + fabs(r);
-          if (x != 0.0) {
-            const double ix = 1.0 / x;
-            p *= ix;
-            q *= ix;
-            r *= ix;
-          }
+          // (no pre-scaling by |p|+|q|+|r|: the entries of a balanced 27x27 action matrix are far from the
+          //  overflow/underflow range, and the Householder vector is scale invariant)
         }
-        double s = sqrt(p * p + q * q + r * r);
-        if (p < 0.0) s = -s;
-        if (s != 0.0) {
+        const double ss2 = p * p + q * q + r * r;
+        if (ss2 != 0.0) {
+          // one reciprocal square root gives both the norm and its inverse
+          double is = rsqrt(ss2);
+          double s = ss2 * is;
+          if (p < 0.0) {
+            s = -s;
+            is = -is;
+          }
           __syncwarp();
           if (lane == 0) {
             if (k == m) {
               if (l != m) a[k * n + k - 1] = -a[k * n + k - 1];
             } else {
-              a[k * n + k - 1] = -s * x;
+              a[k * n + k - 1] = -s;
             }
           }
           p += s;
-          const double is = 1.0 / s, ip = 1.0 / p;
+          const double ip = 1.0 / p;
           x = p * is;
           y = q * is;
           const double z = r * is;
