@@ -350,7 +350,7 @@ def main():
             secs = cpu_pipeline_run(ctx, args.cpu_baseline_keyframes)
             cpu_base = {"value": args.cpu_baseline_keyframes / secs, "unit": UNIT, "cores": ctx["cores"], "kind": "port",
                         "sample": "%d keyframes: torch-CPU fp32 NetVLAD (all cores) + fp32 BLAS top-5 search of the full 100k x 8192 DB + oracle DLS-PnP RANSAC (1 thread)" % args.cpu_baseline_keyframes}
-        launches = 1 + 2 * 7 + 3 + 3 * sweeps + 6
+        launches = (1 + 7 + 3) + (sweeps + 2 * ((nq + 127) // 128)) + 6  # stem + 7 fused blocks + VLAD head; sweeps + top-k + finalize; PnP
         line = {
             "metric": METRIC,
             "value": value,

@@ -69,7 +69,7 @@ template <int QT, int R>
 __global__ void __launch_bounds__(kThreads, (QT * R >= 64 ? 1 : 2))
 scores_kernel(const float* __restrict__ rows, long long n_rows, int d, int ds, int n_slices,
               const float* __restrict__ xq, int nq_valid, float* __restrict__ partial,
-              long long pstride, int* __restrict__ work_counter) {
+              long long pstride, long long slice_stride, int* __restrict__ work_counter) {
   extern __shared__ float4 sq[];  // [QT][ds/4]
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -151,7 +151,7 @@ scores_kernel(const float* __restrict__ rows, long long n_rows, int d, int ds, i
       }
     }
 
-    float* out = partial + (size_t)slice * QT * pstride;
+    float* out = partial + (size_t)slice * slice_stride;
     if constexpr ((R * QT) % 32 == 0) {
       warp_reduce_scatter<R * QT>(acc, lane);
 #pragma unroll
@@ -287,7 +287,7 @@ struct KeyList {
 
 // partial[slice][q][row] -> chunk key lists [q][chunk][32]
 __global__ void __launch_bounds__(kThreads)
-topk_chunk_kernel(const float* __restrict__ partial, int n_slices, int qt_stride, long long pstride,
+topk_chunk_kernel(const float* __restrict__ partial, int n_slices, long long slice_stride, long long pstride,
                   long long n_rows, int tie_high, unsigned long long* __restrict__ ckeys, int n_chunks) {
   __shared__ unsigned long long sk[kWarps * kList];
   const int q = blockIdx.y, chunk = blockIdx.x;
@@ -298,7 +298,7 @@ topk_chunk_kernel(const float* __restrict__ partial, int n_slices, int qt_stride
   KeyList kl;
   kl.init();
   const float* base = partial + (size_t)q * pstride;
-  const size_t sstride = (size_t)qt_stride * pstride;
+  const size_t sstride = (size_t)slice_stride;
   constexpr int kPer = kChunkRows / kThreads;
 #pragma unroll 1
   for (int j0 = 0; j0 < kPer; j0 += 8) {  // rows fetched 8 at a time ahead of the warp-collective merges
@@ -468,7 +468,8 @@ __device__ __forceinline__ void cp_async_wait() {
 
 __global__ void __launch_bounds__(kThreads, 1)
 scores_ring_kernel(const float* __restrict__ rows, long long n_rows, int d, int ds, int n_slices,
-                   const float* __restrict__ xq, int nq_valid, float* __restrict__ partial, long long pstride) {
+                   const float* __restrict__ xq, int nq_valid, float* __restrict__ partial, long long pstride,
+                   long long slice_stride) {
   constexpr int QT = 16, R = 8;
   extern __shared__ float4 sq[];  // [QT][ds/4] queries | ring [warps][stages][R][32] float4
   const int tid = threadIdx.x;
@@ -543,7 +544,7 @@ scores_ring_kernel(const float* __restrict__ rows, long long n_rows, int d, int 
       }
     }
     cp_async_wait<0>();
-    float* out = partial + (size_t)slice * QT * pstride;
+    float* out = partial + (size_t)slice * slice_stride;
     warp_reduce_scatter<R * QT>(acc, lane);
 #pragma unroll
     for (int g = 0; g < (R * QT) / 32; ++g) {
@@ -557,11 +558,11 @@ scores_ring_kernel(const float* __restrict__ rows, long long n_rows, int d, int 
 template <int QT, int R>
 cudaError_t launch_scores(int grid, size_t smem, cudaStream_t st, const float* rows, long long n_rows,
                           int d, int ds, int n_slices, const float* xq, int nq_valid, float* partial,
-                          long long pstride, int* work_counter) {
+                          long long pstride, long long slice_stride, int* work_counter) {
   auto kern = scores_kernel<QT, R>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kThreads, smem, st>>>(rows, n_rows, d, ds, n_slices, xq, nq_valid, partial, pstride, work_counter);
+  kern<<<grid, kThreads, smem, st>>>(rows, n_rows, d, ds, n_slices, xq, nq_valid, partial, pstride, slice_stride, work_counter);
   return cudaGetLastError();
 }
 
@@ -664,13 +665,18 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
     return CB_OK;
   }
   const long long pstride = (n_rows + 31) & ~31LL;
-  int q0 = 0;
-  while (q0 < nq) {
-    SweepPlan p = plan_sweep(ix, nq - q0);
-    const int nq_valid = (nq - q0) < p.qt ? (nq - q0) : p.qt;
-    int rc = grow((void**)&ix->partial, &ix->partial_bytes, (size_t)p.n_slices * p.qt * pstride * sizeof(float));
+  // Queries are processed in groups of <= 128: all sweeps of a group first (16 queries each, partial scores kept for the
+  // whole group), then ONE top-k launch and ONE finalize launch for the group -- the selection kernels' fixed latency is
+  // paid once per group instead of once per sweep (matters when the DB is sharded and each sweep is short).
+  constexpr int kGroup = 128;
+  for (int g0 = 0; g0 < nq; g0 += kGroup) {
+    const int gq = (nq - g0) < kGroup ? (nq - g0) : kGroup;
+    SweepPlan p = plan_sweep(ix, gq);  // one plan (tile size, d-slicing) for the whole group
+    const int n_tiles = (gq + p.qt - 1) / p.qt;
+    const long long slice_stride = (long long)n_tiles * p.qt * pstride;
+    int rc = grow((void**)&ix->partial, &ix->partial_bytes, (size_t)p.n_slices * slice_stride * sizeof(float));
     if (rc) return rc;
-    const size_t ce = (size_t)p.qt * n_chunks * kList;
+    const size_t ce = (size_t)gq * n_chunks * kList;
     if (ix->chunk_elems < ce) {
       if (ix->chunk_k) cudaFree(ix->chunk_k);
       ix->chunk_k = nullptr;
@@ -678,52 +684,56 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
       CB_CUDA(cudaMalloc(&ix->chunk_k, ce * sizeof(unsigned long long)));
       ix->chunk_elems = ce;
     }
-    const float* xq = xq_dev + (size_t)q0 * ix->d;
-    cudaError_t e = cudaSuccess;
-    int* wc = nullptr;
-    if (p.qt <= 4) {  // streaming regime: dynamic row-group tickets (one counter per d-slice)
-      if (!ix->work_counter) CB_CUDA(cudaMalloc((void**)&ix->work_counter, 16 * sizeof(int)));
-      CB_CUDA(cudaMemsetAsync(ix->work_counter, 0, 16 * sizeof(int), st));
-      wc = ix->work_counter;
-    }
-    const bool rec = ix->timing && ix->ev_used < 64;
-    if (rec) cudaEventRecord(ix->ev[2 * ix->ev_used], st);
-#define CB_SWEEP(QT, R)                                                                          \
-  e = launch_scores<QT, R>(p.grid, p.smem, st, ix->rows, n_rows, ix->d, p.ds, p.n_slices, xq,    \
-                           nq_valid, ix->partial, pstride, wc)
-    switch (p.qt) {
-      case 1: CB_SWEEP(1, 8); break;
-      case 2: CB_SWEEP(2, 8); break;
-      case 4: CB_SWEEP(4, 8); break;
-      case 8: CB_SWEEP(8, 8); break;
-      default: {
-        const size_t ring_bytes = (size_t)kWarps * kRingStages * 8 * 32 * sizeof(float4);
-        if (p.smem + ring_bytes <= 227 * 1024 && !ix->no_ring) {
-          e = cudaFuncSetAttribute(scores_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.smem + ring_bytes));
-          if (e == cudaSuccess) {
-            scores_ring_kernel<<<p.grid, kThreads, p.smem + ring_bytes, st>>>(ix->rows, n_rows, ix->d, p.ds, p.n_slices, xq,
-                                                                              nq_valid, ix->partial, pstride);
-            e = cudaGetLastError();
-          }
-        } else {
-          CB_SWEEP(16, 8);
-        }
-        break;
+    for (int tq = 0; tq < gq; tq += p.qt) {
+      const int nq_valid = (gq - tq) < p.qt ? (gq - tq) : p.qt;
+      const float* xq = xq_dev + (size_t)(g0 + tq) * ix->d;
+      float* ptile = ix->partial + (size_t)tq * pstride;
+      cudaError_t e = cudaSuccess;
+      int* wc = nullptr;
+      if (p.qt <= 4) {  // streaming regime: dynamic row-group tickets (one counter per d-slice)
+        if (!ix->work_counter) CB_CUDA(cudaMalloc((void**)&ix->work_counter, 16 * sizeof(int)));
+        CB_CUDA(cudaMemsetAsync(ix->work_counter, 0, 16 * sizeof(int), st));
+        wc = ix->work_counter;
       }
-    }
+      const bool rec = ix->timing && ix->ev_used < 64;
+      if (rec) cudaEventRecord(ix->ev[2 * ix->ev_used], st);
+#define CB_SWEEP(QT, R)                                                                                        \
+  e = launch_scores<QT, R>(p.grid, p.smem, st, ix->rows, n_rows, ix->d, p.ds, p.n_slices, xq, nq_valid, ptile, \
+                           pstride, slice_stride, wc)
+      switch (p.qt) {
+        case 1: CB_SWEEP(1, 8); break;
+        case 2: CB_SWEEP(2, 8); break;
+        case 4: CB_SWEEP(4, 8); break;
+        case 8: CB_SWEEP(8, 8); break;
+        default: {
+          const size_t ring_bytes = (size_t)kWarps * kRingStages * 8 * 32 * sizeof(float4);
+          if (p.smem + ring_bytes <= 227 * 1024 && !ix->no_ring) {
+            e = cudaFuncSetAttribute(scores_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.smem + ring_bytes));
+            if (e == cudaSuccess) {
+              scores_ring_kernel<<<p.grid, kThreads, p.smem + ring_bytes, st>>>(ix->rows, n_rows, ix->d, p.ds, p.n_slices, xq,
+                                                                                nq_valid, ptile, pstride, slice_stride);
+              e = cudaGetLastError();
+            }
+          } else {
+            CB_SWEEP(16, 8);
+          }
+          break;
+        }
+      }
 #undef CB_SWEEP
-    if (rec) {
-      cudaEventRecord(ix->ev[2 * ix->ev_used + 1], st);
-      ++ix->ev_used;
+      if (rec) {
+        cudaEventRecord(ix->ev[2 * ix->ev_used + 1], st);
+        ++ix->ev_used;
+      }
+      if (e != cudaSuccess) return cb::fail(CB_ECUDA, "scores_kernel launch failed: %s", cudaGetErrorString(e));
     }
-    if (e != cudaSuccess) return cb::fail(CB_ECUDA, "scores_kernel launch failed: %s", cudaGetErrorString(e));
-    topk_chunk_kernel<<<dim3(n_chunks, nq_valid), kThreads, 0, st>>>(ix->partial, p.n_slices, p.qt, pstride, n_rows, tie_high,
-                                                                     ix->chunk_k, n_chunks);
+    topk_chunk_kernel<<<dim3(n_chunks, gq), kThreads, 0, st>>>(ix->partial, p.n_slices, slice_stride, pstride, n_rows, tie_high,
+                                                               ix->chunk_k, n_chunks);
     CB_LAUNCH_CHECK();
-    finalize_kernel<<<nq_valid, 1024, 0, st>>>(ix->chunk_k, n_chunks, ix->rows, ix->d, ix->rank, ix->world, xq, k, tie_high,
-                                               scores_dev + (size_t)q0 * k, labels_dev + (size_t)q0 * k);
+    finalize_kernel<<<gq, 1024, 0, st>>>(ix->chunk_k, n_chunks, ix->rows, ix->d, ix->rank, ix->world,
+                                         xq_dev + (size_t)g0 * ix->d, k, tie_high, scores_dev + (size_t)g0 * k,
+                                         labels_dev + (size_t)g0 * k);
     CB_LAUNCH_CHECK();
-    q0 += nq_valid;
   }
   return CB_OK;
 }
