@@ -160,6 +160,35 @@ class Cerebro:
             return edge
         return None
 
+    # ---- one wake-up of faiss__naive_loopcandidate_generator (Cerebro.cpp:366-492, compiled under HAVE_FAISS)
+    FAISS_LAG = 150  # Cerebro.cpp:374
+    FAISS_DOT_PROD_THRESH = 0.9  # Cerebro.cpp:376
+
+    def faiss_naive_step(self):
+        """The FAISS-flavoured candidate rule on the same device index: descriptors enter the searchable set with
+        a 150-keyframe lag (expressed as ``limit_rows``; the reference delays ``index.add`` instead, :415-433), every
+        new descriptor is searched top-5 (:460), a loop is reported when exactly 3 new descriptors were searched, the
+        newest top-1 score exceeds 0.9 and the three top-1 labels lie within LOCALITY_THRESH (:476)."""
+        l = self.wholeImageComputedList_size()
+        if l - self._last_l < 3:  # :403
+            return None
+        last_l = self._last_l
+        self._last_l = l
+        limit = l - self.FAISS_LAG
+        if limit < 5:  # index.ntotal < 5 -> nothing is searched (:449)
+            return None
+        if l - last_l != 3:  # tmp_ only has 3 entries when exactly 3 descriptors arrived (:476 `_n == 3`)
+            return None
+        q = self.index.get_rows(last_l, 3)
+        D, I = self.index.search(q, 5, limit_rows=limit, tie=TIE_LOW_LABEL)
+        tmp, tmp_i = [float(D[j, 0]) for j in range(3)], [int(I[j, 0]) for j in range(3)]
+        if (tmp[2] > np.float32(self.FAISS_DOT_PROD_THRESH) and abs(tmp_i[0] - tmp_i[1]) < self.LOCALITY_THRESH
+                and abs(tmp_i[0] - tmp_i[2]) < self.LOCALITY_THRESH):
+            edge = (self._whole[l - 1], self._whole[tmp_i[2]], tmp[2])  # :484
+            self._found.append(edge)
+            return edge
+        return None
+
     # ---- loopcandiate_consumer_thread body (Cerebro.cpp:1203-1277), geometry supplied by the caller
     def loopcandidate_consumer_step(self, correspondences, params=None):
         """correspondences[j] = (w_X [n,3], c_uv [n,2]) for every not-yet-consumed foundLoops entry

@@ -59,3 +59,50 @@ def test_python_cerebro_stream_matches_oracle(native_lib, cuda_device):
         e = D.pose_error(rec["b_T_a"], o["T"])
         assert e[0] < 1e-3 and e[1] < 1e-2
     nd.close()
+
+
+def test_faiss_naive_rule_matches_oracle(native_lib, cuda_device):
+    """Cerebro.faiss_naive_step (top-5 search with a 150-keyframe lag) vs oracle.faiss_naive_stream on descriptors
+    fed straight into the index (the descriptor stage is covered above)."""
+    from cerebro_b200.loop_detector import Cerebro
+    from oracle.search import faiss_naive_stream
+
+    class _FakeDesc:  # the rule only needs descriptor_size
+        dim = 1024
+
+    d, n = 1024, 420
+    base = synth.unit_rows(n, d, seed=70)
+    desc = base.copy()
+    for i in range(45):
+        desc[360 + i] = synth.planted_queries(base, [40 + i], seed=200 + i, score=0.95)[0]
+    cer = Cerebro(_FakeDesc(), capacity=n)
+    found = []
+    for a in range(0, n, 3):
+        cer.index.add(desc[a : a + 3])
+        cer._whole.extend(range(a, a + 3))
+        e = cer.faiss_naive_step()
+        if e is not None:
+            found.append(e)
+    expected = faiss_naive_stream(desc, list(range(3, n + 1, 3)))
+    assert len(expected) >= 5
+    assert [(a, b) for a, b, _ in found] == [(a, b) for a, b, _ in expected]
+    assert np.allclose([s for *_, s in found], [s for *_, s in expected], atol=1e-6)
+
+
+def test_descriptor_row_stride(native_lib, cuda_device):
+    """cb_descriptor_compute with padded image rows (cv::Mat step > cols*channels, Cerebro.cpp:243-256)."""
+    import ctypes as C
+
+    from cerebro_b200 import _lib
+    from cerebro_b200.descriptor import NetvladDescriptor
+    from cerebro_b200.keras_weights import fold_mobilenet_netvlad
+
+    nd = NetvladDescriptor(fold_mobilenet_netvlad(golden_io.raw_weights("gray_conv6")), 96, 128, 1, max_batch=2)
+    imgs = synth.band_limited_images(2, 96, 128, 1, seed=3)
+    ref = nd.compute(imgs)
+    padded = np.zeros((2, 96, 160), dtype=np.uint8)
+    padded[:, :, :128] = imgs[..., 0]
+    out = np.empty((2, nd.dim), dtype=np.float32)
+    _lib.check(_lib.load().cb_descriptor_compute(nd._h, 2, _lib.ptr(padded), 160, _lib.ptr(out)))
+    assert np.array_equal(out, ref)
+    nd.close()
