@@ -614,30 +614,39 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dwpw_kernel(const __half* __
             acc[u][4] = bb1.x, acc[u][5] = bb1.y, acc[u][6] = bb1.z, acc[u][7] = bb1.w;
           }
         }
+        // interior fast path: when every tap of every pixel handled by this warp is inside the image (the common
+        // case) the loads carry no predicates and no zero-fill selects
+        bool all_in = true;
 #pragma unroll
-        for (int t9 = 0; t9 < 9; ++t9) {
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(dw_w + t9 * CIN + ch0));
-          const float4 w1 = __ldg(reinterpret_cast<const float4*>(dw_w + t9 * CIN + ch0 + 4));
-          uint4 raw[PASSES];
-#pragma unroll
-          for (int u = 0; u < PASSES; ++u)
-            raw[u] = ((vmask[u] >> t9) & 1u) ? *reinterpret_cast<const uint4*>(pb[u] + tap_off[t9] + ch0)
-                                              : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-          for (int u = 0; u < PASSES; ++u) {
-            const __half2* hv = reinterpret_cast<const __half2*>(&raw[u]);
-            const float2 v0 = __half22float2(hv[0]), v1 = __half22float2(hv[1]), v2 = __half22float2(hv[2]),
-                         v3 = __half22float2(hv[3]);
-            acc[u][0] = fmaf(v0.x, w0.x, acc[u][0]);
-            acc[u][1] = fmaf(v0.y, w0.y, acc[u][1]);
-            acc[u][2] = fmaf(v1.x, w0.z, acc[u][2]);
-            acc[u][3] = fmaf(v1.y, w0.w, acc[u][3]);
-            acc[u][4] = fmaf(v2.x, w1.x, acc[u][4]);
-            acc[u][5] = fmaf(v2.y, w1.y, acc[u][5]);
-            acc[u][6] = fmaf(v3.x, w1.z, acc[u][6]);
-            acc[u][7] = fmaf(v3.y, w1.w, acc[u][7]);
-          }
+        for (int u = 0; u < PASSES; ++u) all_in = all_in && (vmask[u] == 0x1FFu);
+        all_in = __all_sync(FULL, all_in);
+#define CB_DW_TAPS(LOAD)                                                                                   \
+  _Pragma("unroll") for (int t9 = 0; t9 < 9; ++t9) {                                                       \
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(dw_w + t9 * CIN + ch0));                       \
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(dw_w + t9 * CIN + ch0 + 4));                   \
+    uint4 raw[PASSES];                                                                                     \
+    _Pragma("unroll") for (int u = 0; u < PASSES; ++u) raw[u] = LOAD;                                      \
+    _Pragma("unroll") for (int u = 0; u < PASSES; ++u) {                                                   \
+      const __half2* hv = reinterpret_cast<const __half2*>(&raw[u]);                                       \
+      const float2 v0 = __half22float2(hv[0]), v1 = __half22float2(hv[1]), v2 = __half22float2(hv[2]),    \
+                   v3 = __half22float2(hv[3]);                                                             \
+      acc[u][0] = fmaf(v0.x, w0.x, acc[u][0]);                                                             \
+      acc[u][1] = fmaf(v0.y, w0.y, acc[u][1]);                                                             \
+      acc[u][2] = fmaf(v1.x, w0.z, acc[u][2]);                                                             \
+      acc[u][3] = fmaf(v1.y, w0.w, acc[u][3]);                                                             \
+      acc[u][4] = fmaf(v2.x, w1.x, acc[u][4]);                                                             \
+      acc[u][5] = fmaf(v2.y, w1.y, acc[u][5]);                                                             \
+      acc[u][6] = fmaf(v3.x, w1.z, acc[u][6]);                                                             \
+      acc[u][7] = fmaf(v3.y, w1.w, acc[u][7]);                                                             \
+    }                                                                                                      \
+  }
+        if (all_in) {
+          CB_DW_TAPS(*reinterpret_cast<const uint4*>(pb[u] + tap_off[t9] + ch0))
+        } else {
+          CB_DW_TAPS((((vmask[u] >> t9) & 1u) ? *reinterpret_cast<const uint4*>(pb[u] + tap_off[t9] + ch0)
+                                              : make_uint4(0u, 0u, 0u, 0u)))
         }
+#undef CB_DW_TAPS
         bool pok[PASSES];
 #pragma unroll
         for (int u = 0; u < PASSES; ++u) pok[u] = tile * 128 + u * PIX_PER_PASS + pl < M_total;
@@ -988,17 +997,22 @@ __global__ void __launch_bounds__(kGemmThreads) vlad_assign_tc_kernel(const __gr
   }
 }
 
-// grid (D/64, frames): V[k][d] = sum_p a[p][k] (x[p][d] + C[d][k]) for a 64-wide d slice
+// grid (D/64, frames, kAggSplit): partial V[k][d] = sum over a quarter of the pixels of a[p][k] x[p][d] (and of a[p][k])
+// for a 64-wide d slice; the kAggSplit partials are summed in a fixed order by vlad_norm_kernel, which also adds the
+// cluster-centre term  C[d][k] * sum_p a[p][k]  (x + C, PLUS, predict_utils.py:47).
+constexpr int kAggSplit = 4;
+
 __global__ void __launch_bounds__(256) vlad_aggregate_kernel(const __half* __restrict__ x, const float* __restrict__ a,
-                                                            int P, int D, const float* __restrict__ Cc /*[D][16]*/,
-                                                            float* __restrict__ V /*[frames][16][D]*/) {
-  const int f = blockIdx.y, d0 = blockIdx.x * 64;
+                                                            int P, int D, float* __restrict__ Vp /*[frames][split][16][D]*/,
+                                                            float* __restrict__ Ap /*[frames][split][16]*/) {
+  const int f = blockIdx.y, d0 = blockIdx.x * 64, sp = blockIdx.z;
   const int k = threadIdx.x >> 4, dq = threadIdx.x & 15;
+  const int p_begin = (int)((long long)P * sp / kAggSplit), p_end = (int)((long long)P * (sp + 1) / kAggSplit);
   const __half* xf = x + (size_t)f * P * D + d0 + dq * 4;
   const float* af = a + (size_t)f * P * kK + k;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, asum = 0.f;
 #pragma unroll 4
-  for (int p = 0; p < P; ++p) {
+  for (int p = p_begin; p < p_end; ++p) {
     const float av = af[(size_t)p * kK];
     const uint2 raw = *reinterpret_cast<const uint2*>(xf + (size_t)p * D);
     const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
@@ -1010,22 +1024,36 @@ __global__ void __launch_bounds__(256) vlad_aggregate_kernel(const __half* __res
     asum += av;
   }
   const int d = d0 + dq * 4;
-  float* vo = V + ((size_t)f * kK + k) * D + d;
-  vo[0] = acc0 + asum * Cc[(size_t)(d + 0) * kK + k];
-  vo[1] = acc1 + asum * Cc[(size_t)(d + 1) * kK + k];
-  vo[2] = acc2 + asum * Cc[(size_t)(d + 2) * kK + k];
-  vo[3] = acc3 + asum * Cc[(size_t)(d + 3) * kK + k];
+  float* vo = Vp + (((size_t)f * kAggSplit + sp) * kK + k) * D + d;
+  vo[0] = acc0, vo[1] = acc1, vo[2] = acc2, vo[3] = acc3;
+  if (blockIdx.x == 0 && dq == 0) Ap[((size_t)f * kAggSplit + sp) * kK + k] = asum;
 }
 
-// CTA per frame: intra-normalise each cluster over D, flatten K-major, L2-normalise (eps 1e-12 on the
-// squared norm, like tf.nn.l2_normalize)
-__global__ void __launch_bounds__(512) vlad_norm_kernel(const float* __restrict__ V, int D, float* __restrict__ out) {
+// CTA per frame: sum the pixel-split partials, add the centre term, intra-normalise each cluster over D, flatten
+// K-major, L2-normalise (eps 1e-12 on the squared norm, like tf.nn.l2_normalize).  D <= 512.
+__global__ void __launch_bounds__(512) vlad_norm_kernel(const float* __restrict__ Vp, const float* __restrict__ Ap,
+                                                       const float* __restrict__ Cc /*[D][16]*/, int D,
+                                                       float* __restrict__ out) {
   __shared__ float s_ss[kK];
   const int f = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 16 warps, one per cluster
-  const float* v = V + ((size_t)f * kK + warp) * D;
+  float asum = 0.f;
+#pragma unroll
+  for (int sp = 0; sp < kAggSplit; ++sp) asum += Ap[((size_t)f * kAggSplit + sp) * kK + warp];
+  float v[16];  // D / 32 values per lane (D <= 512)
   float ss = 0.f;
-  for (int d = lane; d < D; d += 32) ss = fmaf(v[d], v[d], ss);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int d = lane + 32 * i;
+    float val = 0.f;
+    if (d < D) {
+#pragma unroll
+      for (int sp = 0; sp < kAggSplit; ++sp) val += Vp[(((size_t)f * kAggSplit + sp) * kK + warp) * D + d];
+      val += asum * Cc[(size_t)d * kK + warp];
+    }
+    v[i] = val;
+    ss = fmaf(val, val, ss);
+  }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(FULL, ss, off);
   if (lane == 0) s_ss[warp] = ss;
@@ -1039,7 +1067,11 @@ __global__ void __launch_bounds__(512) vlad_norm_kernel(const float* __restrict_
   }
   const float inv_t = rsqrtf(fmaxf(tot, 1e-12f));
   float* o = out + (size_t)f * kK * D + (size_t)warp * D;
-  for (int d = lane; d < D; d += 32) o[d] = v[d] * inv_k * inv_t;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int d = lane + 32 * i;
+    if (d < D) o[d] = v[i] * inv_k * inv_t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1257,9 +1289,10 @@ int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cud
         d->act[cur], Ptot, d->D, d->vlad_w, d->vlad_b, d->assign);
     CB_LAUNCH_CHECK();
   }
-  vlad_aggregate_kernel<<<dim3(d->D / 64, n), 256, 0, st>>>(d->act[cur], d->assign, P, d->D, d->vlad_c, d->Vraw);
+  float* Ap = d->Vraw + (size_t)d->max_batch * kAggSplit * kK * d->D;  // [frames][split][16] after the partial V block
+  vlad_aggregate_kernel<<<dim3(d->D / 64, n, kAggSplit), 256, 0, st>>>(d->act[cur], d->assign, P, d->D, d->Vraw, Ap);
   CB_LAUNCH_CHECK();
-  vlad_norm_kernel<<<n, 512, 0, st>>>(d->Vraw, d->D, out_dev);
+  vlad_norm_kernel<<<n, 512, 0, st>>>(d->Vraw, Ap, d->vlad_c, d->D, out_dev);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
@@ -1332,7 +1365,7 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
   d->Wf = wd;
   d->D = c;
   d->K = w->vlad_k;
-  if (w->vlad_d != c || c % 64) {
+  if (w->vlad_d != c || c % 64 || c > 512) {
     cb_descriptor_destroy(d);
     return cb::fail(CB_EINVAL, "NetVLAD input dim %d does not match backbone output %d (or not a multiple of 64)", w->vlad_d, c);
   }
@@ -1340,7 +1373,7 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
   cudaError_t e = cudaSuccess;
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc((void**)&d->act[i], d->act_elems * sizeof(__half));
   if (e == cudaSuccess) e = cudaMalloc((void**)&d->assign, (size_t)max_batch * d->Hf * d->Wf * kK * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d->Vraw, (size_t)max_batch * kK * d->D * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d->Vraw, (size_t)max_batch * kAggSplit * kK * (d->D + 1) * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&d->img_dev, (size_t)max_batch * rows * cols * chnls);
   if (e == cudaSuccess) e = cudaMalloc((void**)&d->out_dev, (size_t)max_batch * kK * d->D * sizeof(float));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
