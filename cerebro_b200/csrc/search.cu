@@ -555,6 +555,129 @@ scores_ring_kernel(const float* __restrict__ rows, long long n_rows, int d, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Same sweep with packed fp32 FMAs (FFMA2: two IEEE fp32 fmas per issue slot, `fma.rn.f32x2`).  The pair is
+// (query 2p, query 2p+1) of one row: the database element is duplicated into both halves of a register pair
+// (one MOV per 8 FFMA2), the two queries' elements come out of shared memory already adjacent -- the query
+// tile is stored [segment][component][query quad][lane] so that one conflict-free LDS.128 yields component c
+// of four queries for this lane's element.  Per (row, query) the products are still accumulated in the order
+// x,y,z,w of consecutive segments, each with a single-rounding fma: results are bit-identical to
+// scores_kernel<16,8>; the FMA pipe sees half the instructions.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dup_f32x2(float x) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+scores_ring2_kernel(const float* __restrict__ rows, long long n_rows, int d, int ds, int n_slices,
+                    const float* __restrict__ xq, int nq_valid, float* __restrict__ partial, long long pstride,
+                    long long slice_stride) {
+  constexpr int QT = 16, R = 8;
+  extern __shared__ float4 sq[];  // queries [ds/128][4 comps][4 quads][32 lanes] float4 | ring [warps][stages][R][32] float4
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int slice = blockIdx.x % n_slices;
+  const int group = blockIdx.x / n_slices;
+  const int n_groups = gridDim.x / n_slices;
+  const int d0 = slice * ds;
+  const int ds4 = ds >> 2;
+  float4* ring = sq + QT * ds4 + (size_t)warp * kRingStages * R * 32 + lane;
+
+  {
+    float* sqf = reinterpret_cast<float*>(sq);
+    for (int i = tid; i < QT * ds4; i += kThreads) {
+      const int t = i / ds4, c4 = i - t * ds4;  // query, float4 index inside the slice (= segment*32 + lane)
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < nq_valid) v = reinterpret_cast<const float4*>(xq + (size_t)t * d + d0)[c4];
+      const int j = c4 >> 5, ln = c4 & 31;
+      float* dst = sqf + ((size_t)(j * 16 + (t >> 2)) * 32 + ln) * 4 + (t & 3);  // component 0; +4*32*4 floats per component
+      dst[0 * 512] = v.x;
+      dst[1 * 512] = v.y;
+      dst[2 * 512] = v.z;
+      dst[3 * 512] = v.w;
+    }
+  }
+  __syncthreads();
+
+  constexpr int kRowsPerCta = kWarps * R;
+  const long long n_blocks = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
+  const int nj = ds >> 7;
+
+  for (long long rb = group; rb < n_blocks; rb += n_groups) {
+    const long long r0 = rb * kRowsPerCta + (long long)warp * R;
+    if (r0 >= n_rows) continue;  // warp-uniform
+    unsigned long long acc2[R * QT / 2];  // [r][query pair]
+#pragma unroll
+    for (int i = 0; i < R * QT / 2; ++i) acc2[i] = 0ull;
+    const float4* p[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      long long rr = r0 + r;
+      if (rr >= n_rows) rr = n_rows - 1;  // tail rows: computed, never written
+      p[r] = reinterpret_cast<const float4*>(rows + (size_t)rr * d + d0) + lane;
+    }
+#pragma unroll
+    for (int st = 0; st < kRingStages - 1; ++st) {
+      if (st < nj) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) cp_async16(ring + (st * R + r) * 32, p[r] + st * 32);
+      }
+      cp_async_commit();
+    }
+    for (int j = 0; j < nj; ++j) {
+      const int jn = j + kRingStages - 1;
+      if (jn < nj) {
+        const int stn = jn % kRingStages;
+#pragma unroll
+        for (int r = 0; r < R; ++r) cp_async16(ring + (stn * R + r) * 32, p[r] + jn * 32);
+      }
+      cp_async_commit();
+      cp_async_wait<kRingStages - 1>();  // segment j has landed (for this lane's own chunks)
+      const int stc = j % kRingStages;
+      float4 cur[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) cur[r] = ring[(stc * R + r) * 32];
+      const ulonglong2* qb = reinterpret_cast<const ulonglong2*>(sq) + (size_t)j * 512 + lane;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ulonglong2 qv[4];
+#pragma unroll
+        for (int tq = 0; tq < 4; ++tq) qv[tq] = qb[(c * 4 + tq) * 32];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float xc = c == 0 ? cur[r].x : (c == 1 ? cur[r].y : (c == 2 ? cur[r].z : cur[r].w));
+          const unsigned long long xd = dup_f32x2(xc);
+#pragma unroll
+          for (int tq = 0; tq < 4; ++tq) {
+            acc2[r * 8 + 2 * tq] = ffma2(xd, qv[tq].x, acc2[r * 8 + 2 * tq]);
+            acc2[r * 8 + 2 * tq + 1] = ffma2(xd, qv[tq].y, acc2[r * 8 + 2 * tq + 1]);
+          }
+        }
+      }
+    }
+    cp_async_wait<0>();
+    float acc[R * QT];
+#pragma unroll
+    for (int i = 0; i < R * QT / 2; ++i)
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * i]), "=f"(acc[2 * i + 1]) : "l"(acc2[i]));
+    float* out = partial + (size_t)slice * slice_stride;
+    warp_reduce_scatter<R * QT>(acc, lane);
+#pragma unroll
+    for (int g = 0; g < (R * QT) / 32; ++g) {
+      const int id = g * 32 + lane;
+      const int r = id / QT, t = id % QT;
+      if (r0 + r < n_rows && t < nq_valid) out[(size_t)t * pstride + r0 + r] = acc[g];
+    }
+  }
+}
+
 template <int QT, int R>
 cudaError_t launch_scores(int grid, size_t smem, cudaStream_t st, const float* rows, long long n_rows,
                           int d, int ds, int n_slices, const float* xq, int nq_valid, float* partial,
@@ -593,6 +716,7 @@ struct cb_index {
   int max_qt = 16;
   int* work_counter = nullptr;
   bool no_ring = false;  // CB_NO_RING=1: register-prefetch sweep for the 16-query tile as well
+  bool no_ffma2 = false;  // CB_NO_FFMA2=1: scalar-FFMA version of the 16-query ring sweep
   // optional device-side timing of the sweep kernel (bench.py roofline)
   bool timing = false;
   cudaEvent_t ev[2 * 64] = {};
@@ -708,10 +832,11 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
         default: {
           const size_t ring_bytes = (size_t)kWarps * kRingStages * 8 * 32 * sizeof(float4);
           if (p.smem + ring_bytes <= 227 * 1024 && !ix->no_ring) {
-            e = cudaFuncSetAttribute(scores_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.smem + ring_bytes));
+            auto kern = ix->no_ffma2 ? scores_ring_kernel : scores_ring2_kernel;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.smem + ring_bytes));
             if (e == cudaSuccess) {
-              scores_ring_kernel<<<p.grid, kThreads, p.smem + ring_bytes, st>>>(ix->rows, n_rows, ix->d, p.ds, p.n_slices, xq,
-                                                                                nq_valid, ptile, pstride, slice_stride);
+              kern<<<p.grid, kThreads, p.smem + ring_bytes, st>>>(ix->rows, n_rows, ix->d, p.ds, p.n_slices, xq, nq_valid, ptile,
+                                                                  pstride, slice_stride);
               e = cudaGetLastError();
             }
           } else {
@@ -762,6 +887,8 @@ int cb_index_create(cb_index** out, int d, int64_t capacity, int device, int ran
   {
     const char* env = getenv("CB_NO_RING");
     ix->no_ring = env && env[0] == '1';
+    const char* env2 = getenv("CB_NO_FFMA2");
+    ix->no_ffma2 = env2 && env2[0] == '1';
   }
   cudaError_t e = cudaMalloc(&ix->rows, (size_t)capacity * d * sizeof(float));
   if (e != cudaSuccess) {
