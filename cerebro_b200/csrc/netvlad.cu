@@ -676,6 +676,352 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dwpw_kernel(const __half* __
 }
 
 // ---------------------------------------------------------------------------------------------
+// fused depthwise -> pointwise, TMA-halo version (the default).
+// The M tile is a 16 x 8 patch of output pixels of one frame; its (15 S + 3) x (7 S + 3) input halo of one
+// K block of channels is fetched by ONE 4-D TMA box (channels, x, y, frame) into a shared-memory ring --
+// out-of-image taps are zero-filled by the TMA unit, which IS the layer's zero padding -- so the depthwise
+// producers never wait on global memory: they read their 9 taps with conflict-free LDS.128, accumulate with
+// packed FFMA2 and write the swizzled K-major A tile.  Roles:
+//   warp 0      : TMA of the pointwise weights (resident or ring)      warp 6      : TMA of the halos
+//   warp 1      : TMEM allocator + tcgen05.mma issuer                  warps 7-22  : depthwise producers
+//   warps 2-5   : epilogue (bias + ReLU6 + fp16, predicated on the patch being inside the frame)
+// ---------------------------------------------------------------------------------------------
+constexpr int kHaloThreads = 224 + kProdThreads;  // 736
+constexpr int kTH = 16, kTW = 8;
+
+template <int CIN, int COUT, int S>
+struct HaloCfg {
+  static constexpr int KB = (S == 2 || CIN < 64) ? 32 : 64;  // channels per K block (= per halo box)
+  static constexpr int NKB = CIN / KB;
+  static constexpr int SWZ = KB * 2;
+  static constexpr int HH = (kTH - 1) * S + 3, HW = (kTW - 1) * S + 3;
+  static constexpr int kHaloTx = HH * HW * KB * 2;                 // bytes one box delivers
+  static constexpr int kHaloBytes = (kHaloTx + 127) / 128 * 128;   // ring stride (TMA destinations are 128B aligned)
+  static constexpr int kABytes = 128 * KB * 2;
+  static constexpr int kBBytes = COUT * KB * 2;
+  static constexpr bool kResident = NKB * kBBytes <= 128 * 1024;
+  static constexpr int kBS = kResident ? NKB : 2;
+  static constexpr int kStrip = S == 2 ? 2 : 4;                    // output rows per producer task
+  static constexpr int kTasks = (KB / 8) * kTW * (kTH / kStrip);   // producer tasks per K block (256 or 128)
+  static constexpr int kTeams = kProdThreads / kTasks;             // K blocks in production concurrently (2 or 4)
+  static constexpr int kTeamWarps = kTasks / 32;
+  static constexpr int kAS = kBS * kBBytes >= 128 * 1024 ? 2 : (kTeams > 3 ? kTeams : 3);
+  static constexpr int kStageBytes = 4 * 32 * 128;                 // epilogue staging: 32 pixels x 64 channels per warp
+  static constexpr int kBudget = 232448 - 1024 - 512 - kStageBytes;
+  static constexpr int kFit = (kBudget - kBS * kBBytes - kAS * kABytes) / kHaloBytes;
+  static constexpr int kHS = kFit > 4 ? 4 : kFit;
+  static_assert(kHS >= 2, "halo ring needs two stages");
+  static constexpr int kAcc = COUT <= 256 ? 2 : 1;
+  // a team waits on ring slot g % K with parity (g / K) & 1: that is only well defined while it cannot run more than one
+  // phase ahead of the slot, i.e. while the number of teams does not exceed the ring depth
+  static_assert(kTeams <= kAS && kTeams <= kHS, "more producer teams than ring slots");
+  static constexpr int kTotal = kAS * kABytes + kBS * kBBytes + kStageBytes + kHS * kHaloBytes + 1024 + 512;
+};
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+template <int CIN, int COUT, int S>
+__global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid_constant__ CUtensorMap tmH,
+                                                                   const float* __restrict__ dw_w /*[3][3][CIN]*/,
+                                                                   const float* __restrict__ dw_b,
+                                                                   const __grid_constant__ CUtensorMap tmB,
+                                                                   const float* __restrict__ bias,
+                                                                   const __grid_constant__ CUtensorMap tmO, int tiles_x,
+                                                                   int tiles_per_frame, int n_tiles) {
+  using SM = HaloCfg<CIN, COUT, S>;
+  constexpr int KB = SM::KB, NKB = SM::NKB, SWZ = SM::SWZ;
+  constexpr int kAS = SM::kAS, kHS = SM::kHS, kAcc = SM::kAcc;
+  constexpr int N_MMA = COUT > 256 ? 256 : COUT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + kAS * SM::kABytes;
+  uint8_t* smem_o = smem_b + SM::kBS * SM::kBBytes;  // epilogue staging, 4 KB per epilogue warp (1024-aligned)
+  uint8_t* smem_h = smem_o + SM::kStageBytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_h + kHS * SM::kHaloBytes);
+  uint64_t* a_empty = a_full + 4;
+  uint64_t* h_full = a_empty + 4;
+  uint64_t* h_empty = h_full + 4;
+  uint64_t* b_full = h_empty + 4;  // [2] (ring) or [1] (resident)
+  uint64_t* b_empty = b_full + 2;
+  uint64_t* tmem_full_bar = b_empty + 2;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmH);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&a_full[s], SM::kTeamWarps);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&h_full[s], 1);
+      mbar_init(&h_empty[s], SM::kTeamWarps);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc(tmem_ptr, kAcc * COUT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (SM::kResident) {
+        mbar_expect_tx(&b_full[0], NKB * SM::kBBytes);
+        for (int kb = 0; kb < NKB; ++kb) {
+          uint8_t* sb = smem_b + kb * SM::kBBytes;
+          tma_load_2d(&tmB, &b_full[0], sb, kb * KB, 0);
+          if (COUT > 256) tma_load_2d(&tmB, &b_full[0], sb + 256 * KB * 2, kb * KB, 256);
+        }
+      } else {
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+          for (int kb = 0; kb < NKB; ++kb, ++g) {
+            const int s = g & 1;
+            mbar_wait(&b_empty[s], ((g >> 1) & 1) ^ 1);
+            mbar_expect_tx(&b_full[s], SM::kBBytes);
+            uint8_t* sb = smem_b + s * SM::kBBytes;
+            tma_load_2d(&tmB, &b_full[s], sb, kb * KB, 0);
+            if (COUT > 256) tma_load_2d(&tmB, &b_full[s], sb + 256 * KB * 2, kb * KB, 256);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(N_MMA >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t g = 0, ti = 0;
+      if (SM::kResident) mbar_wait(&b_full[0], 0);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        const int acc = ti % kAcc;
+        mbar_wait(&tmem_empty_bar[acc], ((ti / kAcc) & 1) ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * COUT;
+        for (int kb = 0; kb < NKB; ++kb, ++g) {
+          const int sa = g % kAS;
+          const int sb = SM::kResident ? kb : (int)(g & 1);
+          if (!SM::kResident) mbar_wait(&b_full[sb], (g >> 1) & 1);
+          mbar_wait(&a_full[sa], (g / kAS) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + sa * SM::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + sb * SM::kBBytes);
+#pragma unroll
+          for (int k = 0; k < KB / 16; ++k) {
+            const uint64_t ad = make_kmajor_desc<SWZ>(a_addr + k * 32);
+#pragma unroll
+            for (int h = 0; h < COUT / N_MMA; ++h) {
+              const uint64_t bd = make_kmajor_desc<SWZ>(b_addr + h * (256 * KB * 2) + k * 32);
+              umma_f16(d_tmem + h * 256, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(&a_empty[sa]);
+          if (!SM::kResident) umma_commit(&b_empty[sb]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else if (warp < 6) {
+    // ---- epilogue: TMEM -> bias + ReLU6 -> fp16 -> swizzled staging row -> TMA store of a (64 ch, 8 x, 4 y) box; the
+    //      TMA unit clips the parts of the patch that lie outside the frame
+    const int q = warp & 3;
+    const uint32_t stage = smem_u32(smem_o + q * 4096);
+    const uint32_t srow = stage + lane * 128;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int acc = ti % kAcc;
+      const int f = tile / tiles_per_frame, rem = tile - f * tiles_per_frame;
+      const int tyi = rem / tiles_x, txi = rem - tyi * tiles_x;
+      mbar_wait(&tmem_full_bar[acc], (ti / kAcc) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < COUT; c += 64) {
+        if (lane == 0) bulk_wait_read0();  // the previous store has finished reading the staging rows
+        __syncwarp();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + acc * COUT + ((uint32_t)(q * 32) << 16) + (uint32_t)(c + hh * 32), v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c + hh * 32 + j));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + hh * 32 + j + 4));
+            __half2 h[4];
+            h[0] = __floats2half2_rn(relu6(__uint_as_float(v[j + 0]) + b0.x), relu6(__uint_as_float(v[j + 1]) + b0.y));
+            h[1] = __floats2half2_rn(relu6(__uint_as_float(v[j + 2]) + b0.z), relu6(__uint_as_float(v[j + 3]) + b0.w));
+            h[2] = __floats2half2_rn(relu6(__uint_as_float(v[j + 4]) + b1.x), relu6(__uint_as_float(v[j + 5]) + b1.y));
+            h[3] = __floats2half2_rn(relu6(__uint_as_float(v[j + 6]) + b1.z), relu6(__uint_as_float(v[j + 7]) + b1.w));
+            const int chunk = hh * 4 + (j >> 3);
+            sts128(srow + ((chunk ^ (lane & 7)) << 4), *reinterpret_cast<uint4*>(h));
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&tmO, stage, c, txi * kTW, tyi * kTH + q * 4, f);
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+    if (lane == 0) bulk_wait0();
+  } else if (warp == 6) {
+    if (lane == 0) {
+      constexpr int P = (S == 1) ? 1 : 0;
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int f = tile / tiles_per_frame, rem = tile - f * tiles_per_frame;
+        const int tyi = rem / tiles_x, txi = rem - tyi * tiles_x;
+        const int x0 = txi * kTW * S - P, y0 = tyi * kTH * S - P;
+        for (int kb = 0; kb < NKB; ++kb, ++g) {
+          const int hs = g % kHS;
+          mbar_wait(&h_empty[hs], ((g / kHS) & 1) ^ 1);
+          mbar_expect_tx(&h_full[hs], SM::kHaloTx);
+          tma_load_4d(&tmH, &h_full[hs], smem_h + hs * SM::kHaloBytes, kb * KB, x0, y0, f);
+        }
+      }
+    }
+  } else {
+    // ---- depthwise producers.  Task = (group of 8 channels, column tx, strip of kStrip output rows): the (kStrip-1)S+3 input rows
+    //      of a column are each read once per kx and feed up to three output rows from registers; the 3 weights of
+    //      the kx column are fetched once per task.  A team of kTasks threads produces one K block; the kTeams teams
+    //      work on consecutive K blocks concurrently.
+    const int pt = threadIdx.x - 224;  // 0..511
+    constexpr int CGB = KB / 8;
+    constexpr int PXB = KB * 2;  // bytes per halo pixel
+    constexpr int kStrip = SM::kStrip;
+    constexpr int NR = (kStrip - 1) * S + 3;
+    const int team = pt / SM::kTasks, tt = pt % SM::kTasks;
+    const int cgl = tt % CGB;
+    const int tx = (tt / CGB) % kTW;
+    const int strip = tt / (CGB * kTW);
+    const uint32_t hoff = (uint32_t)((strip * kStrip * S * SM::HW + tx * S) * PXB + cgl * 16);
+    uint32_t aoff[kStrip];
+#pragma unroll
+    for (int i = 0; i < kStrip; ++i) {
+      const int r = (strip * kStrip + i) * kTW + tx;
+      const int chunk = (SWZ == 128) ? (cgl ^ (r & 7)) : (cgl ^ ((r >> 1) & 3));
+      aoff[i] = (uint32_t)(r * SWZ + chunk * 16);
+    }
+    const uint32_t smem_h_u32 = smem_u32(smem_h), smem_a_u32 = smem_u32(smem_a);
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t total = (uint32_t)my_tiles * NKB;
+    for (uint32_t g = team; g < total; g += SM::kTeams) {
+      const int kb = g % NKB;
+      const int sa = g % kAS, hs = g % kHS;
+      const int ch0 = kb * KB + cgl * 8;
+      unsigned long long acc[kStrip][4];
+      {
+        const ulonglong2 bb0 = __ldg(reinterpret_cast<const ulonglong2*>(dw_b + ch0));
+        const ulonglong2 bb1 = __ldg(reinterpret_cast<const ulonglong2*>(dw_b + ch0 + 4));
+#pragma unroll
+        for (int i = 0; i < kStrip; ++i) acc[i][0] = bb0.x, acc[i][1] = bb0.y, acc[i][2] = bb1.x, acc[i][3] = bb1.y;
+      }
+      mbar_wait(&h_full[hs], (g / kHS) & 1);
+      const uint32_t hb = smem_h_u32 + hs * SM::kHaloBytes + hoff;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        unsigned long long w[3][4];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const ulonglong2 w0 = __ldg(reinterpret_cast<const ulonglong2*>(dw_w + (ky * 3 + kx) * CIN + ch0));
+          const ulonglong2 w1 = __ldg(reinterpret_cast<const ulonglong2*>(dw_w + (ky * 3 + kx) * CIN + ch0 + 4));
+          w[ky][0] = w0.x, w[ky][1] = w0.y, w[ky][2] = w1.x, w[ky][3] = w1.y;
+        }
+#pragma unroll
+        for (int ir = 0; ir < NR; ++ir) {
+          const uint4 raw = lds128(hb + (ir * SM::HW + kx) * PXB);
+          const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+          unsigned long long v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 fv = __half22float2(hv[j]);
+            v[j] = pack_f32x2(fv.x, fv.y);
+          }
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int d = ir - ky;
+            if (d >= 0 && d % S == 0 && d / S < kStrip) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[d / S][j] = ffma2(v[j], w[ky][j], acc[d / S][j]);
+            }
+          }
+        }
+      }
+      mbar_wait(&a_empty[sa], ((g / kAS) & 1) ^ 1);
+      const uint32_t at = smem_a_u32 + sa * SM::kABytes;
+#pragma unroll
+      for (int i = 0; i < kStrip; ++i) {
+        __half2 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float lo, hi;
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i][j]));
+          h[j] = __floats2half2_rn(relu6(lo), relu6(hi));
+        }
+        sts128(at + aoff[i], *reinterpret_cast<uint4*>(h));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&a_full[sa]);
+        mbar_arrive(&h_empty[hs]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kAcc * COUT);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // stem on tcgen05: implicit GEMM  [pixels x 32 (27 taps, zero padded)] x [32 x 32 output channels].
 //   warp 0    : TMEM allocator + tcgen05.mma issuer
 //   warps 1-4 : im2col producers (one output pixel per thread: 27 byte loads -> exact fp16 integers x-128
@@ -1081,7 +1427,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+int encode_fn(EncodeTiledFn* out) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -1089,6 +1435,34 @@ int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
     if (e != cudaSuccess || !p) return cb::fail(CB_ECUDA, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
     fn = (EncodeTiledFn)p;
+  }
+  *out = fn;
+  return CB_OK;
+}
+
+// NHWC fp16 activation [frames][H][W][C] as a 4-D tensor (C, W, H, frames); box = one K block of channels of a
+// halo patch.  No swizzle: the depthwise producers read 16-byte channel groups of consecutive pixels.
+int make_map_halo(CUtensorMap* map, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t frames, uint32_t box_c,
+                  uint32_t box_w, uint32_t box_h, bool swizzle128 = false) {
+  EncodeTiledFn fn = nullptr;
+  int rc = encode_fn(&fn);
+  if (rc) return rc;
+  const cuuint64_t dims[4] = {C, W, H, frames};
+  const cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  const cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cb::fail(CB_ECUDA, "cuTensorMapEncodeTiled (halo) failed with CUresult %d", (int)r);
+  return CB_OK;
+}
+
+int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = nullptr;
+  {
+    int rc = encode_fn(&fn);
+    if (rc) return rc;
   }
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {cols * 2};
@@ -1114,6 +1488,10 @@ struct Block {
   CUtensorMap tmA[2], tmB;  // A map per ping-pong buffer (the GEMM input may live in either)
   bool fused = false;  // depthwise folded into the tcgen05 GEMM producer
   CUtensorMap tmBf;    // weight map with a <=256-row box for the fused kernel
+  bool halo = false;   // TMA-halo version of the fused kernel available
+  CUtensorMap tmH[2];  // 4-D halo maps of the block's input, one per ping-pong buffer
+  CUtensorMap tmO[2];  // 4-D store maps of the block's output (64 ch x 8 x 4 boxes, 128B swizzle)
+  CUtensorMap tmBh;    // weight map with the halo kernel's K block
 };
 
 }  // namespace
@@ -1144,6 +1522,7 @@ struct cb_descriptor {
   cudaStream_t stream = nullptr;
   bool force_simt = false;
   bool no_fuse = false;  // CB_NO_FUSE=1: separate depthwise + GEMM kernels
+  bool no_halo = false;  // CB_NO_HALO=1: fused kernel whose producers read the activations straight from global memory
   int stop_layer = -1;  // CB_DEBUG_STOP_LAYER: stop the forward pass after this layer (bring-up / parity tests)
   int last_buf = 0;                 // ping-pong buffer holding the most recent layer output
   std::vector<size_t> layer_elems;  // per-frame elements of layer l's output
@@ -1198,6 +1577,31 @@ int run_fused(const Block& b, int n, int sm, const __half* in, __half* out, cuda
   return launch_fused<512, 512, 1>(b, n, sm, in, out, st);
 }
 
+template <int CIN, int COUT, int S>
+int launch_halo(const Block& b, int n, int sm_count, int in_buf, cudaStream_t st) {
+  using SM = HaloCfg<CIN, COUT, S>;
+  auto kern = dwpw_halo_kernel<CIN, COUT, S>;
+  CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+  const int tiles_x = (b.Wo + kTW - 1) / kTW, tiles_y = (b.Ho + kTH - 1) / kTH;
+  const int per_frame = tiles_x * tiles_y;
+  const int n_tiles = n * per_frame;
+  const int grid = n_tiles < sm_count ? n_tiles : sm_count;  // persistent: one CTA per SM
+  kern<<<grid, kHaloThreads, SM::kTotal, st>>>(b.tmH[in_buf], b.dw_w, b.dw_b, b.tmBh, b.pw_b, b.tmO[in_buf ^ 1], tiles_x, per_frame,
+                                               n_tiles);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+int run_halo(const Block& b, int n, int sm, int in_buf, cudaStream_t st) {
+  if (b.C == 32) return launch_halo<32, 64, 1>(b, n, sm, in_buf, st);
+  if (b.C == 64) return launch_halo<64, 128, 2>(b, n, sm, in_buf, st);
+  if (b.C == 128 && b.Cout == 128) return launch_halo<128, 128, 1>(b, n, sm, in_buf, st);
+  if (b.C == 128) return launch_halo<128, 256, 2>(b, n, sm, in_buf, st);
+  if (b.C == 256 && b.Cout == 256) return launch_halo<256, 256, 1>(b, n, sm, in_buf, st);
+  if (b.C == 256) return launch_halo<256, 512, 2>(b, n, sm, in_buf, st);
+  return launch_halo<512, 512, 1>(b, n, sm, in_buf, st);
+}
+
 int run_pw(cb_descriptor* d, const Block& b, long long M, int in_buf, __half* out, cudaStream_t st) {
   const __half* in = d->act[in_buf];
   if (b.use_tc && !d->force_simt) {
@@ -1249,7 +1653,8 @@ int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cud
     const int dw_layer = layer + 1, pw_layer = layer + 2;
     if (b.has_pw && b.use_tc && b.fused && !d->no_fuse && !d->force_simt && d->stop_layer != dw_layer) {
       // fused depthwise -> pointwise: one kernel, one ping-pong flip (the depthwise output never exists)
-      int rc = run_fused(b, n, d->sm_count, d->act[cur], d->act[cur ^ 1], st);
+      int rc = (b.halo && !d->no_halo) ? run_halo(b, n, d->sm_count, cur, st)
+                                       : run_fused(b, n, d->sm_count, d->act[cur], d->act[cur ^ 1], st);
       if (rc) return rc;
       cur ^= 1;
       d->last_buf = cur;
@@ -1327,6 +1732,8 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
   d->force_simt = env && env[0] == '1';
   const char* env3 = getenv("CB_NO_FUSE");
   d->no_fuse = env3 && env3[0] == '1';
+  const char* env4 = getenv("CB_NO_HALO");
+  d->no_halo = env4 && env4[0] == '1';
   const char* env2 = getenv("CB_DEBUG_STOP_LAYER");
   d->stop_layer = env2 ? atoi(env2) : -1;
   d->H1 = conv_out_s2(rows);
@@ -1448,6 +1855,18 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
         if (b.fused && !rc)
           rc = make_map_2d(&b.tmBf, b.pw_w, (uint64_t)b.Cout, (uint64_t)b.C, (uint32_t)(b.Cout > 256 ? 256 : b.Cout),
                            (uint32_t)(b.C < 64 ? b.C : 64));
+        if (b.fused && !rc) {
+          const uint32_t kbh = (b.stride == 2 || b.C < 64) ? 32 : 64;
+          const uint32_t hh = (kTH - 1) * b.stride + 3, hw = (kTW - 1) * b.stride + 3;
+          int rh = make_map_2d(&b.tmBh, b.pw_w, (uint64_t)b.Cout, (uint64_t)b.C, (uint32_t)(b.Cout > 256 ? 256 : b.Cout), kbh);
+          for (int i2 = 0; i2 < 2 && !rh; ++i2)
+            rh = make_map_halo(&b.tmH[i2], d->act[i2], (uint64_t)b.C, (uint64_t)b.Win, (uint64_t)b.Hin, (uint64_t)max_batch, kbh,
+                               hw, hh);
+          for (int i2 = 0; i2 < 2 && !rh; ++i2)
+            rh = make_map_halo(&b.tmO[i2], d->act[i2], (uint64_t)b.Cout, (uint64_t)b.Wo, (uint64_t)b.Ho, (uint64_t)max_batch, 64, kTW,
+                               4, true);
+          b.halo = rh == CB_OK;  // a frame too small for the box keeps the global-memory producers
+        }
       }
     }
   }
