@@ -20,6 +20,7 @@
 //                         ranks them with the requested tie rule and writes the top k.
 //   merge_lists_kernel  : merges already-final fp64 lists (multi-GPU all-gather result).
 #include "common.cuh"
+#include "ptx.cuh"
 
 #include <math_constants.h>
 #include <stdlib.h>
@@ -569,11 +570,6 @@ __device__ __forceinline__ unsigned long long dup_f32x2(float x) {
   asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 scores_ring2_kernel(const float* __restrict__ rows, long long n_rows, int d, int ds, int n_slices,
@@ -678,6 +674,178 @@ scores_ring2_kernel(const float* __restrict__ rows, long long n_rows, int d, int
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Many-query sweep on the tensor cores (tcgen05, fp16 inputs, fp32 accumulation in TMEM).
+// With more than a handful of queries the fp32 SIMT sweep is FMA-bound (64 queries x 100k x 8192 = 52 GFMA,
+// 1.5 ms at the SM's 128 FMA/clk) although the database only takes 0.5 ms to stream; on the tensor cores the
+// same arithmetic costs a fraction of the load time and the sweep is HBM-bound again.
+//   Operands: every fp32 value x is kept as two fp16 planes, hi = fp16(x) and lo = fp16(x - hi) (22 mantissa bits;
+//   below 6e-5 fp16 goes subnormal and the absolute error is bounded by 3e-8 per element).  The score is accumulated
+//   as  q_hi.x_hi + q_hi.x_lo + q_lo.x_hi  -- three MMAs into the same accumulator, the dropped q_lo.x_lo term is
+//   below 2^-22 relative.  The planes hold 4 bytes per element, exactly the fp32 row: algorithmic bytes unchanged.
+//   The result only RANKS candidates: the 32 best per query are re-scored in fp64 from the fp32 rows (finalize_kernel).
+// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.  Tile = 256 database rows
+// (two 128-row accumulators) x 64 queries; K block = 64 elements (128-byte swizzled rows); 2-stage ring of
+// 80 KB (4 x 16 KB database tiles + 2 x 8 KB query tiles); accumulators double-buffered in TMEM (256 columns).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTcThreads = 192;
+constexpr int kTcRows = 256;      // database rows per tile
+constexpr int kTcQ = 64;          // queries per sweep (N of the MMA)
+constexpr int kTcKB = 64;         // elements per K block
+constexpr int kTcStages = 2;
+constexpr int kTcABytes = 128 * kTcKB * 2;  // one 128-row plane tile
+constexpr int kTcBBytes = kTcQ * kTcKB * 2;
+constexpr int kTcStageBytes = 4 * kTcABytes + 2 * kTcBBytes;
+constexpr int kTcSmem = kTcStages * kTcStageBytes + 1024 + 256;
+
+__global__ void split_f16_kernel(const float* __restrict__ x, long long n, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;  // n is a multiple of 4 (d % 128 == 0)
+  const float4 v = *reinterpret_cast<const float4*>(x + i);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __half h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2half_rn(f[j]);
+    l[j] = __float2half_rn(f[j] - __half2float(h[j]));
+  }
+  *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<uint2*>(l);
+}
+
+// queries: nq rows split into [kTcQ][d] planes, rows >= nq zero
+__global__ void split_queries_kernel(const float* __restrict__ xq, int nq, int d, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)kTcQ * d) return;
+  const int q = (int)(i / d);
+  const float f = q < nq ? xq[i] : 0.f;
+  const __half h = __float2half_rn(f);
+  hi[i] = h;
+  lo[i] = __float2half_rn(f - __half2float(h));
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+scores_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+                 const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, long long n_rows, int d,
+                 int nq_valid, float* __restrict__ partial, long long pstride, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);
+  uint64_t* empty = full + kTcStages;
+  uint64_t* tmem_full_bar = empty + kTcStages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = d / kTcKB;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmAhi);
+    tma_prefetch_desc(&tmAlo);
+    tma_prefetch_desc(&tmBhi);
+    tma_prefetch_desc(&tmBlo);
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc(tmem_ptr, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = tile * kTcRows;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = g % kTcStages;
+          mbar_wait(&empty[s], ((g / kTcStages) & 1) ^ 1);
+          mbar_expect_tx(&full[s], kTcStageBytes);
+          uint8_t* st = smem + s * kTcStageBytes;
+          tma_load_2d(&tmAhi, &full[s], st, kb * kTcKB, row0);
+          tma_load_2d(&tmAhi, &full[s], st + kTcABytes, kb * kTcKB, row0 + 128);
+          tma_load_2d(&tmAlo, &full[s], st + 2 * kTcABytes, kb * kTcKB, row0);
+          tma_load_2d(&tmAlo, &full[s], st + 3 * kTcABytes, kb * kTcKB, row0 + 128);
+          tma_load_2d(&tmBhi, &full[s], st + 4 * kTcABytes, kb * kTcKB, 0);
+          tma_load_2d(&tmBlo, &full[s], st + 4 * kTcABytes + kTcBBytes, kb * kTcKB, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(kTcQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t g = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        const int acc = ti & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = g % kTcStages;
+          mbar_wait(&full[s], (g / kTcStages) & 1);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * kTcStageBytes);
+          const uint32_t b_hi = st + 4 * kTcABytes, b_lo = b_hi + kTcBBytes;
+#pragma unroll
+          for (int k = 0; k < kTcKB / 16; ++k) {
+            const uint64_t bh = make_kmajor_desc<128>(b_hi + k * 32), bl = make_kmajor_desc<128>(b_lo + k * 32);
+#pragma unroll
+            for (int rb = 0; rb < 2; ++rb) {
+              const uint32_t dt = tmem_base + acc * 128 + rb * kTcQ;
+              const uint64_t ah = make_kmajor_desc<128>(st + rb * kTcABytes + k * 32);
+              const uint64_t al = make_kmajor_desc<128>(st + (2 + rb) * kTcABytes + k * 32);
+              umma_f16(dt, ah, bh, idesc, (kb | k) ? 1u : 0u);
+              umma_f16(dt, ah, bl, idesc, 1u);
+              umma_f16(dt, al, bh, idesc, 1u);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int acc = ti & 1;
+      mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int rb = 0; rb < 2; ++rb) {
+        const long long row = (long long)tile * kTcRows + rb * 128 + q * 32 + lane;
+        const bool row_ok = row < n_rows;
+#pragma unroll 1
+        for (int c = 0; c < kTcQ; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + acc * 128 + rb * kTcQ + c + ((uint32_t)(q * 32) << 16), v);
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c + j < nq_valid) partial[(size_t)(c + j) * pstride + row] = __uint_as_float(v[j]);  // warp-uniform test
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 template <int QT, int R>
 cudaError_t launch_scores(int grid, size_t smem, cudaStream_t st, const float* rows, long long n_rows,
                           int d, int ds, int n_slices, const float* xq, int nq_valid, float* partial,
@@ -717,6 +885,14 @@ struct cb_index {
   int* work_counter = nullptr;
   bool no_ring = false;  // CB_NO_RING=1: register-prefetch sweep for the 16-query tile as well
   bool no_ffma2 = false;  // CB_NO_FFMA2=1: scalar-FFMA version of the 16-query ring sweep
+  // tensor-core sweep: fp16 hi/lo planes of the rows (built lazily, kept in step with `rows` at search time)
+  bool no_tc = false;     // CB_NO_TC=1, or the planes could not be allocated: SIMT sweeps only
+  __half* hi = nullptr;   // [capacity][d]
+  __half* lo = nullptr;
+  int64_t split_rows = 0;  // local rows already converted
+  __half* q_hi = nullptr;  // [64][d] query planes
+  __half* q_lo = nullptr;
+  CUtensorMap tmAhi, tmAlo, tmBhi, tmBlo;
   // optional device-side timing of the sweep kernel (bench.py roofline)
   bool timing = false;
   cudaEvent_t ev[2 * 64] = {};
@@ -777,6 +953,43 @@ SweepPlan plan_sweep(const cb_index* ix, int nq_left) {
   return p;
 }
 
+// Tensor-core sweep prerequisites: the fp16 planes exist and cover every local row.  Returns false (and disables the
+// path) when the planes cannot be allocated -- the SIMT sweeps need no extra memory.
+bool ensure_planes(cb_index* ix, cudaStream_t st) {
+  if (ix->no_tc) return false;
+  if (!ix->hi) {
+    const size_t plane = (size_t)ix->capacity * ix->d * sizeof(__half);
+    const size_t qplane = (size_t)kTcQ * ix->d * sizeof(__half);
+    cudaError_t e = cudaMalloc((void**)&ix->hi, plane);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ix->lo, plane);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ix->q_hi, qplane);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ix->q_lo, qplane);
+    int rc = e == cudaSuccess ? CB_OK : CB_ENOMEM;
+    if (!rc) rc = make_map_2d(&ix->tmAhi, ix->hi, (uint64_t)ix->capacity, (uint64_t)ix->d, 128, kTcKB);
+    if (!rc) rc = make_map_2d(&ix->tmAlo, ix->lo, (uint64_t)ix->capacity, (uint64_t)ix->d, 128, kTcKB);
+    if (!rc) rc = make_map_2d(&ix->tmBhi, ix->q_hi, (uint64_t)kTcQ, (uint64_t)ix->d, kTcQ, kTcKB);
+    if (!rc) rc = make_map_2d(&ix->tmBlo, ix->q_lo, (uint64_t)kTcQ, (uint64_t)ix->d, kTcQ, kTcKB);
+    if (!rc) rc = cudaFuncSetAttribute(scores_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem) == cudaSuccess
+                      ? CB_OK
+                      : CB_ECUDA;
+    if (rc) {
+      cudaGetLastError();
+      cudaFree(ix->hi), cudaFree(ix->lo), cudaFree(ix->q_hi), cudaFree(ix->q_lo);
+      ix->hi = ix->lo = ix->q_hi = ix->q_lo = nullptr;
+      ix->no_tc = true;
+      return false;
+    }
+    ix->split_rows = 0;
+  }
+  if (ix->split_rows < ix->nlocal) {
+    const long long n = (long long)(ix->nlocal - ix->split_rows) * ix->d;
+    const size_t off = (size_t)ix->split_rows * ix->d;
+    split_f16_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(ix->rows + off, n, ix->hi + off, ix->lo + off);
+    ix->split_rows = ix->nlocal;
+  }
+  return true;
+}
+
 int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t limit_rows,
                        int tie_mode, double* scores_dev, long long* labels_dev, cudaStream_t st) {
   const int tie_high = tie_mode == CB_TIE_HIGH_LABEL;
@@ -796,6 +1009,13 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
   for (int g0 = 0; g0 < nq; g0 += kGroup) {
     const int gq = (nq - g0) < kGroup ? (nq - g0) : kGroup;
     SweepPlan p = plan_sweep(ix, gq);  // one plan (tile size, d-slicing) for the whole group
+    // more than a few queries: the fp32 SIMT sweep would be FMA-bound; the tensor-core sweep stays HBM-bound
+    const bool use_tc = gq > 4 && ix->d % kTcKB == 0 && ensure_planes(ix, st);
+    if (use_tc) {
+      p.qt = kTcQ;
+      p.n_slices = 1;
+      p.ds = ix->d;
+    }
     const int n_tiles = (gq + p.qt - 1) / p.qt;
     const long long slice_stride = (long long)n_tiles * p.qt * pstride;
     int rc = grow((void**)&ix->partial, &ix->partial_bytes, (size_t)p.n_slices * slice_stride * sizeof(float));
@@ -813,6 +1033,23 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
       const float* xq = xq_dev + (size_t)(g0 + tq) * ix->d;
       float* ptile = ix->partial + (size_t)tq * pstride;
       cudaError_t e = cudaSuccess;
+      if (use_tc) {
+        const long long qelems = (long long)kTcQ * ix->d;
+        split_queries_kernel<<<(unsigned)((qelems + 255) / 256), 256, 0, st>>>(xq, nq_valid, ix->d, ix->q_hi, ix->q_lo);
+        const int n_tc_tiles = (int)((n_rows + kTcRows - 1) / kTcRows);
+        const int grid = n_tc_tiles < ix->sm_count ? n_tc_tiles : ix->sm_count;
+        const bool rec_tc = ix->timing && ix->ev_used < 64;
+        if (rec_tc) cudaEventRecord(ix->ev[2 * ix->ev_used], st);
+        scores_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(ix->tmAhi, ix->tmAlo, ix->tmBhi, ix->tmBlo, n_rows, ix->d, nq_valid, ptile,
+                                                            pstride, n_tc_tiles);
+        if (rec_tc) {
+          cudaEventRecord(ix->ev[2 * ix->ev_used + 1], st);
+          ++ix->ev_used;
+        }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cb::fail(CB_ECUDA, "scores_tc_kernel launch failed: %s", cudaGetErrorString(e));
+        continue;
+      }
       int* wc = nullptr;
       if (p.qt <= 4) {  // streaming regime: dynamic row-group tickets (one counter per d-slice)
         if (!ix->work_counter) CB_CUDA(cudaMalloc((void**)&ix->work_counter, 16 * sizeof(int)));
@@ -889,6 +1126,8 @@ int cb_index_create(cb_index** out, int d, int64_t capacity, int device, int ran
     ix->no_ring = env && env[0] == '1';
     const char* env2 = getenv("CB_NO_FFMA2");
     ix->no_ffma2 = env2 && env2[0] == '1';
+    const char* env3 = getenv("CB_NO_TC");
+    ix->no_tc = env3 && env3[0] == '1';
   }
   cudaError_t e = cudaMalloc(&ix->rows, (size_t)capacity * d * sizeof(float));
   if (e != cudaSuccess) {
@@ -917,6 +1156,10 @@ int cb_index_destroy(cb_index* ix) {
   cudaFree(ix->out_l);
   cudaFree(ix->stage);
   cudaFree(ix->work_counter);
+  cudaFree(ix->hi);
+  cudaFree(ix->lo);
+  cudaFree(ix->q_hi);
+  cudaFree(ix->q_lo);
   for (cudaEvent_t ev : ix->ev)
     if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ix->stream);
@@ -928,6 +1171,7 @@ int cb_index_reset(cb_index* ix) {
   if (!ix) return cb::fail(CB_EINVAL, "index is NULL");
   ix->ntotal = 0;
   ix->nlocal = 0;
+  ix->split_rows = 0;
   return CB_OK;
 }
 
