@@ -606,7 +606,7 @@ constexpr int kTH = 16, kTW = 8;
 
 template <int CIN, int COUT, int S>
 struct HaloCfg {
-  static constexpr int KB = (S == 2 || CIN < 64) ? 32 : 64;  // channels per K block (= per halo box)
+  static constexpr int KB = 32;  // channels per K block (= per halo box): 64-byte pixels, 64-byte swizzled A/B rows
   static constexpr int NKB = CIN / KB;
   static constexpr int SWZ = KB * 2;
   static constexpr int HH = (kTH - 1) * S + 3, HW = (kTW - 1) * S + 3;
@@ -614,18 +614,19 @@ struct HaloCfg {
   static constexpr int kHaloBytes = (kHaloTx + 127) / 128 * 128;   // ring stride (TMA destinations are 128B aligned)
   static constexpr int kABytes = 128 * KB * 2;
   static constexpr int kBBytes = COUT * KB * 2;
-  static constexpr bool kResident = NKB * kBBytes <= 128 * 1024;
-  static constexpr int kBS = kResident ? NKB : 2;
+  static constexpr bool kResident = NKB * kBBytes <= 64 * 1024;    // whole [COUT][CIN] matrix in smem, else a ring
+  static constexpr int kBS = kResident ? NKB : ((S == 2 && kBBytes >= 32 * 1024) ? 2 : 3);
   static constexpr int kStrip = S == 2 ? 2 : 4;                    // output rows per producer task
-  static constexpr int kTasks = (KB / 8) * kTW * (kTH / kStrip);   // producer tasks per K block (256 or 128)
-  static constexpr int kTeams = kProdThreads / kTasks;             // K blocks in production concurrently (2 or 4)
+  static constexpr int kTasks = (KB / 8) * kTW * (kTH / kStrip);   // producer tasks per K block (128 or 256)
+  static constexpr int kTeams = kProdThreads / kTasks;             // K blocks in production concurrently (4 or 2)
   static constexpr int kTeamWarps = kTasks / 32;
-  static constexpr int kAS = kBS * kBBytes >= 128 * 1024 ? 2 : (kTeams > 3 ? kTeams : 3);
+  static constexpr int kAS = kTeams > 3 ? kTeams : 3;
   static constexpr int kStageBytes = 4 * 32 * 128;                 // epilogue staging: 32 pixels x 64 channels per warp
   static constexpr int kBudget = 232448 - 1024 - 512 - kStageBytes;
   static constexpr int kFit = (kBudget - kBS * kBBytes - kAS * kABytes) / kHaloBytes;
-  static constexpr int kHS = kFit > 4 ? 4 : kFit;
-  static_assert(kHS >= 2, "halo ring needs two stages");
+  // halo stages beyond the number of teams are the prefetch depth: a team's next box is already in flight while it
+  // works on the current one
+  static constexpr int kHS = kFit > 8 ? 8 : kFit;
   static constexpr int kAcc = COUT <= 256 ? 2 : 1;
   // a team waits on ring slot g % K with parity (g / K) & 1: that is only well defined while it cannot run more than one
   // phase ahead of the slot, i.e. while the number of teams does not exceed the ring depth
@@ -653,11 +654,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
   uint8_t* smem_h = smem_o + SM::kStageBytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_h + kHS * SM::kHaloBytes);
   uint64_t* a_empty = a_full + 4;
-  uint64_t* h_full = a_empty + 4;
-  uint64_t* h_empty = h_full + 4;
-  uint64_t* b_full = h_empty + 4;  // [2] (ring) or [1] (resident)
-  uint64_t* b_empty = b_full + 2;
-  uint64_t* tmem_full_bar = b_empty + 2;  // [2]
+  uint64_t* h_full = a_empty + 4;  // [8]
+  uint64_t* h_empty = h_full + 8;
+  uint64_t* b_full = h_empty + 8;  // [kBS <= 3] (ring) or [1] (resident)
+  uint64_t* b_empty = b_full + 4;
+  uint64_t* tmem_full_bar = b_empty + 4;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
@@ -670,12 +671,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
     for (int s = 0; s < 4; ++s) {
       mbar_init(&a_full[s], SM::kTeamWarps);
       mbar_init(&a_empty[s], 1);
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 8; ++s) {
       mbar_init(&h_full[s], 1);
       mbar_init(&h_empty[s], SM::kTeamWarps);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 4);
     }
@@ -701,8 +704,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
           for (int kb = 0; kb < NKB; ++kb, ++g) {
-            const int s = g & 1;
-            mbar_wait(&b_empty[s], ((g >> 1) & 1) ^ 1);
+            const int s = g % SM::kBS;
+            mbar_wait(&b_empty[s], ((g / SM::kBS) & 1) ^ 1);
             mbar_expect_tx(&b_full[s], SM::kBBytes);
             uint8_t* sb = smem_b + s * SM::kBBytes;
             tma_load_2d(&tmB, &b_full[s], sb, kb * KB, 0);
@@ -723,8 +726,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
         const uint32_t d_tmem = tmem_base + acc * COUT;
         for (int kb = 0; kb < NKB; ++kb, ++g) {
           const int sa = g % kAS;
-          const int sb = SM::kResident ? kb : (int)(g & 1);
-          if (!SM::kResident) mbar_wait(&b_full[sb], (g >> 1) & 1);
+          const int sb = SM::kResident ? kb : (int)(g % SM::kBS);
+          if (!SM::kResident) mbar_wait(&b_full[sb], (g / SM::kBS) & 1);
           mbar_wait(&a_full[sa], (g / kAS) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + sa * SM::kABytes);
@@ -767,15 +770,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
           tmem_ld32(tmem_base + acc * COUT + ((uint32_t)(q * 32) << 16) + (uint32_t)(c + hh * 32), v);
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c + hh * 32 + j));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + hh * 32 + j + 4));
-            __half2 h[4];
-            h[0] = __floats2half2_rn(relu6(__uint_as_float(v[j + 0]) + b0.x), relu6(__uint_as_float(v[j + 1]) + b0.y));
-            h[1] = __floats2half2_rn(relu6(__uint_as_float(v[j + 2]) + b0.z), relu6(__uint_as_float(v[j + 3]) + b0.w));
-            h[2] = __floats2half2_rn(relu6(__uint_as_float(v[j + 4]) + b1.x), relu6(__uint_as_float(v[j + 5]) + b1.y));
-            h[3] = __floats2half2_rn(relu6(__uint_as_float(v[j + 6]) + b1.z), relu6(__uint_as_float(v[j + 7]) + b1.w));
+            const ulonglong2 b0 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c + hh * 32 + j));
+            const ulonglong2 b1 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c + hh * 32 + j + 4));
+            uint4 o;
+            o.x = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1])), b0.x));
+            o.y = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), b0.y));
+            o.z = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])), b1.x));
+            o.w = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])), b1.y));
             const int chunk = hh * 4 + (j >> 3);
-            sts128(srow + ((chunk ^ (lane & 7)) << 4), *reinterpret_cast<uint4*>(h));
+            sts128(srow + ((chunk ^ (lane & 7)) << 4), o);
           }
         }
         fence_proxy_async();
@@ -877,14 +880,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
       const uint32_t at = smem_a_u32 + sa * SM::kABytes;
 #pragma unroll
       for (int i = 0; i < kStrip; ++i) {
-        __half2 h[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float lo, hi;
-          asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i][j]));
-          h[j] = __floats2half2_rn(relu6(lo), relu6(hi));
-        }
-        sts128(at + aoff[i], *reinterpret_cast<uint4*>(h));
+        uint4 o;
+        o.x = relu6_pack_h2(acc[i][0]);
+        o.y = relu6_pack_h2(acc[i][1]);
+        o.z = relu6_pack_h2(acc[i][2]);
+        o.w = relu6_pack_h2(acc[i][3]);
+        sts128(at + aoff[i], o);
       }
       fence_proxy_async();
       __syncwarp();
@@ -1685,7 +1686,7 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
           rc = make_map_2d(&b.tmBf, b.pw_w, (uint64_t)b.Cout, (uint64_t)b.C, (uint32_t)(b.Cout > 256 ? 256 : b.Cout),
                            (uint32_t)(b.C < 64 ? b.C : 64));
         if (b.fused && !rc) {
-          const uint32_t kbh = (b.stride == 2 || b.C < 64) ? 32 : 64;
+          const uint32_t kbh = 32;  // HaloCfg::KB
           const uint32_t hh = (kTH - 1) * b.stride + 3, hw = (kTW - 1) * b.stride + 3;
           int rh = make_map_2d(&b.tmBh, b.pw_w, (uint64_t)b.Cout, (uint64_t)b.C, (uint32_t)(b.Cout > 256 ? 256 : b.Cout), kbh);
           for (int i2 = 0; i2 < 2 && !rh; ++i2)

@@ -123,6 +123,20 @@ __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
   return r;
 }
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// ReLU6 of two fp32 values, rounded to fp16: clamping AFTER the rounding is identical to clamping before it (0 and 6
+// are exact in fp16 and rounding is monotonic) and costs two half2 min/max instead of four fp32 ones.
+__device__ __forceinline__ uint32_t relu6_pack_h2(unsigned long long v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  __half2 h = __floats2half2_rn(lo, hi);
+  h = __hmin2(__hmax2(h, __float2half2_rn(0.f)), __float2half2_rn(6.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
   unsigned long long r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
