@@ -1225,36 +1225,90 @@ __global__ void __launch_bounds__(kGemmThreads) vlad_assign_tc_kernel(const __gr
   }
 }
 
-// grid (D/64, frames, kAggSplit): partial V[k][d] = sum over a quarter of the pixels of a[p][k] x[p][d] (and of a[p][k])
-// for a 64-wide d slice; the kAggSplit partials are summed in a fixed order by vlad_norm_kernel, which also adds the
-// cluster-centre term  C[d][k] * sum_p a[p][k]  (x + C, PLUS, predict_utils.py:47).
-constexpr int kAggSplit = 4;
+// ---------------------------------------------------------------------------------------------
+// VLAD aggregation: partial V[k][d] = sum over a slice of the pixels of a[p][k] x[p][d].
+// grid (kAggSplit, frames), 256 threads = 4 pixel lanes x 64 channel groups: a thread owns 8 channels x all 16
+// clusters (64 packed-FFMA2 accumulators), reads each x value ONCE (one 16-byte load per pixel) and the pixel's 16
+// soft-assignments through warp-uniform (broadcast) loads.  The 4 pixel lanes are summed through shared memory in a
+// fixed order; the kAggSplit partials are summed in a fixed order by vlad_norm_kernel, which also adds the
+// centre term (sum_p a[p][k]) * C[d][k]  (x + C, predict_utils.py:47).  Deterministic: no atomics.
+// ---------------------------------------------------------------------------------------------
+constexpr int kAggSplit = 8;
+constexpr int kAggSmem = 128 * 64 * 4;
 
 __global__ void __launch_bounds__(256) vlad_aggregate_kernel(const __half* __restrict__ x, const float* __restrict__ a,
                                                             int P, int D, float* __restrict__ Vp /*[frames][split][16][D]*/,
                                                             float* __restrict__ Ap /*[frames][split][16]*/) {
-  const int f = blockIdx.y, d0 = blockIdx.x * 64, sp = blockIdx.z;
-  const int k = threadIdx.x >> 4, dq = threadIdx.x & 15;
+  extern __shared__ float red[];  // [128 accumulators][64 channel groups]
+  const int f = blockIdx.y, sp = blockIdx.x;
+  const int dq = threadIdx.x & 63, pl = threadIdx.x >> 6;
+  const int d0 = dq * 8;
+  const bool active = d0 < D;
   const int p_begin = (int)((long long)P * sp / kAggSplit), p_end = (int)((long long)P * (sp + 1) / kAggSplit);
-  const __half* xf = x + (size_t)f * P * D + d0 + dq * 4;
-  const float* af = a + (size_t)f * P * kK + k;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, asum = 0.f;
-#pragma unroll 4
-  for (int p = p_begin; p < p_end; ++p) {
-    const float av = af[(size_t)p * kK];
-    const uint2 raw = *reinterpret_cast<const uint2*>(xf + (size_t)p * D);
-    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-    acc0 = fmaf(av, f0.x, acc0);
-    acc1 = fmaf(av, f0.y, acc1);
-    acc2 = fmaf(av, f1.x, acc2);
-    acc3 = fmaf(av, f1.y, acc3);
-    asum += av;
+  const __half* xf = x + (size_t)f * P * D + d0;
+  const float* af = a + (size_t)f * P * kK;
+  unsigned long long acc[kK][4];
+#pragma unroll
+  for (int k = 0; k < kK; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[k][j] = 0ull;
+  if (active) {
+#pragma unroll 2
+    for (int p = p_begin + pl; p < p_end; p += 4) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xf + (size_t)p * D));
+      const float4* ap = reinterpret_cast<const float4*>(af + (size_t)p * kK);
+      float av[kK];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = __ldg(ap + q);
+        av[4 * q] = t.x, av[4 * q + 1] = t.y, av[4 * q + 2] = t.z, av[4 * q + 3] = t.w;
+      }
+      const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+      unsigned long long v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fv = __half22float2(hv[j]);
+        v[j] = pack_f32x2(fv.x, fv.y);
+      }
+#pragma unroll
+      for (int k = 0; k < kK; ++k) {
+        const unsigned long long ak = pack_f32x2(av[k], av[k]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[k][j] = ffma2(ak, v[j], acc[k][j]);
+      }
+    }
   }
-  const int d = d0 + dq * 4;
-  float* vo = Vp + (((size_t)f * kAggSplit + sp) * kK + k) * D + d;
-  vo[0] = acc0, vo[1] = acc1, vo[2] = acc2, vo[3] = acc3;
-  if (blockIdx.x == 0 && dq == 0) Ap[((size_t)f * kAggSplit + sp) * kK + k] = asum;
+  float r[kK * 8];
+#pragma unroll
+  for (int k = 0; k < kK; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) asm("mov.b64 {%0, %1}, %2;" : "=f"(r[k * 8 + 2 * j]), "=f"(r[k * 8 + 2 * j + 1]) : "l"(acc[k][j]));
+  for (int lane_r = 1; lane_r < 4; ++lane_r) {  // fixed-order sum of the pixel lanes
+    if (pl == lane_r) {
+#pragma unroll
+      for (int i = 0; i < kK * 8; ++i) red[i * 64 + dq] = r[i];
+    }
+    __syncthreads();
+    if (pl == 0) {
+#pragma unroll
+      for (int i = 0; i < kK * 8; ++i) r[i] += red[i * 64 + dq];
+    }
+    __syncthreads();
+  }
+  if (pl == 0 && active) {
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+      float* vo = Vp + (((size_t)f * kAggSplit + sp) * kK + k) * D + d0;
+      *reinterpret_cast<float4*>(vo) = make_float4(r[k * 8], r[k * 8 + 1], r[k * 8 + 2], r[k * 8 + 3]);
+      *reinterpret_cast<float4*>(vo + 4) = make_float4(r[k * 8 + 4], r[k * 8 + 5], r[k * 8 + 6], r[k * 8 + 7]);
+    }
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kK) {  // sum_p a[p][k] of this slice (warp 2: off the critical path of lane 0)
+    const int k = threadIdx.x - 64;
+    float asum = 0.f;
+    for (int p = p_begin; p < p_end; ++p) asum += af[(size_t)p * kK + k];
+    Ap[((size_t)f * kAggSplit + sp) * kK + k] = asum;
+  }
 }
 
 // CTA per frame: sum the pixel-split partials, add the centre term, intra-normalise each cluster over D, flatten
@@ -1524,7 +1578,8 @@ int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cud
     CB_LAUNCH_CHECK();
   }
   float* Ap = d->Vraw + (size_t)d->max_batch * kAggSplit * kK * d->D;  // [frames][split][16] after the partial V block
-  vlad_aggregate_kernel<<<dim3(d->D / 64, n, kAggSplit), 256, 0, st>>>(d->act[cur], d->assign, P, d->D, d->Vraw, Ap);
+  CB_CUDA(cudaFuncSetAttribute(vlad_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAggSmem));
+  vlad_aggregate_kernel<<<dim3(kAggSplit, n), 256, kAggSmem, st>>>(d->act[cur], d->assign, P, d->D, d->Vraw, Ap);
   CB_LAUNCH_CHECK();
   vlad_norm_kernel<<<n, 512, 0, st>>>(d->Vraw, Ap, d->vlad_c, d->D, out_dev);
   CB_LAUNCH_CHECK();
