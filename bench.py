@@ -303,6 +303,7 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s"
     alg_bytes = float(n_mine) * DIM * 4
+    sweep_kernel = "scores_tc_kernel" if os.environ.get("CB_TC_V1") == "1" else "scores_tc2_kernel"
     achieved = alg_bytes / (sweep_ms / max(n_sw, 1) * 1e-3) / 1e9 if n_sw else None
 
     # ---- end to end through the host C-ABI calls (pinned host buffers in, host results out)
@@ -377,10 +378,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": launches,
             "stages_ms": {"descriptor": st_desc, "search": st_search, "pnp": st_pnp},
-            "roofline": {"kernel": "scores_tc_kernel (tcgen05 search sweep, 64 queries per pass, %d launch(es) per step)" % sweeps, "bound": "hbm",
+            "roofline": {"kernel": "%s (tcgen05 search sweep, 64 queries per pass, %d launch(es) per step)" % (sweep_kernel, sweeps), "bound": "hbm",
                          "achieved": achieved,
                          "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
-                         "traffic": _traffic_from_profile(world), "peak_source": peak_src,
+                         "traffic": _traffic_from_profile(world, sweep_kernel), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": sweep_ms / max(n_sw, 1)},
             "roofline_streaming": {"kernel": "scores_kernel<4,8> (3-query sweep: the reference's v, vm, vmm batch)", "bound": "hbm",
                                    "achieved": alg_bytes / (sweep3_ms / max(n_sw3, 1) * 1e-3) / 1e9 if n_sw3 else None,
@@ -394,16 +395,22 @@ def main():
         dist.destroy_process_group()
 
 
-def _traffic_from_profile(world):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep kernel, from the committed ncu --set full
-    capture of this same workload (profiles/r1_traffic.json); only valid for the single-GPU 100k x 8192 DB."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if world != 1 or not os.path.exists(path):
+def _traffic_from_profile(world, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep kernel, from the newest committed
+    ncu --set full capture of this same workload (profiles/*_traffic.json, written by tools/summarize_ncu.py);
+    only valid for the single-GPU 100k x 8192 DB."""
+    import glob
+
+    if world != 1:
         return None
-    try:
-        return json.load(open(path)).get("scores_tc_kernel_dram_bytes_per_launch")
-    except Exception:
-        return None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            v = json.load(open(path)).get(kernel + "_dram_bytes_per_launch")
+        except Exception:
+            v = None
+        if v:
+            return v
+    return None
 
 
 def _sweep_timing(index, q, nq=16):

@@ -846,6 +846,202 @@ scores_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core sweep, second layout ("tiled planes").  Same arithmetic as scores_tc_kernel (three fp16 MMAs per K step
+// into one fp32 TMEM accumulator), but the private fp16 copy of the database is stored in the order the sweep consumes
+// it, so that every pipeline stage is ONE contiguous 32 KB block of HBM:
+//     hl[tile][kb][plane*2 + rb][128 rows][32 elements]     tile = 256 database rows, kb = 32-element K block,
+//                                                            plane = hi / lo, rb = which 128-row half
+// and the queries as  qhl[kb][plane][64 queries][32 elements].  K blocks of 32 halves (64-byte swizzle) make a stage
+// 40 KB (32 KB database + 8 KB queries), so FIVE stages fit: four stages (128 KB of database) are in flight per SM
+// while one is multiplied -- the first layout had two 80 KB stages, i.e. at most one in flight.
+// Work units are (tile, K split): the host picks the number of K splits (1..8) that fills the last wave of the
+// persistent grid (100k rows = 391 tiles over 148 SMs is 2.64 waves; 3 splits make it 7.93); split s writes its
+// partial scores to slice s of `partial`, which topk_chunk_kernel already sums (the SIMT sweeps slice d the same way).
+// ---------------------------------------------------------------------------------------------
+constexpr int kT2KB = 32;                            // elements per K block
+constexpr int kT2Stages = 5;
+constexpr int kT2ASub = 128 * kT2KB * 2;             // one 128-row sub-tile of one plane (8 KB)
+constexpr int kT2ABytes = 4 * kT2ASub;               // hi rb0 | hi rb1 | lo rb0 | lo rb1
+constexpr int kT2BSub = kTcQ * kT2KB * 2;            // one query plane (4 KB)
+constexpr int kT2StageBytes = kT2ABytes + 2 * kT2BSub;
+constexpr int kT2Smem = kT2Stages * kT2StageBytes + 1024 + 256;
+constexpr int kT2MaxSplits = 8;
+
+// rows [row0, row0 + n_rows) of the fp32 database -> tiled hi/lo planes
+__global__ void split_tiled_kernel(const float* __restrict__ rows, long long row0, long long n_rows, int d, __half* __restrict__ hl) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n_rows * d) return;
+  const long long r = row0 + i / d;
+  const int e = (int)(i % d);
+  const float4 v = *reinterpret_cast<const float4*>(rows + r * d + e);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __half h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2half_rn(f[j]);
+    l[j] = __float2half_rn(f[j] - __half2float(h[j]));
+  }
+  const int nkb = d / kT2KB;
+  const long long tile = r >> 8;
+  const int rb = (int)(r >> 7) & 1, rr = (int)(r & 127), kb = e / kT2KB, ee = e % kT2KB;
+  const size_t base = ((((size_t)tile * nkb + kb) * 4 + rb) * 128 + rr) * kT2KB + ee;
+  *reinterpret_cast<uint2*>(hl + base) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(hl + base + 2 * 128 * kT2KB) = *reinterpret_cast<uint2*>(l);
+}
+
+// nq query rows -> qhl[kb][plane][kTcQ][kT2KB], rows >= nq zero
+__global__ void split_queries_tiled_kernel(const float* __restrict__ xq, int nq, int d, __half* __restrict__ qhl) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)kTcQ * d) return;
+  const int q = (int)(i / d), e = (int)(i % d);
+  const float f = q < nq ? xq[i] : 0.f;
+  const __half h = __float2half_rn(f);
+  const int kb = e / kT2KB, ee = e % kT2KB;
+  const size_t base = (((size_t)kb * 2) * kTcQ + q) * kT2KB + ee;
+  qhl[base] = h;
+  qhl[base + kTcQ * kT2KB] = __float2half_rn(f - __half2float(h));
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+scores_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, long long n_rows, int nkb,
+                  int nq_valid, float* __restrict__ partial, long long pstride, long long slice_stride, int n_tiles,
+                  int n_splits) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kT2Stages * kT2StageBytes);
+  uint64_t* empty = full + kT2Stages;
+  uint64_t* tmem_full_bar = empty + kT2Stages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = n_tiles * n_splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kT2Stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc(tmem_ptr, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int tile = u / n_splits, sp = u - tile * n_splits;
+        const int kb0 = (int)((long long)sp * nkb / n_splits), kb1 = (int)((long long)(sp + 1) * nkb / n_splits);
+        for (int kb = kb0; kb < kb1; ++kb, ++g) {
+          const int s = g % kT2Stages;
+          mbar_wait(&empty[s], ((g / kT2Stages) & 1) ^ 1);
+          mbar_expect_tx(&full[s], kT2StageBytes);
+          uint8_t* st = smem + s * kT2StageBytes;
+          const int arow = (tile * nkb + kb) * 512;  // < 2^31: checked on the host
+          tma_load_2d(&tmA, &full[s], st, 0, arow);
+          tma_load_2d(&tmA, &full[s], st + 2 * kT2ASub, 0, arow + 256);
+          tma_load_2d(&tmB, &full[s], st + kT2ABytes, 0, kb * 2 * kTcQ);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(kTcQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t g = 0, ti = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
+        const int tile = u / n_splits, sp = u - tile * n_splits;
+        const int kb0 = (int)((long long)sp * nkb / n_splits), kb1 = (int)((long long)(sp + 1) * nkb / n_splits);
+        const int acc = ti & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = kb0; kb < kb1; ++kb, ++g) {
+          const int s = g % kT2Stages;
+          mbar_wait(&full[s], (g / kT2Stages) & 1);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * kT2StageBytes);
+          const uint32_t b_hi = st + kT2ABytes, b_lo = b_hi + kT2BSub;
+#pragma unroll
+          for (int k = 0; k < kT2KB / 16; ++k) {
+            const uint64_t bh = make_kmajor_desc<64>(b_hi + k * 32), bl = make_kmajor_desc<64>(b_lo + k * 32);
+#pragma unroll
+            for (int rb = 0; rb < 2; ++rb) {
+              const uint32_t dt = tmem_base + acc * 128 + rb * kTcQ;
+              const uint64_t ah = make_kmajor_desc<64>(st + rb * kT2ASub + k * 32);
+              const uint64_t al = make_kmajor_desc<64>(st + (2 + rb) * kT2ASub + k * 32);
+              umma_f16(dt, ah, bh, idesc, (kb > kb0 || k) ? 1u : 0u);
+              umma_f16(dt, ah, bl, idesc, 1u);
+              umma_f16(dt, al, bh, idesc, 1u);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t ti = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
+      const int tile = u / n_splits, sp = u - tile * n_splits;
+      float* __restrict__ pout = partial + (size_t)sp * slice_stride;
+      const int acc = ti & 1;
+      mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int rb = 0; rb < 2; ++rb) {
+        const long long row = (long long)tile * kTcRows + rb * 128 + q * 32 + lane;
+        const bool row_ok = row < n_rows;
+#pragma unroll 1
+        for (int c = 0; c < kTcQ; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + acc * 128 + rb * kTcQ + c + ((uint32_t)(q * 32) << 16), v);
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c + j < nq_valid) pout[(size_t)(c + j) * pstride + row] = __uint_as_float(v[j]);  // warp-uniform test
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// number of K splits that best fills the last wave of a persistent grid of `sms` CTAs (fewest splits among near-ties)
+int pick_splits(int n_tiles, int nkb, int sms) {
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= kT2MaxSplits && s <= nkb; ++s) {
+    const long long units = (long long)n_tiles * s;
+    const long long waves = (units + sms - 1) / sms;
+    const double eff = (double)units / (double)(waves * sms);
+    if (eff > best_eff + 0.03) {
+      best_eff = eff;
+      best = s;
+    }
+  }
+  return best;
+}
+
 template <int QT, int R>
 cudaError_t launch_scores(int grid, size_t smem, cudaStream_t st, const float* rows, long long n_rows,
                           int d, int ds, int n_slices, const float* xq, int nq_valid, float* partial,
@@ -893,6 +1089,11 @@ struct cb_index {
   __half* q_hi = nullptr;  // [64][d] query planes
   __half* q_lo = nullptr;
   CUtensorMap tmAhi, tmAlo, tmBhi, tmBlo;
+  // tiled planes (scores_tc2_kernel, the default): one buffer, stage-contiguous; CB_TC_V1=1 keeps the row-major planes
+  bool tc_v1 = false;
+  __half* hl = nullptr;   // [capacity/256][d/32][4][128][32]
+  __half* qhl = nullptr;  // [d/32][2][64][32]
+  CUtensorMap tmA2, tmB2;
   // optional device-side timing of the sweep kernel (bench.py roofline)
   bool timing = false;
   cudaEvent_t ev[2 * 64] = {};
@@ -957,6 +1158,38 @@ SweepPlan plan_sweep(const cb_index* ix, int nq_left) {
 // path) when the planes cannot be allocated -- the SIMT sweeps need no extra memory.
 bool ensure_planes(cb_index* ix, cudaStream_t st) {
   if (ix->no_tc) return false;
+  if (!ix->tc_v1) {
+    if (!ix->hl) {
+      const int nkb = ix->d / kT2KB;
+      const uint64_t tiles = ((uint64_t)ix->capacity + kTcRows - 1) / kTcRows;
+      const uint64_t arows = tiles * nkb * 512;  // 64-byte rows of the tiled buffer; TMA coordinates are 32-bit signed
+      int rc = arows < (1ull << 31) ? CB_OK : CB_ENOMEM;
+      cudaError_t e = cudaSuccess;
+      if (!rc) e = cudaMalloc((void**)&ix->hl, (size_t)arows * kT2KB * sizeof(__half));
+      if (!rc && e == cudaSuccess) e = cudaMalloc((void**)&ix->qhl, (size_t)2 * kTcQ * ix->d * sizeof(__half));
+      if (e != cudaSuccess) rc = CB_ENOMEM;
+      if (!rc) rc = make_map_2d(&ix->tmA2, ix->hl, arows, kT2KB, 256, kT2KB);
+      if (!rc) rc = make_map_2d(&ix->tmB2, ix->qhl, (uint64_t)nkb * 2 * kTcQ, kT2KB, 2 * kTcQ, kT2KB);
+      if (!rc) rc = cudaFuncSetAttribute(scores_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2Smem) == cudaSuccess
+                        ? CB_OK
+                        : CB_ECUDA;
+      if (rc) {
+        cudaGetLastError();
+        cudaFree(ix->hl), cudaFree(ix->qhl);
+        ix->hl = ix->qhl = nullptr;
+        ix->no_tc = true;
+        return false;
+      }
+      ix->split_rows = 0;
+    }
+    if (ix->split_rows < ix->nlocal) {
+      const long long n = (long long)(ix->nlocal - ix->split_rows) * ix->d;
+      split_tiled_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(ix->rows, ix->split_rows, ix->nlocal - ix->split_rows,
+                                                                           ix->d, ix->hl);
+      ix->split_rows = ix->nlocal;
+    }
+    return true;
+  }
   if (!ix->hi) {
     const size_t plane = (size_t)ix->capacity * ix->d * sizeof(__half);
     const size_t qplane = (size_t)kTcQ * ix->d * sizeof(__half);
@@ -1011,9 +1244,10 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
     SweepPlan p = plan_sweep(ix, gq);  // one plan (tile size, d-slicing) for the whole group
     // more than a few queries: the fp32 SIMT sweep would be FMA-bound; the tensor-core sweep stays HBM-bound
     const bool use_tc = gq > 4 && ix->d % kTcKB == 0 && ensure_planes(ix, st);
+    const int n_tc_tiles = (int)((n_rows + kTcRows - 1) / kTcRows);
     if (use_tc) {
       p.qt = kTcQ;
-      p.n_slices = 1;
+      p.n_slices = ix->tc_v1 ? 1 : pick_splits(n_tc_tiles, ix->d / kT2KB, ix->sm_count);  // K splits land in slices
       p.ds = ix->d;
     }
     const int n_tiles = (gq + p.qt - 1) / p.qt;
@@ -1035,13 +1269,20 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
       cudaError_t e = cudaSuccess;
       if (use_tc) {
         const long long qelems = (long long)kTcQ * ix->d;
-        split_queries_kernel<<<(unsigned)((qelems + 255) / 256), 256, 0, st>>>(xq, nq_valid, ix->d, ix->q_hi, ix->q_lo);
-        const int n_tc_tiles = (int)((n_rows + kTcRows - 1) / kTcRows);
-        const int grid = n_tc_tiles < ix->sm_count ? n_tc_tiles : ix->sm_count;
+        if (ix->tc_v1)
+          split_queries_kernel<<<(unsigned)((qelems + 255) / 256), 256, 0, st>>>(xq, nq_valid, ix->d, ix->q_hi, ix->q_lo);
+        else
+          split_queries_tiled_kernel<<<(unsigned)((qelems + 255) / 256), 256, 0, st>>>(xq, nq_valid, ix->d, ix->qhl);
+        const int n_units = ix->tc_v1 ? n_tc_tiles : n_tc_tiles * p.n_slices;
+        const int grid = n_units < ix->sm_count ? n_units : ix->sm_count;
         const bool rec_tc = ix->timing && ix->ev_used < 64;
         if (rec_tc) cudaEventRecord(ix->ev[2 * ix->ev_used], st);
-        scores_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(ix->tmAhi, ix->tmAlo, ix->tmBhi, ix->tmBlo, n_rows, ix->d, nq_valid, ptile,
-                                                            pstride, n_tc_tiles);
+        if (ix->tc_v1)
+          scores_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(ix->tmAhi, ix->tmAlo, ix->tmBhi, ix->tmBlo, n_rows, ix->d, nq_valid,
+                                                              ptile, pstride, n_tc_tiles);
+        else
+          scores_tc2_kernel<<<grid, kTcThreads, kT2Smem, st>>>(ix->tmA2, ix->tmB2, n_rows, ix->d / kT2KB, nq_valid, ptile, pstride,
+                                                               slice_stride, n_tc_tiles, p.n_slices);
         if (rec_tc) {
           cudaEventRecord(ix->ev[2 * ix->ev_used + 1], st);
           ++ix->ev_used;
@@ -1128,6 +1369,8 @@ int cb_index_create(cb_index** out, int d, int64_t capacity, int device, int ran
     ix->no_ffma2 = env2 && env2[0] == '1';
     const char* env3 = getenv("CB_NO_TC");
     ix->no_tc = env3 && env3[0] == '1';
+    const char* env4 = getenv("CB_TC_V1");
+    ix->tc_v1 = env4 && env4[0] == '1';
   }
   cudaError_t e = cudaMalloc(&ix->rows, (size_t)capacity * d * sizeof(float));
   if (e != cudaSuccess) {
@@ -1160,6 +1403,8 @@ int cb_index_destroy(cb_index* ix) {
   cudaFree(ix->lo);
   cudaFree(ix->q_hi);
   cudaFree(ix->q_lo);
+  cudaFree(ix->hl);
+  cudaFree(ix->qhl);
   for (cudaEvent_t ev : ix->ev)
     if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ix->stream);

@@ -176,3 +176,39 @@ def test_full_size_properties(native_lib, cuda_device):
     torch.cuda.synchronize()
     assert torch.equal(L8, L1)
     assert torch.equal(S8, S1)  # fp64 re-scoring is shard-independent, bit for bit
+
+
+@pytest.mark.parametrize("n,d,nq", [(1500, 1024, 64), (300, 8192, 9), (5000, 4096, 40)])
+def test_sweep_variants_agree(native_lib, cuda_device, monkeypatch, n, d, nq):
+    """The tensor-core sweep on tiled planes (default), on row-major planes (CB_TC_V1=1) and the fp32 CUDA-core sweep
+    (CB_NO_TC=1) must return the same labels and fp64 scores as the oracle -- with rows trickling in between searches
+    (planes extended incrementally), ragged tile tails and a row limit."""
+    from cerebro_b200.index import IndexFlatIP
+
+    db = synth.unit_rows(n, d, seed=11)
+    rng = np.random.default_rng(3)
+    half = n // 2 + 7
+    t1 = rng.integers(0, half, nq)
+    t2 = rng.integers(0, n, nq)
+    q1 = synth.planted_queries(db, t1, seed=4)
+    q2 = synth.planted_queries(db, t2, seed=5)
+    o = _oracle_index(db)
+    o_half = _oracle_index(db[:half])
+    for env in ({}, {"CB_TC_V1": "1"}, {"CB_NO_TC": "1"}):
+        for key in ("CB_TC_V1", "CB_NO_TC"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        ix = IndexFlatIP(d, capacity=n + 3)
+        ix.add(db[:half])
+        D, I, S = ix.search(q1, 5, return_f64=True)
+        assert np.array_equal(I, o_half.search(q1, 5)[1]), env
+        ix.add(db[half:])
+        D, I, S = ix.search(q2, 5, return_f64=True)
+        assert np.array_equal(I, o.search(q2, 5)[1]), env
+        ref = q2.astype(np.float64) @ db.astype(np.float64).T
+        assert np.allclose(S, np.take_along_axis(ref, I, 1), rtol=0, atol=1e-12), env
+        lim = n - 129
+        D, I = ix.search(q2, 5, limit_rows=lim)
+        assert np.array_equal(I, o.search(q2, 5, limit_rows=lim)[1]), env
+        ix.close()
