@@ -38,6 +38,37 @@ class NetvladWeights(C.Structure):
     ]
 
 
+class IrBlock(C.Structure):  # cb_ir_block
+    _fields_ = [
+        ("c_in", C.c_int),
+        ("c_exp", C.c_int),
+        ("c_out", C.c_int),
+        ("stride", C.c_int),
+        ("residual", C.c_int),
+        ("expand_w", C.POINTER(C.c_float)),
+        ("expand_b", C.POINTER(C.c_float)),
+        ("dw_w", C.POINTER(C.c_float)),
+        ("dw_b", C.POINTER(C.c_float)),
+        ("project_w", C.POINTER(C.c_float)),
+        ("project_b", C.POINTER(C.c_float)),
+    ]
+
+
+class NetvladV2Weights(C.Structure):  # cb_netvlad_v2_weights
+    _fields_ = [
+        ("in_channels", C.c_int),
+        ("conv1_w", C.POINTER(C.c_float)),
+        ("conv1_b", C.POINTER(C.c_float)),
+        ("n_blocks", C.c_int),
+        ("blocks", C.POINTER(IrBlock)),
+        ("vlad_k", C.c_int),
+        ("vlad_d", C.c_int),
+        ("vlad_w", C.POINTER(C.c_float)),
+        ("vlad_b", C.POINTER(C.c_float)),
+        ("vlad_c", C.POINTER(C.c_float)),
+    ]
+
+
 class RansacParams(C.Structure):
     _fields_ = [
         ("error_thresh", C.c_double),
@@ -79,6 +110,7 @@ _SIGNATURES = {
     "cb_index_get_rows": (C.c_int, [_vp, _i64, _i64, _vp]),
     "cb_index_device_rows": (_vp, [_vp]),
     "cb_descriptor_create": (C.c_int, [C.POINTER(_vp), C.POINTER(NetvladWeights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cb_descriptor_create_v2": (C.c_int, [C.POINTER(_vp), C.POINTER(NetvladV2Weights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "cb_descriptor_destroy": (C.c_int, [_vp]),
     "cb_descriptor_dim": (C.c_int, [_vp]),
     "cb_descriptor_compute": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp]),

@@ -210,7 +210,9 @@ template <int N_TILE, int KB>
 __global__ void __launch_bounds__(kGemmThreads) pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const float* __restrict__ bias, __half* __restrict__ out,
-                                                              int M_total, int N_total, int K) {
+                                                              int M_total, int N_total, int K,
+                                                              const __half* __restrict__ residual, int relu) {
+  // residual != NULL: out = acc + bias + residual (MobileNetV2's Add); relu == 0: linear bottleneck (no ReLU6)
   using SM = GemmSmem<N_TILE, KB>;
   constexpr int SWZ = KB * 2;  // bytes per tile row = swizzle span (128 or 64)
   extern __shared__ uint8_t smem_raw[];
@@ -290,11 +292,26 @@ __global__ void __launch_bounds__(kGemmThreads) pw_gemm_kernel(const __grid_cons
         for (int j = 0; j < 32; j += 8) {
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + j));
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + j + 4));
+          float f[8] = {__uint_as_float(v[j + 0]) + b0.x, __uint_as_float(v[j + 1]) + b0.y, __uint_as_float(v[j + 2]) + b0.z,
+                        __uint_as_float(v[j + 3]) + b0.w, __uint_as_float(v[j + 4]) + b1.x, __uint_as_float(v[j + 5]) + b1.y,
+                        __uint_as_float(v[j + 6]) + b1.z, __uint_as_float(v[j + 7]) + b1.w};
+          if (residual) {  // kernel-uniform
+            const uint4 rr = *reinterpret_cast<const uint4*>(residual + (size_t)row * N_total + n0 + c + j);
+            const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 t = __half22float2(rh[i]);
+              f[2 * i] += t.x;
+              f[2 * i + 1] += t.y;
+            }
+          }
+          if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = relu6(f[i]);
+          }
           __half2 h[4];
-          h[0] = __floats2half2_rn(relu6(__uint_as_float(v[j + 0]) + b0.x), relu6(__uint_as_float(v[j + 1]) + b0.y));
-          h[1] = __floats2half2_rn(relu6(__uint_as_float(v[j + 2]) + b0.z), relu6(__uint_as_float(v[j + 3]) + b0.w));
-          h[2] = __floats2half2_rn(relu6(__uint_as_float(v[j + 4]) + b1.x), relu6(__uint_as_float(v[j + 5]) + b1.y));
-          h[3] = __floats2half2_rn(relu6(__uint_as_float(v[j + 6]) + b1.z), relu6(__uint_as_float(v[j + 7]) + b1.w));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
           *reinterpret_cast<uint4*>(orow + c + j) = *reinterpret_cast<uint4*>(h);
         }
       }
@@ -1031,7 +1048,8 @@ __global__ void __launch_bounds__(kConvThreads) conv1_tc_kernel(const uint8_t* _
 // CUDA-core version of the same contraction: thread = (pixel, 8 output channels)
 __global__ void __launch_bounds__(256) pw_simt_kernel(const __half* __restrict__ in, const __half* __restrict__ w /*[N][K]*/,
                                                      const float* __restrict__ bias, __half* __restrict__ out,
-                                                     long long M_total, int N, int K) {
+                                                     long long M_total, int N, int K,
+                                                     const __half* __restrict__ residual, int relu) {
   const int ngs = N >> 3;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= M_total * ngs) return;
@@ -1063,9 +1081,23 @@ __global__ void __launch_bounds__(256) pw_simt_kernel(const __half* __restrict__
       }
     }
   }
+  if (residual) {
+    const uint4 rr = *reinterpret_cast<const uint4*>(residual + (size_t)m * N + ng * 8);
+    const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __half22float2(rh[i]);
+      acc[2 * i] += t.x;
+      acc[2 * i + 1] += t.y;
+    }
+  }
+  if (relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = relu6(acc[j]);
+  }
   __half2 h[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(relu6(acc[2 * j]), relu6(acc[2 * j + 1]));
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
   *reinterpret_cast<uint4*>(out + (size_t)m * N + ng * 8) = *reinterpret_cast<uint4*>(h);
 }
 
@@ -1375,6 +1407,26 @@ struct Block {
   CUtensorMap tmBh;    // weight map with the halo kernel's K block
 };
 
+// One 1x1 convolution of the MobileNetV2 path (channel counts padded to multiples of 64 with zero weights / biases, so
+// every layer runs on the tcgen05 GEMM; padded channels stay exactly zero through ReLU6, the linear bottlenecks and Add).
+struct PwLayer {
+  int C = 0, Cout = 0;  // padded
+  __half* w = nullptr;  // [Cout][C] fp16, K-major B operand
+  float* b = nullptr;   // [Cout]
+  int n_tile = 0, kb = 0;
+  bool use_tc = false;
+  CUtensorMap tmA[3], tmB;  // A map per activation buffer
+};
+
+struct IrBlock {  // inverted-residual block: [expand 1x1 + ReLU6] -> depthwise 3x3 + ReLU6 -> project 1x1 (linear) [+ input]
+  int Hin = 0, Win = 0, Ho = 0, Wo = 0, stride = 1, residual = 0;
+  int Cin = 0, Cexp = 0, Cout = 0;  // padded
+  bool has_expand = false;
+  PwLayer expand, project;
+  float* dw_w = nullptr;  // [3][3][Cexp]
+  float* dw_b = nullptr;
+};
+
 }  // namespace
 
 struct cb_descriptor {
@@ -1386,15 +1438,17 @@ struct cb_descriptor {
   __half* conv1_hi = nullptr;  // [32][32] K-major, scale 2/255 folded in, hi/lo split (tcgen05 stem)
   __half* conv1_lo = nullptr;
   std::vector<Block> blocks;
+  bool v2 = false;            // MobileNetV2 prefix (cb_descriptor_create_v2): `ir` instead of `blocks`, three buffers
+  std::vector<IrBlock> ir;
   int K = 16, D = 0, Hf = 0, Wf = 0;
   float* vlad_w = nullptr;
   float* vlad_b = nullptr;
   float* vlad_c = nullptr;
   __half* vlad_whi = nullptr;  // [16][D] K-major hi/lo split of the soft-assignment weights (tcgen05 path)
   __half* vlad_wlo = nullptr;
-  CUtensorMap tmX[2], tmWhi, tmWlo;
+  CUtensorMap tmX[3], tmWhi, tmWlo;
   bool vlad_tc = false;
-  __half* act[2] = {nullptr, nullptr};
+  __half* act[3] = {nullptr, nullptr, nullptr};  // ping-pong (+ a third buffer for MobileNetV2's skip connections)
   size_t act_elems = 0;
   float* assign = nullptr;
   float* Vraw = nullptr;
@@ -1425,7 +1479,7 @@ int launch_gemm(const Block& b, long long M, int in_buf, __half* out, cudaStream
   auto kern = pw_gemm_kernel<N_TILE, KB>;
   CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
   dim3 grid((unsigned)((M + 127) / 128), (unsigned)(b.Cout / N_TILE));
-  kern<<<grid, kGemmThreads, SM::kTotal, st>>>(b.tmA[in_buf], b.tmB, b.pw_b, out, (int)M, b.Cout, b.C);
+  kern<<<grid, kGemmThreads, SM::kTotal, st>>>(b.tmA[in_buf], b.tmB, b.pw_b, out, (int)M, b.Cout, b.C, nullptr, 1);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
@@ -1503,13 +1557,12 @@ int run_pw(cb_descriptor* d, const Block& b, long long M, int in_buf, __half* ou
     }
   }
   const long long threads = M * (b.Cout / 8);
-  pw_simt_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(in, b.pw_w, b.pw_b, out, M, b.Cout, b.C);
+  pw_simt_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(in, b.pw_w, b.pw_b, out, M, b.Cout, b.C, nullptr, 1);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
 
-int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cudaStream_t st) {
-  int cur = 0;
+int run_stem(cb_descriptor* d, int n, const uint8_t* img_dev, int cur, cudaStream_t st) {
   if (!d->force_simt && !d->no_fuse) {
     const long long M = (long long)n * d->H1 * d->W1;
     const unsigned grid = (unsigned)((M + 128 * kConvTiles - 1) / (128 * kConvTiles));
@@ -1528,6 +1581,19 @@ int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cud
     else
       conv1_kernel<3><<<grid, 256, 0, st>>>(img_dev, n, d->rows, d->cols, d->H1, d->W1, d->conv1_w, d->conv1_b, d->act[cur]);
     CB_LAUNCH_CHECK();
+  }
+  return CB_OK;
+}
+
+int run_vlad_head(cb_descriptor* d, int n, int cur, float* out_dev, cudaStream_t st);
+int forward_v2(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cudaStream_t st);
+
+int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cudaStream_t st) {
+  if (d->v2) return forward_v2(d, n, img_dev, out_dev, st);
+  int cur = 0;
+  {
+    int rc = run_stem(d, n, img_dev, cur, st);
+    if (rc) return rc;
   }
   int layer = 0;
   d->last_buf = cur;
@@ -1564,6 +1630,10 @@ int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cud
       if (d->stop_layer == ++layer) return CB_OK;
     }
   }
+  return run_vlad_head(d, n, cur, out_dev, st);
+}
+
+int run_vlad_head(cb_descriptor* d, int n, int cur, float* out_dev, cudaStream_t st) {
   const int P = d->Hf * d->Wf;
   const long long Ptot = (long long)n * P;
   if (d->vlad_tc && !d->force_simt && !d->no_fuse) {
@@ -1586,7 +1656,176 @@ int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cud
   return CB_OK;
 }
 
+template <int N_TILE, int KB>
+int launch_gemm_layer(const PwLayer& L, long long M, int in_buf, __half* out, const __half* residual, int relu, cudaStream_t st) {
+  using SM = GemmSmem<N_TILE, KB>;
+  auto kern = pw_gemm_kernel<N_TILE, KB>;
+  CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+  dim3 grid((unsigned)((M + 127) / 128), (unsigned)(L.Cout / N_TILE));
+  kern<<<grid, kGemmThreads, SM::kTotal, st>>>(L.tmA[in_buf], L.tmB, L.b, out, (int)M, L.Cout, L.C, residual, relu);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+int run_pw_layer(cb_descriptor* d, const PwLayer& L, long long M, int in_buf, __half* out, const __half* residual, int relu,
+                 cudaStream_t st) {
+  if (L.use_tc && !d->force_simt) {
+    if (L.kb == 64) {
+      switch (L.n_tile) {
+        case 64: return launch_gemm_layer<64, 64>(L, M, in_buf, out, residual, relu, st);
+        case 128: return launch_gemm_layer<128, 64>(L, M, in_buf, out, residual, relu, st);
+        default: return launch_gemm_layer<256, 64>(L, M, in_buf, out, residual, relu, st);
+      }
+    } else {
+      switch (L.n_tile) {
+        case 64: return launch_gemm_layer<64, 32>(L, M, in_buf, out, residual, relu, st);
+        case 128: return launch_gemm_layer<128, 32>(L, M, in_buf, out, residual, relu, st);
+        default: return launch_gemm_layer<256, 32>(L, M, in_buf, out, residual, relu, st);
+      }
+    }
+  }
+  const long long threads = M * (L.Cout / 8);
+  pw_simt_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d->act[in_buf], L.w, L.b, out, M, L.Cout, L.C, residual, relu);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+// MobileNetV2 prefix: stem, then per block [expand GEMM] -> depthwise -> project GEMM (+ skip), rotating three buffers:
+// the block input stays untouched until the project epilogue has added it.
+int forward_v2(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cudaStream_t st) {
+  int cur = 0;
+  int rc = run_stem(d, n, img_dev, cur, st);
+  if (rc) return rc;
+  int layer = 0;
+  d->last_buf = cur;
+  if (d->stop_layer == layer) return CB_OK;
+  for (const IrBlock& b : d->ir) {
+    int x = cur;
+    if (b.has_expand) {
+      x = (cur + 1) % 3;
+      rc = run_pw_layer(d, b.expand, (long long)n * b.Hin * b.Win, cur, d->act[x], nullptr, 1, st);
+      if (rc) return rc;
+      d->last_buf = x;
+      if (d->stop_layer == ++layer) return CB_OK;
+    }
+    const int dwb = b.has_expand ? (cur + 2) % 3 : (cur + 1) % 3;
+    const long long threads = (long long)n * b.Ho * ((b.Wo + kPX - 1) / kPX) * (b.Cexp / 8);
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    if (b.stride == 1)
+      dw_kernel<1><<<grid, 256, 0, st>>>(d->act[x], n, b.Hin, b.Win, b.Cexp, b.Ho, b.Wo, b.dw_w, b.dw_b, d->act[dwb]);
+    else
+      dw_kernel<2><<<grid, 256, 0, st>>>(d->act[x], n, b.Hin, b.Win, b.Cexp, b.Ho, b.Wo, b.dw_w, b.dw_b, d->act[dwb]);
+    CB_LAUNCH_CHECK();
+    d->last_buf = dwb;
+    if (d->stop_layer == ++layer) return CB_OK;
+    const int ob = b.has_expand ? x : (cur + 2) % 3;  // never the block input (the skip) nor the depthwise output
+    rc = run_pw_layer(d, b.project, (long long)n * b.Ho * b.Wo, dwb, d->act[ob], b.residual ? d->act[cur] : nullptr, 0, st);
+    if (rc) return rc;
+    cur = ob;
+    d->last_buf = cur;
+    if (d->stop_layer == ++layer) return CB_OK;
+  }
+  return run_vlad_head(d, n, cur, out_dev, st);
+}
+
 inline int conv_out_s2(int h) { return (h + 1 - 3) / 2 + 1; }  // ZeroPadding2D((0,1),(0,1)) + 3x3 'valid' stride 2
+inline int pad64(int c) { return (c + 63) / 64 * 64; }
+
+// natural [c][cout] fp32 weights + [cout] bias -> zero-padded fp16 [Cout][C] + fp32 [Cout], tensor maps for the three buffers
+int setup_pw_layer(cb_descriptor* d, PwLayer& L, const float* w, const float* b, int c, int cout, int C, int Cout, uint64_t Mmax) {
+  L.C = C;
+  L.Cout = Cout;
+  std::vector<__half> tmp((size_t)C * Cout, __float2half_rn(0.f));
+  for (int k = 0; k < c; ++k)
+    for (int nn = 0; nn < cout; ++nn) tmp[(size_t)nn * C + k] = __float2half_rn(w[(size_t)k * cout + nn]);
+  std::vector<float> bias((size_t)Cout, 0.f);
+  for (int nn = 0; nn < cout; ++nn) bias[nn] = b[nn];
+  cudaError_t e = cudaMalloc((void**)&L.w, tmp.size() * sizeof(__half));
+  if (e == cudaSuccess) e = cudaMemcpy(L.w, tmp.data(), tmp.size() * sizeof(__half), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return cb::fail(CB_ENOMEM, "pointwise weight upload failed: %s", cudaGetErrorString(e));
+  int rc = upload_f32(&L.b, bias.data(), bias.size());
+  if (rc) return rc;
+  L.kb = (C % 64 == 0) ? 64 : ((C % 32 == 0) ? 32 : 0);
+  L.n_tile = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : ((Cout % 64 == 0) ? 64 : 0));
+  L.use_tc = L.kb != 0 && L.n_tile != 0;
+  if (L.use_tc) {
+    for (int i = 0; i < 3 && !rc; ++i) rc = make_map_2d(&L.tmA[i], d->act[i], Mmax, (uint64_t)C, 128, (uint32_t)L.kb);
+    if (!rc) rc = make_map_2d(&L.tmB, L.w, (uint64_t)Cout, (uint64_t)C, (uint32_t)L.n_tile, (uint32_t)L.kb);
+  }
+  return rc;
+}
+
+// activation buffers (n_bufs of max_elems * max_batch halves), head scratch, host-API staging, streams
+int alloc_common(cb_descriptor* d, size_t max_elems, int n_bufs) {
+  const int max_batch = d->max_batch;
+  d->act_elems = max_elems * (size_t)max_batch;
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < n_bufs && e == cudaSuccess; ++i) e = cudaMalloc((void**)&d->act[i], d->act_elems * sizeof(__half));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d->assign, (size_t)max_batch * d->Hf * d->Wf * kK * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d->Vraw, (size_t)max_batch * kAggSplit * kK * (d->D + 1) * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d->img_dev, (size_t)max_batch * d->rows * d->cols * d->chnls);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d->out_dev, (size_t)max_batch * kK * d->D * sizeof(float));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) return cb::fail(CB_ENOMEM, "descriptor allocation failed: %s", cudaGetErrorString(e));
+  return CB_OK;
+}
+
+// stem weights (fp32 for the CUDA-core kernel, hi/lo fp16 with the 2/255 scale folded in for the tcgen05 one) and the
+// NetVLAD head (fp32 + hi/lo fp16 K-major soft-assignment weights, one feature-map tensor map per activation buffer)
+int setup_stem_and_head(cb_descriptor* d, const float* conv1_w, const float* conv1_b, const float* vlad_w, const float* vlad_b,
+                        const float* vlad_c) {
+  const int chnls = d->chnls, max_batch = d->max_batch;
+  int rc = upload_f32(&d->conv1_w, conv1_w, (size_t)9 * chnls * 32);
+  if (!rc) {
+    std::vector<__half> hi(32 * 32, __float2half_rn(0.f)), lo(32 * 32, __float2half_rn(0.f));
+    for (int k = 0; k < 9 * chnls; ++k)
+      for (int nn = 0; nn < 32; ++nn) {
+        const float v = conv1_w[(size_t)k * 32 + nn] * (2.0f / 255.0f);  // server.py:629 folded into the weights
+        const __half h = __float2half_rn(v);
+        hi[nn * 32 + k] = h;
+        lo[nn * 32 + k] = __float2half_rn(v - __half2float(h));
+      }
+    cudaError_t e2 = cudaMalloc((void**)&d->conv1_hi, hi.size() * sizeof(__half));
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&d->conv1_lo, lo.size() * sizeof(__half));
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(d->conv1_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(d->conv1_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e2 != cudaSuccess) rc = cb::fail(CB_ENOMEM, "stem weight upload failed: %s", cudaGetErrorString(e2));
+  }
+  if (!rc) rc = upload_f32(&d->conv1_b, conv1_b, 32);
+  if (!rc) rc = upload_f32(&d->vlad_w, vlad_w, (size_t)d->D * kK);
+  if (!rc) rc = upload_f32(&d->vlad_b, vlad_b, kK);
+  if (!rc) rc = upload_f32(&d->vlad_c, vlad_c, (size_t)d->D * kK);
+  if (!rc && d->D % 64 == 0) {
+    std::vector<__half> hi((size_t)kK * d->D), lo((size_t)kK * d->D);
+    for (int dd = 0; dd < d->D; ++dd)
+      for (int k = 0; k < kK; ++k) {
+        const float v = vlad_w[(size_t)dd * kK + k];
+        const __half h = __float2half_rn(v);
+        hi[(size_t)k * d->D + dd] = h;
+        lo[(size_t)k * d->D + dd] = __float2half_rn(v - __half2float(h));
+      }
+    cudaError_t e3 = cudaMalloc((void**)&d->vlad_whi, hi.size() * sizeof(__half));
+    if (e3 == cudaSuccess) e3 = cudaMalloc((void**)&d->vlad_wlo, lo.size() * sizeof(__half));
+    if (e3 == cudaSuccess) e3 = cudaMemcpy(d->vlad_whi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e3 == cudaSuccess) e3 = cudaMemcpy(d->vlad_wlo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e3 != cudaSuccess) rc = cb::fail(CB_ENOMEM, "VLAD weight upload failed: %s", cudaGetErrorString(e3));
+    const uint64_t Pmax = (uint64_t)max_batch * d->Hf * d->Wf;
+    for (int i = 0; i < 3 && !rc; ++i)
+      if (d->act[i]) rc = make_map_2d(&d->tmX[i], d->act[i], Pmax, (uint64_t)d->D, 128, 64);
+    if (!rc) rc = make_map_2d(&d->tmWhi, d->vlad_whi, (uint64_t)kK, (uint64_t)d->D, kK, 64);
+    if (!rc) rc = make_map_2d(&d->tmWlo, d->vlad_wlo, (uint64_t)kK, (uint64_t)d->D, kK, 64);
+    d->vlad_tc = !rc;
+  }
+  return rc;
+}
+
+int upload_f32_padded(float** dst, const float* src, size_t rows, size_t c, size_t C) {  // [rows][c] -> [rows][C], zero fill
+  std::vector<float> tmp(rows * C, 0.f);
+  for (size_t r = 0; r < rows; ++r)
+    for (size_t k = 0; k < c; ++k) tmp[r * C + k] = src[r * c + k];
+  return upload_f32(dst, tmp.data(), tmp.size());
+}
 
 }  // namespace
 
@@ -1660,60 +1899,9 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
     cb_descriptor_destroy(d);
     return cb::fail(CB_EINVAL, "NetVLAD input dim %d does not match backbone output %d (or not a multiple of 64)", w->vlad_d, c);
   }
-  d->act_elems = max_elems * (size_t)max_batch;
+  rc = alloc_common(d, max_elems, 2);
+  if (!rc) rc = setup_stem_and_head(d, w->conv1_w, w->conv1_b, w->vlad_w, w->vlad_b, w->vlad_c);
   cudaError_t e = cudaSuccess;
-  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc((void**)&d->act[i], d->act_elems * sizeof(__half));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d->assign, (size_t)max_batch * d->Hf * d->Wf * kK * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d->Vraw, (size_t)max_batch * kAggSplit * kK * (d->D + 1) * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d->img_dev, (size_t)max_batch * rows * cols * chnls);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d->out_dev, (size_t)max_batch * kK * d->D * sizeof(float));
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking);
-  if (e != cudaSuccess) {
-    cb_descriptor_destroy(d);
-    return cb::fail(CB_ENOMEM, "descriptor allocation failed: %s", cudaGetErrorString(e));
-  }
-  rc = upload_f32(&d->conv1_w, w->conv1_w, (size_t)9 * chnls * 32);
-  if (!rc) {
-    std::vector<__half> hi(32 * 32, __float2half_rn(0.f)), lo(32 * 32, __float2half_rn(0.f));
-    for (int k = 0; k < 9 * chnls; ++k)
-      for (int nn = 0; nn < 32; ++nn) {
-        const float v = w->conv1_w[(size_t)k * 32 + nn] * (2.0f / 255.0f);  // server.py:629 folded into the weights
-        const __half h = __float2half_rn(v);
-        hi[nn * 32 + k] = h;
-        lo[nn * 32 + k] = __float2half_rn(v - __half2float(h));
-      }
-    cudaError_t e2 = cudaMalloc((void**)&d->conv1_hi, hi.size() * sizeof(__half));
-    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&d->conv1_lo, lo.size() * sizeof(__half));
-    if (e2 == cudaSuccess) e2 = cudaMemcpy(d->conv1_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice);
-    if (e2 == cudaSuccess) e2 = cudaMemcpy(d->conv1_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice);
-    if (e2 != cudaSuccess) rc = cb::fail(CB_ENOMEM, "stem weight upload failed: %s", cudaGetErrorString(e2));
-  }
-  if (!rc) rc = upload_f32(&d->conv1_b, w->conv1_b, 32);
-  if (!rc) rc = upload_f32(&d->vlad_w, w->vlad_w, (size_t)d->D * kK);
-  if (!rc) rc = upload_f32(&d->vlad_b, w->vlad_b, kK);
-  if (!rc) rc = upload_f32(&d->vlad_c, w->vlad_c, (size_t)d->D * kK);
-  if (!rc && d->D % 64 == 0) {
-    std::vector<__half> hi((size_t)kK * d->D), lo((size_t)kK * d->D);
-    for (int dd = 0; dd < d->D; ++dd)
-      for (int k = 0; k < kK; ++k) {
-        const float v = w->vlad_w[(size_t)dd * kK + k];
-        const __half h = __float2half_rn(v);
-        hi[(size_t)k * d->D + dd] = h;
-        lo[(size_t)k * d->D + dd] = __float2half_rn(v - __half2float(h));
-      }
-    cudaError_t e3 = cudaMalloc((void**)&d->vlad_whi, hi.size() * sizeof(__half));
-    if (e3 == cudaSuccess) e3 = cudaMalloc((void**)&d->vlad_wlo, lo.size() * sizeof(__half));
-    if (e3 == cudaSuccess) e3 = cudaMemcpy(d->vlad_whi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice);
-    if (e3 == cudaSuccess) e3 = cudaMemcpy(d->vlad_wlo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice);
-    if (e3 != cudaSuccess) rc = cb::fail(CB_ENOMEM, "VLAD weight upload failed: %s", cudaGetErrorString(e3));
-    const uint64_t Pmax = (uint64_t)max_batch * d->Hf * d->Wf;
-    if (!rc) rc = make_map_2d(&d->tmX[0], d->act[0], Pmax, (uint64_t)d->D, 128, 64);
-    if (!rc) rc = make_map_2d(&d->tmX[1], d->act[1], Pmax, (uint64_t)d->D, 128, 64);
-    if (!rc) rc = make_map_2d(&d->tmWhi, d->vlad_whi, (uint64_t)kK, (uint64_t)d->D, kK, 64);
-    if (!rc) rc = make_map_2d(&d->tmWlo, d->vlad_wlo, (uint64_t)kK, (uint64_t)d->D, kK, 64);
-    d->vlad_tc = !rc;
-  }
   for (size_t i = 0; i < d->blocks.size() && !rc; ++i) {
     Block& b = d->blocks[i];
     rc = upload_f32(&b.dw_w, w->dw_w[i], (size_t)9 * b.C);
@@ -1763,10 +1951,113 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
   return CB_OK;
 }
 
+int cb_descriptor_create_v2(cb_descriptor** out, const cb_netvlad_v2_weights* w, int rows, int cols, int chnls, int max_batch,
+                            int device) {
+  if (!out) return cb::fail(CB_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (!w || !w->blocks || w->n_blocks < 1) return cb::fail(CB_EINVAL, "weights is NULL / no blocks");
+  if (chnls != w->in_channels || (chnls != 1 && chnls != 3))
+    return cb::fail(CB_EINVAL, "image channels %d do not match the model's %d (must be 1 or 3)", chnls, w->in_channels);
+  if (rows < 32 || cols < 32 || max_batch < 1) return cb::fail(CB_EINVAL, "bad image size / batch");
+  if (w->vlad_k != kK) return cb::fail(CB_EINVAL, "only K=16 NetVLAD heads are built (got %d)", w->vlad_k);
+  int sm = 0;
+  int rc = cb::select_device(device, &sm);
+  if (rc) return rc;
+  cb::DeviceGuard g(device);
+  cb_descriptor* d = new cb_descriptor();
+  d->v2 = true;
+  d->device = device;
+  d->sm_count = sm;
+  d->rows = rows;
+  d->cols = cols;
+  d->chnls = chnls;
+  d->max_batch = max_batch;
+  const char* env = getenv("CB_PW_SIMT");
+  d->force_simt = env && env[0] == '1';
+  const char* env3 = getenv("CB_NO_FUSE");
+  d->no_fuse = env3 && env3[0] == '1';
+  const char* env2 = getenv("CB_DEBUG_STOP_LAYER");
+  d->stop_layer = env2 ? atoi(env2) : -1;
+  d->H1 = conv_out_s2(rows);
+  d->W1 = conv_out_s2(cols);
+  size_t max_elems = (size_t)d->H1 * d->W1 * 32;
+  d->layer_elems.push_back(max_elems);
+  int h = d->H1, wd = d->W1, c = 32, c_nat = 32;  // stem output: 32 channels, unpadded
+  for (int i = 0; i < w->n_blocks; ++i) {
+    const cb_ir_block& src = w->blocks[i];
+    const bool has_expand = src.expand_w != nullptr;
+    const bool bad = src.c_in != c_nat || src.c_in % 8 || src.c_exp % 8 || src.c_out % 8 || (src.stride != 1 && src.stride != 2) ||
+                     (!has_expand && src.c_exp != src.c_in) || (src.residual && (src.stride != 1 || src.c_in != src.c_out)) ||
+                     !src.dw_w || !src.dw_b || !src.project_w || !src.project_b || (has_expand && !src.expand_b);
+    if (bad) {
+      cb_descriptor_destroy(d);
+      return cb::fail(CB_EINVAL, "inverted-residual block %d is inconsistent (channels %d -> %d -> %d, stride %d, residual %d)", i,
+                      src.c_in, src.c_exp, src.c_out, src.stride, src.residual);
+    }
+    IrBlock b;
+    b.has_expand = has_expand;
+    b.stride = src.stride;
+    b.residual = src.residual;
+    b.Cin = c;
+    b.Cexp = has_expand ? pad64(src.c_exp) : c;
+    b.Cout = pad64(src.c_out);
+    b.Hin = h;
+    b.Win = wd;
+    b.Ho = b.stride == 2 ? conv_out_s2(h) : h;
+    b.Wo = b.stride == 2 ? conv_out_s2(wd) : wd;
+    if (has_expand) d->layer_elems.push_back((size_t)h * wd * b.Cexp);
+    d->layer_elems.push_back((size_t)b.Ho * b.Wo * b.Cexp);
+    d->layer_elems.push_back((size_t)b.Ho * b.Wo * b.Cout);
+    for (int k = 0; k < 3; ++k) {
+      const size_t e = d->layer_elems[d->layer_elems.size() - 1 - k];
+      if (e > max_elems) max_elems = e;
+    }
+    h = b.Ho;
+    wd = b.Wo;
+    c = b.Cout;
+    c_nat = src.c_out;
+    d->ir.push_back(b);
+  }
+  d->Hf = h;
+  d->Wf = wd;
+  d->D = c;
+  d->K = w->vlad_k;
+  if (w->vlad_d != c_nat || c_nat % 64 || c > 512) {
+    cb_descriptor_destroy(d);
+    return cb::fail(CB_EINVAL, "NetVLAD input dim %d does not match backbone output %d (or not a multiple of 64)", w->vlad_d, c_nat);
+  }
+  rc = alloc_common(d, max_elems, 3);
+  if (!rc) rc = setup_stem_and_head(d, w->conv1_w, w->conv1_b, w->vlad_w, w->vlad_b, w->vlad_c);
+  c_nat = 32;
+  for (int i = 0; i < w->n_blocks && !rc; ++i) {
+    const cb_ir_block& src = w->blocks[i];
+    IrBlock& b = d->ir[i];
+    if (b.has_expand)
+      rc = setup_pw_layer(d, b.expand, src.expand_w, src.expand_b, src.c_in, src.c_exp, b.Cin, b.Cexp,
+                          (uint64_t)max_batch * b.Hin * b.Win);
+    if (!rc) rc = upload_f32_padded(&b.dw_w, src.dw_w, 9, (size_t)src.c_exp, (size_t)b.Cexp);
+    if (!rc) rc = upload_f32_padded(&b.dw_b, src.dw_b, 1, (size_t)src.c_exp, (size_t)b.Cexp);
+    if (!rc)
+      rc = setup_pw_layer(d, b.project, src.project_w, src.project_b, src.c_exp, src.c_out, b.Cexp, b.Cout,
+                          (uint64_t)max_batch * b.Ho * b.Wo);
+  }
+  if (rc) {
+    cb_descriptor_destroy(d);
+    return rc;
+  }
+  *out = d;
+  return CB_OK;
+}
+
 int cb_descriptor_destroy(cb_descriptor* d) {
   if (!d) return CB_OK;
   cb::DeviceGuard g(d->device);
   if (d->stream) cudaStreamSynchronize(d->stream);
+  for (IrBlock& b : d->ir) {
+    void* ps[] = {b.expand.w, b.expand.b, b.project.w, b.project.b, b.dw_w, b.dw_b};
+    for (void* q : ps)
+      if (q) cudaFree(q);
+  }
   for (Block& b : d->blocks) {
     cudaFree(b.dw_w);
     cudaFree(b.dw_b);
@@ -1774,7 +2065,7 @@ int cb_descriptor_destroy(cb_descriptor* d) {
     cudaFree(b.pw_b);
   }
   void* ptrs[] = {d->vlad_whi, d->vlad_wlo, d->conv1_hi, d->conv1_lo, d->conv1_w, d->conv1_b, d->vlad_w, d->vlad_b, d->vlad_c, d->act[0], d->act[1],
-                  d->assign,  d->Vraw,    d->img_dev, d->out_dev};
+                  d->act[2], d->assign,  d->Vraw,    d->img_dev, d->out_dev};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (d->stream) cudaStreamDestroy(d->stream);

@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 from . import _lib, keras_weights
-from ._lib import NetvladWeights, check, ptr
+from ._lib import IrBlock, NetvladV2Weights, NetvladWeights, check, ptr
 
 
 def _fptr(a: np.ndarray):
@@ -30,13 +30,46 @@ class NetvladDescriptor:
         self._lib = _lib.load()
         self._h = C.c_void_p()
         self.rows, self.cols, self.chnls, self.max_batch = rows, cols, chnls, max_batch
-        nb = len(net["blocks"])
         keep = []  # keep numpy arrays alive until create returns
 
         def f32(a):
             a = np.ascontiguousarray(a, dtype=np.float32)
             keep.append(a)
             return a
+
+        if net.get("arch") == "mobilenetv2":  # June2019 models: inverted-residual blocks
+            nb = len(net["ir_blocks"])
+            blocks = (IrBlock * nb)()
+            c_in = 32
+            for i, b in enumerate(net["ir_blocks"]):
+                blocks[i].c_in = c_in
+                blocks[i].c_exp = int(b["dw_w"].shape[2])
+                blocks[i].c_out = int(b["project_w"].shape[1])
+                blocks[i].stride = int(b["stride"])
+                blocks[i].residual = int(b["residual"])
+                if b["expand_w"] is not None:
+                    blocks[i].expand_w = _fptr(f32(b["expand_w"]))
+                    blocks[i].expand_b = _fptr(f32(b["expand_b"]))
+                blocks[i].dw_w = _fptr(f32(b["dw_w"]))
+                blocks[i].dw_b = _fptr(f32(b["dw_b"]))
+                blocks[i].project_w = _fptr(f32(b["project_w"]))
+                blocks[i].project_b = _fptr(f32(b["project_b"]))
+                c_in = blocks[i].c_out
+            w2 = NetvladV2Weights()
+            w2.in_channels = int(net["conv1_w"].shape[2])
+            w2.conv1_w = _fptr(f32(net["conv1_w"]))
+            w2.conv1_b = _fptr(f32(net["conv1_b"]))
+            w2.n_blocks = nb
+            w2.blocks = blocks
+            w2.vlad_k = int(net["vlad_w"].shape[1])
+            w2.vlad_d = int(net["vlad_w"].shape[0])
+            w2.vlad_w = _fptr(f32(net["vlad_w"]))
+            w2.vlad_b = _fptr(f32(net["vlad_b"]))
+            w2.vlad_c = _fptr(f32(net["vlad_c"]))
+            check(self._lib.cb_descriptor_create_v2(C.byref(self._h), C.byref(w2), rows, cols, chnls, max_batch, device))
+            self.dim = int(self._lib.cb_descriptor_dim(self._h))
+            return
+        nb = len(net["blocks"])
 
         w = NetvladWeights()
         w.in_channels = int(net["conv1_w"].shape[2])

@@ -283,6 +283,85 @@ def fold_mobilenet_netvlad(w: Dict[str, np.ndarray]) -> dict:
     return net
 
 
+# depthwise stride of inverted-residual block i (0 = expanded_conv) in keras_applications' MobileNetV2, the builder the
+# June2019 models were made with (keras_helpers.py / the model_config embedded in each .h5)
+MOBILENETV2_STRIDES = [1, 2, 1, 2, 1, 1, 2, 1, 1, 1, 1, 1, 1, 2, 1, 1, 1]
+
+
+def is_mobilenetv2(w: Dict[str, np.ndarray]) -> bool:
+    return "Conv1/kernel" in w and "expanded_conv_depthwise/depthwise_kernel" in w
+
+
+def fold_mobilenetv2_netvlad(w: Dict[str, np.ndarray]) -> dict:
+    """Fold BN and describe a MobileNetV2-prefix + NetVLAD model (the June2019 ``mobilenetv2-block_9_add`` files the
+    mynteye launch files select, launch/mynteye_vinsfusion.launch:100).  Layer list = the embedded ``model_config``:
+    Conv1 (3x3 s2, pad bottom/right) + bn_Conv1 + ReLU6, then inverted-residual blocks: [expand 1x1 + BN + ReLU6],
+    depthwise 3x3 (s1 'same' | pad bottom/right + s2 'valid') + BN + ReLU6, project 1x1 + BN (linear), Add with the block
+    input when stride 1 and the channel counts agree.  Returns
+      arch 'mobilenetv2', conv1_w (3,3,Cin,32), conv1_b (32,),
+      ir_blocks: list of dict(expand_w (Cin,Cexp)|None, expand_b, dw_w (3,3,Cexp), dw_b, project_w (Cexp,Cout), project_b,
+                              stride, residual), vlad_w (D,K), vlad_b (K,), vlad_c (D,K)."""
+
+    def bn(prefix):
+        g = w[prefix + "/gamma"].astype(np.float64)
+        b = w[prefix + "/beta"].astype(np.float64)
+        m = w[prefix + "/moving_mean"].astype(np.float64)
+        v = w[prefix + "/moving_variance"].astype(np.float64)
+        sc = g / np.sqrt(v + BN_EPS)
+        return sc, b - m * sc
+
+    def pw(name):
+        k = w[name + "/kernel"].astype(np.float64)[0, 0]
+        sc, o = bn(name + "_BN")
+        return (k * sc).astype(np.float32), o.astype(np.float32)
+
+    def dw(name):
+        k = w[name + "/depthwise_kernel"].astype(np.float64)[:, :, :, 0]
+        sc, o = bn(name + "_BN")
+        return (k * sc).astype(np.float32), o.astype(np.float32)
+
+    sc, o = bn("bn_Conv1")
+    net = {
+        "arch": "mobilenetv2",
+        "conv1_w": (w["Conv1/kernel"].astype(np.float64) * sc).astype(np.float32),
+        "conv1_b": o.astype(np.float32),
+        "ir_blocks": [],
+    }
+    names = ["expanded_conv"]
+    i = 1
+    while ("block_%d_depthwise/depthwise_kernel" % i) in w:
+        names.append("block_%d" % i)
+        i += 1
+    c_in = 32
+    for i, nm in enumerate(names):
+        blk = {"stride": MOBILENETV2_STRIDES[i]}
+        if (nm + "_expand/kernel") in w:
+            blk["expand_w"], blk["expand_b"] = pw(nm + "_expand")
+        else:
+            blk["expand_w"], blk["expand_b"] = None, None
+        blk["dw_w"], blk["dw_b"] = dw(nm + "_depthwise")
+        blk["project_w"], blk["project_b"] = pw(nm + "_project")
+        c_out = blk["project_w"].shape[1]
+        blk["residual"] = int(blk["stride"] == 1 and c_in == c_out and blk["expand_w"] is not None)
+        net["ir_blocks"].append(blk)
+        c_in = c_out
+    vl = [k.split("/")[0] for k in w if k.endswith("/cluster_centers")]
+    if len(vl) != 1:
+        raise KerasWeightsError("expected exactly one NetVLAD layer, found %r" % vl)
+    v = vl[0]
+    net["vlad_w"] = np.ascontiguousarray(w[v + "/kernel"][0, 0]).astype(np.float32)
+    net["vlad_b"] = np.ascontiguousarray(w[v + "/bias"].reshape(-1)).astype(np.float32)
+    net["vlad_c"] = np.ascontiguousarray(w[v + "/cluster_centers"][0, 0, 0]).astype(np.float32)
+    if net["vlad_w"].shape[0] != c_in:
+        raise KerasWeightsError("NetVLAD input dim %d != backbone output %d" % (net["vlad_w"].shape[0], c_in))
+    return net
+
+
+def fold_model(w: Dict[str, np.ndarray]) -> dict:
+    """BN-fold whichever shipped architecture the raw weight dict belongs to."""
+    return fold_mobilenetv2_netvlad(w) if is_mobilenetv2(w) else fold_mobilenet_netvlad(w)
+
+
 def random_mobilenet_netvlad(in_ch: int = 3, n_blocks: int = 7, K: int = 16, seed: int = 0) -> dict:
     """Random-init weights of the shipped architecture (for synthetic benches)."""
     rng = np.random.default_rng(seed)
@@ -317,10 +396,15 @@ def random_mobilenet_netvlad(in_ch: int = 3, n_blocks: int = 7, K: int = 16, see
 _MAGIC = b"CBW1"
 
 
+_V1_KEYS = ("dw_w", "dw_b", "pw_w", "pw_b")
+_V2_KEYS = ("expand_w", "expand_b", "dw_w", "dw_b", "project_w", "project_b")
+
+
 def _flatten(net: dict) -> List[Tuple[str, np.ndarray]]:
     items = [("conv1_w", net["conv1_w"]), ("conv1_b", net["conv1_b"])]
-    for i, b in enumerate(net["blocks"]):
-        for k in ("dw_w", "dw_b", "pw_w", "pw_b"):
+    v2 = net.get("arch") == "mobilenetv2"
+    for i, b in enumerate(net["ir_blocks"] if v2 else net["blocks"]):
+        for k in _V2_KEYS if v2 else _V1_KEYS:
             if b[k] is not None:
                 items.append(("b%d_%s" % (i, k), b[k]))
     for k in ("vlad_w", "vlad_b", "vlad_c"):
@@ -330,8 +414,11 @@ def _flatten(net: dict) -> List[Tuple[str, np.ndarray]]:
 
 def save_cbw(path: str, net: dict, meta: dict | None = None) -> None:
     items = _flatten(net)
+    v2 = net.get("arch") == "mobilenetv2"
     hdr = {
-        "strides": [b["stride"] for b in net["blocks"]],
+        "arch": "mobilenetv2" if v2 else "mobilenet",
+        "strides": [b["stride"] for b in (net["ir_blocks"] if v2 else net["blocks"])],
+        "residual": [b["residual"] for b in net["ir_blocks"]] if v2 else [],
         "arrays": [[n, list(a.shape)] for n, a in items],
         "meta": meta or {},
     }
@@ -355,9 +442,19 @@ def load_cbw(path: str) -> dict:
         cnt = int(np.prod(shape))
         arrs[name] = np.frombuffer(buf, dtype="<f4", count=cnt, offset=p).reshape(shape).copy()
         p += 4 * cnt
+    if hdr.get("arch") == "mobilenetv2":
+        net = {"arch": "mobilenetv2", "conv1_w": arrs["conv1_w"], "conv1_b": arrs["conv1_b"], "ir_blocks": []}
+        for i, s in enumerate(hdr["strides"]):
+            net["ir_blocks"].append({k: arrs.get("b%d_%s" % (i, k)) for k in _V2_KEYS})
+            net["ir_blocks"][-1]["stride"] = s
+            net["ir_blocks"][-1]["residual"] = hdr["residual"][i]
+        for k in ("vlad_w", "vlad_b", "vlad_c"):
+            net[k] = arrs[k]
+        net["meta"] = hdr.get("meta", {})
+        return net
     net = {"conv1_w": arrs["conv1_w"], "conv1_b": arrs["conv1_b"], "blocks": []}
     for i, s in enumerate(hdr["strides"]):
-        net["blocks"].append({k: arrs.get("b%d_%s" % (i, k)) for k in ("dw_w", "dw_b", "pw_w", "pw_b")})
+        net["blocks"].append({k: arrs.get("b%d_%s" % (i, k)) for k in _V1_KEYS})
         net["blocks"][-1]["stride"] = s
     for k in ("vlad_w", "vlad_b", "vlad_c"):
         net[k] = arrs[k]
@@ -371,4 +468,4 @@ def load_model(path: str) -> dict:
         magic = f.read(8)
     if magic[:4] == _MAGIC:
         return load_cbw(path)
-    return fold_mobilenet_netvlad(load_keras_file(path))
+    return fold_model(load_keras_file(path))

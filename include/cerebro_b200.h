@@ -161,6 +161,40 @@ typedef struct cb_netvlad_weights {
 CB_API int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int rows, int cols,
                          int chnls, int max_batch, int device);
 CB_API int cb_descriptor_destroy(cb_descriptor* d);
+/* The June2019 models (scripts/keras.models/June2019/*mobilenetv2-block_9_add*, selected at
+ * launch/mynteye_vinsfusion.launch:100 and built by keras_helpers.py from keras_applications'
+ * MobileNetV2): Conv1 3x3 s2 (pad bottom/right) + ReLU6, then inverted-residual blocks
+ * [expand 1x1 + ReLU6] -> depthwise 3x3 (s1 'same' | pad bottom/right + s2 'valid') + ReLU6 ->
+ * project 1x1 (linear) [+ block input], then NetVLAD.  Weights BN-folded, fp32, natural
+ * (unpadded) channel counts, multiples of 8. */
+typedef struct cb_ir_block {
+  int c_in, c_exp, c_out;  /* block input / expanded / output channels */
+  int stride;              /* depthwise stride, 1 or 2 */
+  int residual;            /* 1: output = project + block input (the Keras Add layer) */
+  const float* expand_w;   /* [c_in][c_exp], NULL for expanded_conv (then c_exp == c_in) */
+  const float* expand_b;   /* [c_exp] */
+  const float* dw_w;       /* [3][3][c_exp] */
+  const float* dw_b;       /* [c_exp] */
+  const float* project_w;  /* [c_exp][c_out] */
+  const float* project_b;  /* [c_out] */
+} cb_ir_block;
+
+typedef struct cb_netvlad_v2_weights {
+  int in_channels;       /* 1 or 3 */
+  const float* conv1_w;  /* [3][3][in_channels][32] */
+  const float* conv1_b;  /* [32] */
+  int n_blocks;
+  const cb_ir_block* blocks;
+  int vlad_k, vlad_d;
+  const float* vlad_w; /* [D][K] */
+  const float* vlad_b; /* [K] */
+  const float* vlad_c; /* [D][K] */
+} cb_netvlad_v2_weights;
+
+/* Same handle type and the same compute / dim / destroy calls as cb_descriptor_create. */
+CB_API int cb_descriptor_create_v2(cb_descriptor** out, const cb_netvlad_v2_weights* w, int rows, int cols,
+                            int chnls, int max_batch, int device);
+
 CB_API int cb_descriptor_dim(const cb_descriptor* d); /* K * D, what the probe call learns (Cerebro.cpp:113-120) */
 
 /* handle_req (server.py:596-650) for `n` frames: uint8 images [n][rows][cols][chnls]

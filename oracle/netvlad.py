@@ -82,6 +82,61 @@ def backbone(x: torch.Tensor, w: dict, return_all: bool = False):
     return (x, acts) if return_all else x
 
 
+def backbone_v2(x: torch.Tensor, w: dict, return_all: bool = False):
+    """MobileNetV2 prefix of the June2019 models (layer list = the ``model_config`` embedded in
+    scripts/keras.models/June2019/*mobilenetv2-block_9_add*/modelarch_and_weights.*.h5, cut at ``block_<n>_add``):
+    Conv1_pad ((0,1),(0,1)) + Conv1 3x3 s2 'valid' + bn_Conv1 + ReLU6; expanded_conv (depthwise 'same' + BN + ReLU6,
+    project 1x1 + BN, linear); block_i: expand 1x1 + BN + ReLU6, [block_i_pad ((0,1),(0,1)) + depthwise s2 'valid' |
+    depthwise s1 'same'] + BN + ReLU6, project 1x1 + BN (linear), Add with the block input when stride 1 and the channel
+    counts agree (keras_applications MobileNetV2 _inverted_res_block; strides (1,2,1,2,1,1,2,1,1,1,...) for blocks 0..).
+    x: NCHW.  Returns the NCHW feature map."""
+    dt = x.dtype
+    acts = []
+
+    def conv(x, name, stride=1):
+        k = torch.as_tensor(w[name + "/kernel"], dtype=dt).permute(3, 2, 0, 1)
+        return F.conv2d(x, k, stride=stride)
+
+    def dwise(x, name, stride):
+        dk = torch.as_tensor(w[name + "/depthwise_kernel"], dtype=dt)
+        C = dk.shape[2]
+        dk = dk.permute(2, 3, 0, 1)
+        if stride == 2:
+            return F.conv2d(F.pad(x, (0, 1, 0, 1)), dk, stride=2, groups=C)
+        return F.conv2d(x, dk, stride=1, padding=1, groups=C)
+
+    x = F.pad(x, (0, 1, 0, 1))
+    x = _relu6(_bn(conv(x, "Conv1", 2), w, "bn_Conv1", dt))
+    acts.append(x)
+    x = _relu6(_bn(dwise(x, "expanded_conv_depthwise", 1), w, "expanded_conv_depthwise_BN", dt))
+    acts.append(x)
+    x = _bn(conv(x, "expanded_conv_project"), w, "expanded_conv_project_BN", dt)
+    acts.append(x)
+    i = 1
+    while ("block_%d_expand/kernel" % i) in w:
+        pre = "block_%d_" % i
+        stride = MOBILENETV2_STRIDES[i]
+        inp = x
+        x = _relu6(_bn(conv(x, pre + "expand"), w, pre + "expand_BN", dt))
+        acts.append(x)
+        x = _relu6(_bn(dwise(x, pre + "depthwise", stride), w, pre + "depthwise_BN", dt))
+        acts.append(x)
+        x = _bn(conv(x, pre + "project"), w, pre + "project_BN", dt)
+        if stride == 1 and inp.shape[1] == x.shape[1]:
+            x = inp + x
+        acts.append(x)
+        i += 1
+    return (x, acts) if return_all else x
+
+
+# depthwise stride of inverted-residual block i (0 = expanded_conv) in keras_applications' MobileNetV2
+MOBILENETV2_STRIDES = [1, 2, 1, 2, 1, 1, 2, 1, 1, 1, 1, 1, 1, 2, 1, 1, 1]
+
+
+def is_mobilenetv2(w: dict) -> bool:
+    return "Conv1/kernel" in w and "expanded_conv_depthwise/depthwise_kernel" in w
+
+
 def netvlad(x: torch.Tensor, w: dict) -> torch.Tensor:
     """predict_utils.py:36-64.  x: NCHW feature map -> [N, K*D], index k*D+d."""
     dt = x.dtype
@@ -111,6 +166,6 @@ def describe(images_u8: np.ndarray, w: dict, dtype: str = "float32", threads: in
         torch.set_num_threads(threads)
     with torch.no_grad():
         x = preprocess(images_u8, dt)
-        f = backbone(x, w)
+        f = backbone_v2(x, w) if is_mobilenetv2(w) else backbone(x, w)
         d = netvlad(f, w)
     return d.numpy()

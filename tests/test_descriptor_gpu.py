@@ -18,12 +18,12 @@ L2_TOL = 2e-2
 
 
 def _net(model):
-    from cerebro_b200.keras_weights import fold_mobilenet_netvlad
+    from cerebro_b200.keras_weights import fold_model
 
-    return fold_mobilenet_netvlad(golden_io.raw_weights(model))
+    return fold_model(golden_io.raw_weights(model))
 
 
-@pytest.mark.parametrize("model,c", [("gray_conv6", 1), ("mobilenet_conv7", 3)])
+@pytest.mark.parametrize("model,c", [("gray_conv6", 1), ("mobilenet_conv7", 3), ("mobilenetv2_block9_gray", 1), ("mobilenet_pw6", 3)])
 @pytest.mark.parametrize("h,w", [(96, 128), (240, 320)])
 def test_descriptor_matches_golden(native_lib, cuda_device, model, c, h, w):
     from cerebro_b200.descriptor import NetvladDescriptor
@@ -74,6 +74,43 @@ def test_layerwise_against_oracle(native_lib, cuda_device):
     finally:
         os.environ.pop("CB_DEBUG_STOP_LAYER", None)
     print("worst layer abs err", worst)
+
+
+def test_mobilenetv2_layerwise_against_oracle(native_lib, cuda_device):
+    """June2019 MobileNetV2 prefix: every layer (expand / depthwise / linear project + Add) vs the oracle's fp32
+    activation.  Device channel counts are padded to multiples of 64; the padding must be exactly zero."""
+    import torch
+
+    from cerebro_b200.descriptor import NetvladDescriptor
+    from oracle import netvlad as NV
+
+    model, c, h, w = "mobilenetv2_block9_gray", 1, 96, 128
+    raw = golden_io.raw_weights(model)
+    net = _net(model)
+    imgs = synth.band_limited_images(1, h, w, c, seed=5)
+    x = NV.preprocess(imgs, torch.float32)
+    _, acts = NV.backbone_v2(x, raw, return_all=True)
+    try:
+        for variant in ({}, {"CB_PW_SIMT": "1"}):
+            for layer, a in enumerate(acts):
+                os.environ["CB_DEBUG_STOP_LAYER"] = str(layer)
+                os.environ.update(variant)
+                nd = NetvladDescriptor(net, h, w, c, max_batch=1)
+                nd.compute(imgs)
+                got = nd.get_activation(layer)
+                nd.close()
+                ref = a[0].permute(1, 2, 0).contiguous().numpy()  # H, W, C
+                cn = ref.shape[2]
+                cp = cn if layer <= 1 else (cn + 63) // 64 * 64  # stem and expanded_conv depthwise: 32 channels, unpadded
+                got = got.reshape(ref.shape[0], ref.shape[1], cp)
+                assert np.all(got[:, :, cn:] == 0.0), "layer %d: padded channels not zero" % layer
+                err = np.abs(got[:, :, :cn] - ref)
+                scale = max(1.0, float(np.abs(ref).max()))
+                assert err.max() < 0.05 * scale, "layer %d (%s): max abs err %g, scale %g" % (layer, variant, err.max(), scale)
+                assert err.mean() < 0.01, "layer %d (%s): mean abs err %g" % (layer, variant, err.mean())
+    finally:
+        os.environ.pop("CB_DEBUG_STOP_LAYER", None)
+        os.environ.pop("CB_PW_SIMT", None)
 
 
 def test_tcgen05_path_agrees_with_cuda_core_path(native_lib, cuda_device):

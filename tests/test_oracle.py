@@ -1,6 +1,8 @@
 """CPU tests that pin the oracle: committed golden fixtures, invariants, independent solvers."""
 import math
 
+import os
+
 import numpy as np
 import pytest
 
@@ -143,7 +145,8 @@ def test_faiss_naive_stream_runs():
 
 
 # ------------------------------------------------------------------ NetVLAD
-@pytest.mark.parametrize("model,c,dim", [("mobilenet_conv7", 3, 8192), ("gray_conv6", 1, 4096)])
+@pytest.mark.parametrize("model,c,dim", [("mobilenet_conv7", 3, 8192), ("gray_conv6", 1, 4096),
+                                         ("mobilenetv2_block9_gray", 1, 1024), ("mobilenet_pw6", 3, 8192)])
 def test_netvlad_golden_and_invariants(model, c, dim):
     w = golden_io.raw_weights(model)
     gold = golden_io.load("netvlad_golden.npz")["%s_96x128_desc64" % model]
@@ -191,3 +194,53 @@ def test_bn_folding_matches_unfolded_oracle():
     y = F.conv2d(F.pad(x, (0, 1, 0, 1)), k, stride=2) + torch.as_tensor(net["conv1_b"], dtype=torch.float64).view(1, -1, 1, 1)
     y = torch.clamp(y, 0, 6)
     assert torch.allclose(y, acts[0], atol=1e-5)
+
+
+def test_mobilenetv2_folding_and_cbw_roundtrip(tmp_path):
+    """June2019 MobileNetV2 model: BN folding of the inverted-residual blocks (expand / depthwise / linear project / Add)
+    reproduces the un-folded oracle, and the .cbw container round-trips the folded network."""
+    import torch
+    import torch.nn.functional as F
+
+    from cerebro_b200 import keras_weights as KW
+
+    w = golden_io.raw_weights("mobilenetv2_block9_gray")
+    assert KW.is_mobilenetv2(w)
+    net = KW.fold_model(w)
+    assert net["arch"] == "mobilenetv2" and len(net["ir_blocks"]) == 10
+    assert [b["stride"] for b in net["ir_blocks"]] == [1, 2, 1, 2, 1, 1, 2, 1, 1, 1]
+    assert [b["residual"] for b in net["ir_blocks"]] == [0, 0, 1, 0, 1, 1, 0, 1, 1, 1]  # block_{2,4,5,7,8,9}_add in the model_config
+    path = os.path.join(str(tmp_path), "v2.cbw")
+    KW.save_cbw(path, net)
+    net = KW.load_model(path)
+    imgs = synth.band_limited_images(1, 64, 96, 1, seed=2)
+    dt = torch.float64
+    x = NV.preprocess(imgs, dt)
+    ref, acts = NV.backbone_v2(x, w, return_all=True)
+
+    def t(a):
+        return torch.as_tensor(a, dtype=dt)
+
+    def pw(x, wt, b):
+        return F.conv2d(x, t(wt).t()[:, :, None, None]) + t(b).view(1, -1, 1, 1)
+
+    def dw(x, wt, b, stride):
+        k = t(wt).permute(2, 0, 1)[:, None]
+        if stride == 2:
+            y = F.conv2d(F.pad(x, (0, 1, 0, 1)), k, stride=2, groups=k.shape[0])
+        else:
+            y = F.conv2d(x, k, padding=1, groups=k.shape[0])
+        return y + t(b).view(1, -1, 1, 1)
+
+    y = F.conv2d(F.pad(x, (0, 1, 0, 1)), t(net["conv1_w"]).permute(3, 2, 0, 1), stride=2) + t(net["conv1_b"]).view(1, -1, 1, 1)
+    y = torch.clamp(y, 0, 6)
+    for b in net["ir_blocks"]:
+        inp = y
+        if b["expand_w"] is not None:
+            y = torch.clamp(pw(y, b["expand_w"], b["expand_b"]), 0, 6)
+        y = torch.clamp(dw(y, b["dw_w"], b["dw_b"], b["stride"]), 0, 6)
+        y = pw(y, b["project_w"], b["project_b"])
+        if b["residual"]:
+            y = y + inp
+    assert y.shape == ref.shape
+    assert torch.allclose(y, ref, atol=1e-4), float((y - ref).abs().max())

@@ -1,6 +1,6 @@
 """Generates tests/golden/* in the build container (where /root/reference is mounted).
 
-  keras_raw_<model>.npz   RAW Keras weights of two shipped models, re-packed (not sources: data
+  keras_raw_<model>.npz   RAW Keras weights of four shipped models, re-packed (not sources: data
                           the parity tests need on the GPU box, where /root/reference is absent)
   netvlad_golden.npz      seeded uint8 images -> descriptors from oracle/netvlad.py in fp64
   pnp_golden.npz          seeded candidates + sample tables -> oracle RANSAC outputs
@@ -22,6 +22,9 @@ REF = "/root/reference/scripts/keras.models/"
 MODELS = {
     "mobilenet_conv7": REF + "mobilenet_conv7_allpairloss.keras",
     "gray_conv6": REF + "Apr2019/gray_conv6_K16__centeredinput/core_model.1000.keras",
+    # June2019 models: MobileNetV2 prefix (inverted residuals, 1024-D) and MobileNet-v1 cut after conv_pw_6
+    "mobilenetv2_block9_gray": REF + "June2019/centeredinput-m1to1-240x320x1__mobilenetv2-block_9_add__K16__allpairloss/modelarch_and_weights.2000.h5",
+    "mobilenet_pw6": REF + "June2019/centeredinput-m1to1-240x320x3__mobilenet-conv_pw_6_relu__K16__allpairloss/modelarch_and_weights.700.h5",
 }
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -32,7 +35,7 @@ def main():
     for name, path in MODELS.items():
         w = load_keras_file(path)
         np.savez(os.path.join(OUT, "keras_raw_%s.npz" % name), **{k.replace("/", "__"): v for k, v in w.items()})
-        c = w["conv1/kernel"].shape[2]
+        c = (w["conv1/kernel"] if "conv1/kernel" in w else w["Conv1/kernel"]).shape[2]
         for (h, wd) in ((96, 128), (240, 320)):
             imgs = synth.band_limited_images(2, h, wd, c, seed=h + c)
             d64 = netvlad.describe(imgs, w, dtype="float64")
