@@ -92,6 +92,55 @@ class ProcessedLoopCandidate:
         return None
 
 
+class Hypothesis:
+    """HypothesisManager.h:26-131: a chain of (a, b, dot product) nodes with a time-to-live."""
+
+    def __init__(self, a, b, prod):
+        self.list_of_nodes_in_this_hypothesis = [(a, b, prod)]
+        self.time_to_live = 20  # :32
+
+    def decrement_ttl(self):  # :103-108
+        if self.time_to_live <= 0:
+            return
+        self.time_to_live -= 1
+
+    def increment_ttl(self):  # :110-121
+        self.time_to_live += 1
+        if self.time_to_live > 100:
+            self.time_to_live += 1
+
+    def get_ttl(self):
+        return self.time_to_live
+
+    def is_hypothesis_active(self):
+        return self.time_to_live > 0
+
+    def n_elements_in_list(self):
+        return len(self.list_of_nodes_in_this_hypothesis)
+
+
+class HypothesisManager:
+    """HypothesisManager.cpp:15-87 (the monitoring thread that prints to /dev/pts/1 is not part of the path)."""
+
+    def __init__(self):
+        self.active_hyp = []
+
+    def add_node(self, a, b, dot_prod):
+        for h in self.active_hyp:
+            for (_a, _b, _) in reversed(h.list_of_nodes_in_this_hypothesis):  # :42-58, newest node first
+                if abs(a - _a) < 7 and abs(b - _b) < 7:
+                    h.list_of_nodes_in_this_hypothesis.append((a, b, dot_prod))
+                    h.increment_ttl()
+                    return True
+        self.active_hyp.append(Hypothesis(a, b, dot_prod))  # :65-68
+        return True
+
+    def digest(self):  # :74-87: four decrements per searched descriptor
+        for h in self.active_hyp:
+            for _ in range(4):
+                h.decrement_ttl()
+
+
 class Cerebro:
     LOCALITY_THRESH = 12  # Cerebro.cpp:912
     DOT_PROD_THRESH = 0.85  # Cerebro.cpp:913
@@ -107,6 +156,7 @@ class Cerebro:
         self._processed = []  # processedloopcandi_list (Cerebro.h:199-200)
         self._last_l = 0
         self._last_consumed = 0
+        self.hyp_manager = HypothesisManager()  # faiss_multihypothesis_tracking's (Cerebro.cpp:757)
 
     # ---- wholeImageComputedList_* (Cerebro.cpp:305-330)
     def wholeImageComputedList_size(self):
@@ -133,6 +183,30 @@ class Cerebro:
 
     def processedLoops_i(self, i):
         return self._processed[i]
+
+    # ---- resume / persist (DataManager::loadStateFromDisk + Cerebro.cpp:128-160; DataManager::saveStateToDisk)
+    def load_state(self, save_folder_name):
+        """Re-list every stored descriptor (ascending stamp) into wholeImageComputedList and bulk-load the rows into
+        the device index with one call.  Stamps are the nodes' ``stampNSec``.  Returns the number of rows loaded."""
+        from . import state_io
+
+        stamps, descs, _ = state_io.load_state(save_folder_name)
+        if not stamps:
+            return 0
+        if descs.shape[1] != self.descriptor_size:
+            raise ValueError("state.json holds %d-D descriptors, the model produces %d-D" % (descs.shape[1], self.descriptor_size))
+        self.index.add(np.ascontiguousarray(descs, dtype=np.float64))  # cb_index_add_f64: narrowed to fp32 on the device
+        self._whole.extend(stamps)
+        self._last_l = len(self._whole)  # nothing already listed is re-searched as "new"
+        return len(stamps)
+
+    def save_state(self, save_folder_name):
+        """state.json with one data node per listed keyframe, descriptors read back from the device index."""
+        from . import state_io
+
+        n = len(self._whole)
+        rows = self.index.get_rows(0, n) if n else np.zeros((0, self.descriptor_size), dtype=np.float32)
+        return state_io.save_state(save_folder_name, self._whole, rows.astype(np.float64))
 
     # ---- descriptor_computer_thread body (Cerebro.cpp:169-298), for the keyframes handed in
     def descriptor_step(self, stamps, images_u8, n_tracked=None):
@@ -188,6 +262,85 @@ class Cerebro:
             self._found.append(edge)
             return edge
         return None
+
+    # ---- shared by the two top-5 generators below: one wake-up's searches as ONE batched device call
+    CLIQUE_LAG = 150  # start_adding_descriptors_to_index_after (Cerebro.cpp:513, :743)
+    CLIQUE_K = 5
+    CLIQUE_THRESH = 0.85
+    CLIQUE_LOCALITY = 7
+    CLIQUE_RESET = 4
+
+    def _top5_of_new(self, last_l, l):
+        """index.search of every descriptor in [last_l, l) against rows [0, l-150) (the reference adds with a 150-frame
+        lag before searching, :559-581): the whole wake-up is one batched sweep.  None when ntotal < 5 (:600 break)."""
+        limit = l - self.CLIQUE_LAG
+        if limit < self.CLIQUE_K:
+            return None
+        q = self.index.get_rows(last_l, l - last_l)
+        return self.index.search(q, self.CLIQUE_K, limit_rows=limit, tie=TIE_LOW_LABEL)
+
+    # ---- one wake-up of faiss_clique_loopcandidate_generator (Cerebro.cpp:506-722)
+    def faiss_clique_step(self, rand=None):
+        """Top-5 neighbours above 0.85 vote into ``retained`` (label -> votes; the duplicate test is the reference's
+        signed ``(key - label) < 7`` over the ascending std::map, first hit wins, :633-661); every 4th list index the
+        accumulated cliques are pushed to foundLoops with score 0.9 -- all of them when there is one, otherwise each
+        with probability 1/len via ``rand() % 100 < 100/len`` (:664-713; ``rand`` defaults to "always keep")."""
+        rand = rand or (lambda: 0)
+        l = self.wholeImageComputedList_size()
+        last_l = self._last_l
+        if l <= last_l:  # :544
+            return []
+        self._last_l = l
+        res = self._top5_of_new(last_l, l)
+        if res is None:
+            return []
+        D, I = res
+        if not hasattr(self, "_retained"):
+            self._retained = {}
+        retained, out = self._retained, []
+        for j, li in enumerate(range(last_l, l)):
+            for g in range(self.CLIQUE_K):
+                if D[j, g] < np.float32(self.CLIQUE_THRESH):
+                    break
+                dup = -1
+                for key in sorted(retained):
+                    if key - int(I[j, g]) < self.CLIQUE_LOCALITY:
+                        dup = key
+                        break
+                if dup != -1:
+                    retained[dup] += 1
+                else:
+                    retained[int(I[j, g])] = 1
+            if retained and li % self.CLIQUE_RESET == 0:
+                if len(retained) == 1:
+                    keys = list(retained)
+                else:
+                    percent = int(100.0 / len(retained))
+                    keys = [k for k in sorted(retained) if rand() % 100 < percent]
+                for k in keys:
+                    edge = (self._whole[l - 1], self._whole[k], 0.9)
+                    self._found.append(edge)
+                    out.append(edge)
+                retained.clear()
+        return out
+
+    # ---- one wake-up of faiss_multihypothesis_tracking (Cerebro.cpp:731-885)
+    def faiss_multihypothesis_step(self):
+        l = self.wholeImageComputedList_size()
+        last_l = self._last_l
+        if l <= last_l:
+            return self.hyp_manager
+        self._last_l = l
+        res = self._top5_of_new(last_l, l)
+        if res is None:
+            return self.hyp_manager
+        D, I = res
+        for j, li in enumerate(range(last_l, l)):
+            for g in range(self.CLIQUE_K):
+                if D[j, g] > np.float32(0.85):  # :857
+                    self.hyp_manager.add_node(li, int(I[j, g]), float(D[j, g]))
+            self.hyp_manager.digest()
+        return self.hyp_manager
 
     # ---- loopcandiate_consumer_thread body (Cerebro.cpp:1203-1277), geometry supplied by the caller
     def loopcandidate_consumer_step(self, correspondences, params=None):

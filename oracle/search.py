@@ -141,3 +141,125 @@ def faiss_naive_stream(desc: np.ndarray, arrivals, lag: int = 150, thresh: float
             found.append((l - 1, tmp_i[2], tmp[2]))
         last_l = l
     return found
+
+
+# --------------------------------------------------------------------------------------------
+# faiss_clique_loopcandidate_generator (Cerebro.cpp:506-722) and faiss_multihypothesis_tracking
+# (Cerebro.cpp:731-885) + HypothesisManager (HypothesisManager.cpp:15-87, HypothesisManager.h:26-131),
+# replayed over an arrival schedule.  Both are alternates of run() (Cerebro.cpp:352-355).
+# --------------------------------------------------------------------------------------------
+CLIQUE_LAG = 150  # start_adding_descriptors_to_index_after, :513
+CLIQUE_K = 5  # :514
+CLIQUE_THRESH = 0.85  # :515
+CLIQUE_LOCALITY = 7  # :516
+CLIQUE_RESET = 4  # reset_accumulation_every_n_frames, :517
+
+
+def clique_accumulate(retained: dict, D, I) -> None:
+    """:633-661.  ``retained`` maps label -> votes and is walked in ascending key order (std::map); the duplicate
+    test is the reference's SIGNED difference ``(key - label) < LOCALITY`` (no abs), first hit wins."""
+    for g in range(len(D)):
+        if D[g] < np.float32(CLIQUE_THRESH):
+            break
+        dup = -1
+        for key in sorted(retained):
+            if key - int(I[g]) < CLIQUE_LOCALITY:
+                dup = key
+                break
+        if dup != -1:
+            retained[dup] += 1
+        else:
+            retained[int(I[g])] = 1
+
+
+def faiss_clique_stream(desc: np.ndarray, arrivals, rand=None):
+    """Returns foundLoops [(curr, prev, 0.9), ...].  ``rand`` stands in for libc ``rand()`` (:703); default: a
+    generator that always returns 0 (every candidate retained)."""
+    rand = rand or (lambda: 0)
+    index = IndexFlatIP(desc.shape[1])
+    found, retained = [], {}
+    last_l = added = 0
+    for l in arrivals:
+        if l <= last_l:  # :544
+            continue
+        if l > CLIQUE_LAG:  # :559
+            if l - CLIQUE_LAG > added:
+                index.add(desc[added : l - CLIQUE_LAG])
+            added = max(added, l - CLIQUE_LAG)
+        for li in range(last_l, l):  # :593
+            if index.ntotal < CLIQUE_K:  # :600 break
+                break
+            D, I = index.search(desc[li], CLIQUE_K)
+            clique_accumulate(retained, D[0], I[0])
+            if len(retained) > 0 and li % CLIQUE_RESET == 0:  # :664
+                if len(retained) == 1:
+                    found.append((l - 1, next(iter(retained)), 0.9))
+                else:
+                    percent = int(100.0 / len(retained))
+                    for key in sorted(retained):
+                        if rand() % 100 < percent:
+                            found.append((l - 1, key, 0.9))
+                retained.clear()
+        last_l = l
+    return found
+
+
+class Hypothesis:  # HypothesisManager.h:26-131
+    def __init__(self, a, b, prod):
+        self.nodes = [(a, b, prod)]
+        self.time_to_live = 20
+
+    def decrement_ttl(self):
+        if self.time_to_live > 0:
+            self.time_to_live -= 1
+
+    def increment_ttl(self):
+        self.time_to_live += 1
+        if self.time_to_live > 100:
+            self.time_to_live += 1
+
+    def is_hypothesis_active(self):
+        return self.time_to_live > 0
+
+
+class HypothesisManager:  # HypothesisManager.cpp:15-87
+    def __init__(self):
+        self.active_hyp = []
+
+    def add_node(self, a, b, dot_prod):
+        for h in self.active_hyp:  # note: expired hypotheses (ttl 0) stay in the list and still absorb nodes
+            for (_a, _b, _) in reversed(h.nodes):
+                if abs(a - _a) < 7 and abs(b - _b) < 7:
+                    h.nodes.append((a, b, dot_prod))
+                    h.increment_ttl()
+                    return
+        self.active_hyp.append(Hypothesis(a, b, dot_prod))
+
+    def digest(self):
+        for h in self.active_hyp:
+            for _ in range(4):
+                h.decrement_ttl()
+
+
+def faiss_multihypothesis_stream(desc: np.ndarray, arrivals):
+    """Returns the HypothesisManager after the stream (Cerebro.cpp:731-885)."""
+    index = IndexFlatIP(desc.shape[1])
+    hm = HypothesisManager()
+    last_l = added = 0
+    for l in arrivals:
+        if l <= last_l:
+            continue
+        if l > CLIQUE_LAG:
+            if l - CLIQUE_LAG > added:
+                index.add(desc[added : l - CLIQUE_LAG])
+            added = max(added, l - CLIQUE_LAG)
+        for li in range(last_l, l):
+            if index.ntotal < CLIQUE_K:
+                break
+            D, I = index.search(desc[li], CLIQUE_K)
+            for g in range(CLIQUE_K):
+                if D[0, g] > np.float32(0.85):  # :857
+                    hm.add_node(li, int(I[0, g]), float(D[0, g]))
+            hm.digest()
+        last_l = l
+    return hm

@@ -244,3 +244,53 @@ def test_mobilenetv2_folding_and_cbw_roundtrip(tmp_path):
             y = y + inp
     assert y.shape == ref.shape
     assert torch.allclose(y, ref, atol=1e-4), float((y - ref).abs().max())
+
+
+# ------------------------------------------------------------------ candidate-logic variants
+def test_clique_accumulation_signed_locality_quirk():
+    """Cerebro.cpp:645: the duplicate test is ``(key - label) < 7`` WITHOUT abs over the ascending std::map: any retained
+    key smaller than the new label absorbs it; a label more than 7 below every key opens a new clique."""
+    r = {}
+    S.clique_accumulate(r, np.float32([0.95, 0.9, 0.86, 0.5, 0.4]), [606, 168, 172, 11, 12])
+    # 606 first; 168: 606-168=438 >= 7 -> new key; 172: smallest key 168: 168-172=-4 < 7 -> 168 absorbs; 0.5 < thresh: stop
+    assert r == {606: 1, 168: 2}
+    S.clique_accumulate(r, np.float32([0.99]), [900])  # 168 - 900 < 7: the smallest key absorbs even a far larger label
+    assert r == {606: 1, 168: 3}
+    S.clique_accumulate(r, np.float32([0.99]), [100])  # 168-100=68, 606-100=506: new clique
+    assert r == {606: 1, 168: 3, 100: 1}
+
+
+def test_faiss_clique_stream_finds_planted_revisit():
+    n, d = 260, 256
+    desc = synth.unit_rows(n, d, seed=21)
+    for i in range(12):
+        desc[220 + i] = synth.planted_queries(desc, [30 + i], seed=70 + i, score=0.95)[0]
+    arrivals = list(range(2, n + 1, 2))
+    found = S.faiss_clique_stream(desc, arrivals)
+    assert found, "no clique candidates"
+    assert all(sc == 0.9 for *_, sc in found)
+    assert all(28 <= b <= 45 for _, b, _ in found) and all(a >= 219 for a, _, _ in found)
+    # rand() returning 99 drops every candidate of a multi-clique reset, single-clique resets are always kept
+    kept = S.faiss_clique_stream(desc, arrivals, rand=lambda: 99)
+    assert len(kept) <= len(found)
+
+
+def test_hypothesis_manager_ttl_and_chaining():
+    hm = S.HypothesisManager()
+    hm.add_node(500, 100, 0.9)
+    assert len(hm.active_hyp) == 1 and hm.active_hyp[0].time_to_live == 20
+    hm.add_node(503, 104, 0.91)  # within 7 of the newest node on both ends -> same hypothesis, ttl + 1
+    assert len(hm.active_hyp) == 1 and hm.active_hyp[0].time_to_live == 21 and len(hm.active_hyp[0].nodes) == 2
+    hm.add_node(503, 300, 0.9)  # b too far -> new hypothesis
+    assert len(hm.active_hyp) == 2
+    hm.digest()
+    assert [h.time_to_live for h in hm.active_hyp] == [17, 16]
+    for _ in range(10):
+        hm.digest()
+    assert [h.time_to_live for h in hm.active_hyp] == [0, 0] and not hm.active_hyp[0].is_hypothesis_active()
+    hm.add_node(505, 106, 0.9)  # an expired hypothesis is never removed and still absorbs matching nodes
+    assert len(hm.active_hyp) == 2 and hm.active_hyp[0].time_to_live == 1
+    h = S.Hypothesis(0, 0, 1.0)
+    h.time_to_live = 100
+    h.increment_ttl()  # > 100 after the first increment -> a second one (HypothesisManager.h:115-117)
+    assert h.time_to_live == 102

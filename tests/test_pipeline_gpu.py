@@ -106,3 +106,55 @@ def test_descriptor_row_stride(native_lib, cuda_device):
     _lib.check(_lib.load().cb_descriptor_compute(nd._h, 2, _lib.ptr(padded), 160, _lib.ptr(out)))
     assert np.array_equal(out, ref)
     nd.close()
+
+
+def test_clique_and_multihypothesis_rules_match_oracle(native_lib, cuda_device):
+    """faiss_clique_loopcandidate_generator / faiss_multihypothesis_tracking (Cerebro.cpp:506-885) on the device index,
+    one batched top-5 search per wake-up, against the oracle's one-query-at-a-time replay."""
+    from cerebro_b200.loop_detector import Cerebro
+    from oracle import search as S
+
+    class FakeDesc:
+        dim = 256
+
+    n = 300
+    desc = synth.unit_rows(n, 256, seed=21)
+    for i in range(14):
+        desc[230 + i] = synth.planted_queries(desc, [30 + i], seed=70 + i, score=0.95)[0]
+    for i in range(6):
+        desc[270 + i] = synth.planted_queries(desc, [100 + i], seed=90 + i, score=0.93)[0]
+    arrivals = [2, 5, 6, 9] + list(range(12, n + 1, 3))
+    stamps = [1000 + 7 * i for i in range(n)]
+    state = {"x": 12345}
+
+    def lcg():  # deterministic stand-in for rand(), same sequence for product and oracle
+        state["x"] = (1103515245 * state["x"] + 12345) & 0x7FFFFFFF
+        return state["x"]
+
+    expect = S.faiss_clique_stream(desc, arrivals, rand=lcg)
+    assert len(expect) >= 3
+    state["x"] = 12345
+    c = Cerebro(FakeDesc(), capacity=n)
+    got, fed = [], 0
+    for l in arrivals:
+        c.index.add(desc[fed:l])
+        c._whole.extend(stamps[fed:l])
+        fed = l
+        got += c.faiss_clique_step(rand=lcg)
+    assert [(a, b, s) for a, b, s in got] == [(stamps[a], stamps[b], s) for a, b, s in expect]
+    assert c.foundLoops_count() == len(expect)
+
+    hm_o = S.faiss_multihypothesis_stream(desc, arrivals)
+    c2 = Cerebro(FakeDesc(), capacity=n)
+    fed = 0
+    for l in arrivals:
+        c2.index.add(desc[fed:l])
+        c2._whole.extend(stamps[fed:l])
+        fed = l
+        c2.faiss_multihypothesis_step()
+    hm = c2.hyp_manager
+    assert len(hm.active_hyp) == len(hm_o.active_hyp) >= 2
+    for h, ho in zip(hm.active_hyp, hm_o.active_hyp):
+        assert h.get_ttl() == ho.time_to_live
+        assert [(a, b) for a, b, _ in h.list_of_nodes_in_this_hypothesis] == [(a, b) for a, b, _ in ho.nodes]
+        assert np.allclose([s for *_, s in h.list_of_nodes_in_this_hypothesis], [s for *_, s in ho.nodes], atol=1e-6)
