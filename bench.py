@@ -22,6 +22,12 @@ import subprocess
 import sys
 import time
 
+if "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is ONE process that may use every host core,
+    # so lift the cap before numpy / torch load their BLAS and OpenMP runtimes (and again at run time, below)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -71,6 +77,12 @@ def cpu_pipeline_setup(raw, seed=0):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(min(cores, 32))  # batch-1 convolutions do not scale past a few dozen threads
+    try:  # numpy's BLAS (the fp32 search GEMV) may have been capped by an inherited OMP_NUM_THREADS
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     g = torch.Generator().manual_seed(seed)
     db = torch.randn((DB_ROWS, DIM), generator=g, dtype=torch.float32)
     db /= db.norm(dim=1, keepdim=True)

@@ -109,6 +109,11 @@ _SIGNATURES = {
     ),
     "cb_index_get_rows": (C.c_int, [_vp, _i64, _i64, _vp]),
     "cb_index_device_rows": (_vp, [_vp]),
+    "cb_frontend_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int]),
+    "cb_frontend_destroy": (C.c_int, [_vp]),
+    "cb_frontend_match_gms": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "cb_frontend_last_match_ms": (C.c_float, [_vp]),
+    "cb_frontend_collect": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cb_descriptor_create": (C.c_int, [C.POINTER(_vp), C.POINTER(NetvladWeights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "cb_descriptor_create_v2": (C.c_int, [C.POINTER(_vp), C.POINTER(NetvladV2Weights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "cb_descriptor_destroy": (C.c_int, [_vp]),

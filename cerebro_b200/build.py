@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_native")
 LIB = os.path.join(OUT_DIR, "libcerebro_b200.so")
 HARNESS = os.path.join(OUT_DIR, "cerebro_harness")
-SOURCES = ["capi.cu", "search.cu", "pnp.cu", "netvlad.cu"]
+SOURCES = ["capi.cu", "search.cu", "pnp.cu", "netvlad.cu", "frontend.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -1,0 +1,516 @@
+// Correspondence front end of the geometric verifier (sm_100a): ORB descriptors + keypoints + depth images of a loop
+// candidate's two frames  ->  brute-force Hamming matches  ->  GMS inlier mask  ->  3D-2D / 3D-3D sets for the pose solvers.
+//
+// Replaces (reference), in StaticPointFeatureMatching (src/utils/PointFeatureMatching.cpp):
+//   cv::BFMatcher(cv::NORM_HAMMING).match(d1, d2)                              :40-43
+//   gms_matcher(kp1, size1, kp2, size2, matches).GetInlierMask(mask, false, false)  :50-52
+//        (src/utils/GMSMatcher/gms_matcher.h:51-243, gms_matcher.cpp:5-181)
+//   make_3d_2d_collection__using__pfmatches_and_disparity                       :96-153
+//   make_3d_3d_collection__using__pfmatches_and_disparity                       :158-196
+// ORB detection and the stereo block matcher stay OpenCV's on the host.
+//
+// Kernels (integer / byte work; nothing here is a GEMM)
+//   hamming_match_kernel : thread = one query descriptor (8 x u32 in registers); the CTA stages 256 train descriptors at a
+//                          time in shared memory and every thread scans them with broadcast 128-bit loads, xor + popc.
+//                          The train set is split over gridDim.y; partial minima meet in a packed 64-bit atomicMin
+//                          (distance << 32 | train index), which also reproduces OpenCV's first-minimum tie rule.
+//   gms_kernel           : one CTA per image pair.  The 400 x 400 motion-statistics matrix of the reference is never
+//                          formed: matches are bucketed by left grid cell with a shared-memory counting sort, a warp per
+//                          cell finds the most frequent right cell (first maximum) and the 3 x 3 neighbourhood support
+//                          by scanning the (short) buckets; four shifted grids, integer counts, fp64 threshold
+//                          6 * sqrt(mean points per cell) exactly as gms_matcher.cpp:139-146.
+//   collect_kernel       : one CTA per pair: stable compaction of the GMS inliers (match order), K^-1 normalisation,
+//                          (int)-truncated depth-image lookup, 0.1 m <= z <= 25 m gate.
+#include "common.cuh"
+
+#include <stdlib.h>
+
+namespace {
+
+using cb::FULL;
+
+constexpr int kDescWords = 8;       // 256-bit ORB descriptor
+constexpr int kMatchThreads = 128;  // queries per CTA
+constexpr int kTrainTile = 256;     // train descriptors staged per step
+constexpr int kTrainChunk = 1024;   // train descriptors per gridDim.y slice
+constexpr int kGrid = 20;           // gms_matcher.h:63
+constexpr int kCells = kGrid * kGrid;
+constexpr int kGmsThreads = 256;
+constexpr int kGmsWarps = kGmsThreads / 32;
+
+__global__ void __launch_bounds__(kMatchThreads)
+hamming_match_kernel(const uint32_t* __restrict__ d1, const uint32_t* __restrict__ d2, const int* __restrict__ off1,
+                     const int* __restrict__ off2, unsigned long long* __restrict__ best) {
+  __shared__ uint4 tile[kTrainTile * 2];
+  const int pair = blockIdx.z;
+  const int q0 = off1[pair], n1 = off1[pair + 1] - q0;
+  const int t0 = off2[pair], n2 = off2[pair + 1] - t0;
+  const int qi = blockIdx.x * kMatchThreads + threadIdx.x;
+  const int c0 = blockIdx.y * kTrainChunk;
+  if (blockIdx.x * kMatchThreads >= n1 || c0 >= n2) return;  // CTA-uniform
+  const int c1 = min(c0 + kTrainChunk, n2);
+  uint32_t q[kDescWords];
+  const bool active = qi < n1;
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(d1 + (size_t)(q0 + (active ? qi : 0)) * kDescWords);
+    const uint4 a = qp[0], b = qp[1];
+    q[0] = a.x, q[1] = a.y, q[2] = a.z, q[3] = a.w, q[4] = b.x, q[5] = b.y, q[6] = b.z, q[7] = b.w;
+  }
+  unsigned best_d = 0xffffffffu, best_i = 0;
+  for (int base = c0; base < c1; base += kTrainTile) {
+    const int nt = min(kTrainTile, c1 - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt * 2; i += kMatchThreads)
+      tile[i] = reinterpret_cast<const uint4*>(d2 + (size_t)(t0 + base) * kDescWords)[i];
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < nt; ++j) {
+      const uint4 a = tile[2 * j], b = tile[2 * j + 1];  // broadcast loads
+      const unsigned d = __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
+                         __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+      if (d < best_d) {  // strict: the first minimum wins (OpenCV batchDistance)
+        best_d = d;
+        best_i = (unsigned)(base + j);
+      }
+    }
+  }
+  if (active && best_d != 0xffffffffu)
+    atomicMin(best + q0 + qi, ((unsigned long long)best_d << 32) | (unsigned long long)best_i);
+}
+
+__global__ void unpack_matches_kernel(const unsigned long long* __restrict__ best, int n, int* __restrict__ train_idx,
+                                      int* __restrict__ dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = best[i];
+  const bool none = k == ~0ull;  // a pair without train descriptors
+  train_idx[i] = none ? -1 : (int)(k & 0xffffffffu);
+  dist[i] = none ? -1 : (int)(k >> 32);
+}
+
+// GetGridIndexLeft, gms_matcher.h:147-189.  px, py: normalised float32 coordinates; float * int is a float32 product, the
+// + 0.5 is a double addition.
+__device__ __forceinline__ int grid_index_left(float px, float py, int type) {
+  const float fx = __fmul_rn(px, (float)kGrid), fy = __fmul_rn(py, (float)kGrid);
+  int x, y;
+  if (type == 1) {
+    x = (int)floorf(fx), y = (int)floorf(fy);
+    if (y >= kGrid || x >= kGrid) return -1;
+  } else if (type == 2) {
+    x = (int)floor((double)fx + 0.5), y = (int)floorf(fy);
+    if (x >= kGrid || x < 1) return -1;
+  } else if (type == 3) {
+    x = (int)floorf(fx), y = (int)floor((double)fy + 0.5);
+    if (y >= kGrid || y < 1) return -1;
+  } else {
+    x = (int)floor((double)fx + 0.5), y = (int)floor((double)fy + 0.5);
+    if (y >= kGrid || y < 1 || x >= kGrid || x < 1) return -1;
+  }
+  return x + y * kGrid;
+}
+
+// neighbour k (0..8, row-major 3x3 around the cell) of `cell`, -1 outside the grid: GetNB9, gms_matcher.h:199-220
+__device__ __forceinline__ int nb9(int cell, int k) {
+  const int x = cell % kGrid + (k % 3 - 1), y = cell / kGrid + (k / 3 - 1);
+  return (x < 0 || x >= kGrid || y < 0 || y >= kGrid) ? -1 : x + y * kGrid;
+}
+
+// one CTA per pair.  Shared memory: rg[nm] u16 | sorted[nm] u16 | lgm[nm] i16 | count[400] | start[401] | cursor[400] | pairc[400]
+__global__ void __launch_bounds__(kGmsThreads)
+gms_kernel(const float* __restrict__ kp1, const float* __restrict__ kp2, const int* __restrict__ off1, const int* __restrict__ off2,
+           const int* __restrict__ train_idx, int w1, int h1, int w2, int h2, int max_nm, unsigned char* __restrict__ mask,
+           int* __restrict__ n_inliers) {
+  extern __shared__ unsigned char gsm[];
+  unsigned short* rg = reinterpret_cast<unsigned short*>(gsm);
+  unsigned short* sorted = rg + max_nm;
+  short* lgm = reinterpret_cast<short*>(sorted + max_nm);
+  int* count = reinterpret_cast<int*>(lgm + max_nm + (max_nm & 1));
+  int* start = count + kCells;
+  int* cursor = start + kCells + 1;
+  int* pairc = cursor + kCells;
+  __shared__ int s_total;
+  const int pair = blockIdx.x;
+  const int q0 = off1[pair], nm = off1[pair + 1] - q0;  // one match per query descriptor
+  const int t0 = off2[pair];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr unsigned short kBad = 0xffffu;
+
+  // right grid cell of every match (GetGridIndexRight, gms_matcher.h:191-196; assigned once, gms_matcher.cpp:86-88);
+  // scale 0: the right grid is 20 x 20 as well (SetScale(0), gms_matcher.cpp:11)
+  for (int i = tid; i < nm; i += kGmsThreads) {
+    const int t = train_idx[q0 + i];
+    unsigned short r = kBad;
+    if (t >= 0) {
+      const float px = __fdiv_rn(kp2[2 * (size_t)(t0 + t)], (float)w2), py = __fdiv_rn(kp2[2 * (size_t)(t0 + t) + 1], (float)h2);
+      const int x = (int)floorf(__fmul_rn(px, (float)kGrid)), y = (int)floorf(__fmul_rn(py, (float)kGrid));
+      const int g = x + y * kGrid;
+      // the reference indexes mMotionStatistics with g unchecked (out of bounds for a point on the right / bottom border);
+      // such matches are left out here
+      if (g >= 0 && g < kCells && x >= 0 && x < kGrid) r = (unsigned short)g;
+    }
+    rg[i] = r;
+    mask[q0 + i] = 0;
+  }
+  for (int type = 1; type <= 4; ++type) {
+    for (int i = tid; i < kCells; i += kGmsThreads) count[i] = 0, cursor[i] = 0;
+    __syncthreads();
+    // AssignMatchPairs, gms_matcher.cpp:75-100
+    for (int i = tid; i < nm; i += kGmsThreads) {
+      const float px = __fdiv_rn(kp1[2 * (size_t)(q0 + i)], (float)w1), py = __fdiv_rn(kp1[2 * (size_t)(q0 + i) + 1], (float)h1);
+      const int lg = grid_index_left(px, py, type);
+      lgm[i] = (short)lg;
+      if (lg >= 0 && rg[i] != kBad) atomicAdd(&count[lg], 1);
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of 400 counts
+      int carry = 0;
+      for (int b = 0; b < kCells; b += 32) {
+        const int v = (b + lane < kCells) ? count[b + lane] : 0;
+        int s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(FULL, s, o);
+          if (lane >= o) s += u;
+        }
+        if (b + lane < kCells) start[b + lane] = carry + s - v;
+        carry += __shfl_sync(FULL, s, 31);
+      }
+      if (lane == 0) start[kCells] = carry;
+    }
+    __syncthreads();
+    for (int i = tid; i < nm; i += kGmsThreads) {
+      const int lg = lgm[i];
+      if (lg >= 0 && rg[i] != kBad) sorted[start[lg] + atomicAdd(&cursor[lg], 1)] = rg[i];
+    }
+    __syncthreads();
+    // VerifyCellPairs, gms_matcher.cpp:102-149: warp per left cell
+    for (int cell = warp; cell < kCells; cell += kGmsWarps) {
+      const int b0 = start[cell], m = count[cell];
+      int result = -1;
+      if (m > 0) {
+        // most frequent right cell, smallest index among equals (strict > scanning upwards, :113-121)
+        unsigned key = 0;
+        for (int e = lane; e < m; e += 32) {
+          const unsigned short v = sorted[b0 + e];
+          unsigned c = 0;
+          for (int f = 0; f < m; ++f) c += (sorted[b0 + f] == v);
+          const unsigned k = (c << 16) | (0xffffu - v);
+          key = max(key, k);
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) key = max(key, __shfl_xor_sync(FULL, key, o));
+        const int j = (int)(0xffffu - (key & 0xffffu));
+        // neighbourhood support (rotation pattern 1 = identity), :128-137
+        int score = 0, tsum = 0, numpair = 0;
+        for (int k = 0; k < 9; ++k) {
+          const int ll = nb9(cell, k), rr = nb9(j, k);
+          if (ll == -1 || rr == -1) continue;
+          const int lb = start[ll], lm = count[ll];
+          int c = 0;
+          for (int e = lane; e < lm; e += 32) c += (sorted[lb + e] == (unsigned short)rr);
+          score += c;
+          tsum += lm;
+          ++numpair;
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) score += __shfl_xor_sync(FULL, score, o);
+        const double thresh = 6.0 * sqrt((double)tsum / (double)numpair);  // THRESH_FACTOR, :139
+        result = ((double)score < thresh) ? -2 : j;
+      }
+      if (lane == 0) pairc[cell] = result;
+    }
+    __syncthreads();
+    for (int i = tid; i < nm; i += kGmsThreads) {  // gms_matcher.cpp:169-177
+      const int lg = lgm[i];
+      if (lg >= 0 && rg[i] != kBad && pairc[lg] == (int)rg[i]) mask[q0 + i] = 1;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = tid; i < nm; i += kGmsThreads) c += mask[q0 + i];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+  if (lane == 0) atomicAdd(&s_total, c);
+  __syncthreads();
+  if (tid == 0) n_inliers[pair] = s_total;
+}
+
+// One CTA per pair.  Walks the matches in order, 256 at a time, and appends the kept ones (ballot + prefix) so the output
+// order is the reference's (match order = ascending query index).
+//   mode 0: 3D-2D  (world point of frame a at (int)uv, normalised uv of a and uv_d of b)   PointFeatureMatching.cpp:96-153
+//   mode 1: 3D-3D  (points of both frames, both depths gated)                               PointFeatureMatching.cpp:158-196
+__global__ void __launch_bounds__(256)
+collect_kernel(const float* __restrict__ kp1, const float* __restrict__ kp2, const int* __restrict__ off1, const int* __restrict__ off2,
+               const int* __restrict__ train_idx, const unsigned char* __restrict__ mask, const float* __restrict__ img_a,
+               const float* __restrict__ img_b, int H, int W, const double* __restrict__ Kinv, int mode, double* __restrict__ out_X,
+               double* __restrict__ out_uv, double* __restrict__ out_uvd, double* __restrict__ out_Y, int* __restrict__ out_count) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int pair = blockIdx.x;
+  const int q0 = off1[pair], nm = off1[pair + 1] - q0, t0 = off2[pair];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* ia = img_a + (size_t)pair * H * W * 3;
+  const float* ib = img_b ? img_b + (size_t)pair * H * W * 3 : nullptr;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < nm; i0 += 256) {
+    const int i = i0 + tid;
+    bool keep = false;
+    float u = 0.f, v = 0.f, ud = 0.f, vd = 0.f;
+    float3 pa = make_float3(0.f, 0.f, 0.f), pb = pa;
+    if (i < nm && mask[q0 + i]) {
+      const int t = train_idx[q0 + i];
+      u = kp1[2 * (size_t)(q0 + i)], v = kp1[2 * (size_t)(q0 + i) + 1];
+      ud = kp2[2 * (size_t)(t0 + t)], vd = kp2[2 * (size_t)(t0 + t) + 1];
+      const int xa = (int)u, ya = (int)v;  // (int)uv(1,k), (int)uv(0,k): truncation, :124
+      if (xa >= 0 && xa < W && ya >= 0 && ya < H) {
+        const float* p = ia + ((size_t)ya * W + xa) * 3;
+        pa = make_float3(p[0], p[1], p[2]);
+        keep = !(pa.z < 0.1f || pa.z > 25.f);
+      }
+      if (mode == 1 && keep) {
+        const int xb = (int)ud, yb = (int)vd;
+        keep = false;
+        if (ib && xb >= 0 && xb < W && yb >= 0 && yb < H) {
+          const float* p = ib + ((size_t)yb * W + xb) * 3;
+          pb = make_float3(p[0], p[1], p[2]);
+          keep = !(pb.z < 0.1f || pb.z > 25.f);
+        }
+      }
+    }
+    const unsigned bal = __ballot_sync(FULL, keep);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const int pos = before + __popc(bal & ((1u << lane) - 1u));
+    if (keep) {
+      const size_t o = (size_t)q0 + pos;  // outputs are laid out per pair at the pair's query offset
+      out_X[3 * o] = (double)pa.x, out_X[3 * o + 1] = (double)pa.y, out_X[3 * o + 2] = (double)pa.z;
+      if (mode == 0) {
+        // K^-1 [u v 1]^T (stereogeom->get_K().inverse() * uv, :117-118): rows 0 and 1
+        out_uv[2 * o] = Kinv[0] * (double)u + Kinv[1] * (double)v + Kinv[2];
+        out_uv[2 * o + 1] = Kinv[3] * (double)u + Kinv[4] * (double)v + Kinv[5];
+        out_uvd[2 * o] = Kinv[0] * (double)ud + Kinv[1] * (double)vd + Kinv[2];
+        out_uvd[2 * o + 1] = Kinv[3] * (double)ud + Kinv[4] * (double)vd + Kinv[5];
+      } else {
+        out_Y[3 * o] = (double)pb.x, out_Y[3 * o + 1] = (double)pb.y, out_Y[3 * o + 2] = (double)pb.z;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += s_warp[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) out_count[pair] = s_base;
+}
+
+int grow_dev(void** p, size_t* cur, size_t need) {
+  if (*cur >= need) return CB_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cur = 0;
+  cudaError_t e = cudaMalloc(p, need);
+  if (e != cudaSuccess) return cb::fail(CB_ENOMEM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+  *cur = need;
+  return CB_OK;
+}
+
+}  // namespace
+
+struct cb_frontend {
+  int device = 0, max_pairs = 0, max_features = 0;
+  cudaStream_t stream = nullptr;
+  // device copies of one batch (sized for max_pairs * max_features at create time)
+  uint32_t* d1 = nullptr;
+  uint32_t* d2 = nullptr;
+  float* kp1 = nullptr;
+  float* kp2 = nullptr;
+  int* off1 = nullptr;
+  int* off2 = nullptr;
+  unsigned long long* best = nullptr;
+  int* train_idx = nullptr;
+  int* dist = nullptr;
+  unsigned char* mask = nullptr;
+  int* n_inl = nullptr;
+  double* X = nullptr;
+  double* uv = nullptr;
+  double* uvd = nullptr;
+  double* Y = nullptr;
+  double* Kinv = nullptr;
+  int* count = nullptr;
+  float* img_a = nullptr;
+  float* img_b = nullptr;
+  size_t img_bytes_a = 0, img_bytes_b = 0;
+  // shape of the batch currently resident (set by cb_frontend_match_gms, used by cb_frontend_collect)
+  int n_pairs = 0, total1 = 0, total2 = 0;
+  bool have_matches = false;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  float last_match_ms = 0.f;
+};
+
+extern "C" {
+
+int cb_frontend_create(cb_frontend** out, int max_pairs, int max_features, int device) {
+  if (!out) return cb::fail(CB_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (max_pairs < 1 || max_features < 1 || max_features > 16384)
+    return cb::fail(CB_EINVAL, "max_pairs must be >= 1 and max_features in [1, 16384]");
+  int rc = cb::select_device(device, nullptr);
+  if (rc) return rc;
+  cb::DeviceGuard g(device);
+  cb_frontend* f = new cb_frontend();
+  f->device = device;
+  f->max_pairs = max_pairs;
+  f->max_features = max_features;
+  const size_t tot = (size_t)max_pairs * max_features;
+  cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+  auto A = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+  };
+  A((void**)&f->d1, tot * 32);
+  A((void**)&f->d2, tot * 32);
+  A((void**)&f->kp1, tot * 8);
+  A((void**)&f->kp2, tot * 8);
+  A((void**)&f->off1, (size_t)(max_pairs + 1) * 4);
+  A((void**)&f->off2, (size_t)(max_pairs + 1) * 4);
+  A((void**)&f->best, tot * 8);
+  A((void**)&f->train_idx, tot * 4);
+  A((void**)&f->dist, tot * 4);
+  A((void**)&f->mask, tot);
+  A((void**)&f->n_inl, (size_t)max_pairs * 4);
+  A((void**)&f->X, tot * 24);
+  A((void**)&f->uv, tot * 16);
+  A((void**)&f->uvd, tot * 16);
+  A((void**)&f->Y, tot * 24);
+  A((void**)&f->Kinv, 9 * 8);
+  A((void**)&f->count, (size_t)max_pairs * 4);
+  if (e == cudaSuccess) e = cudaEventCreate(&f->ev[0]);
+  if (e == cudaSuccess) e = cudaEventCreate(&f->ev[1]);
+  if (e != cudaSuccess) {
+    cb_frontend_destroy(f);
+    return cb::fail(CB_ENOMEM, "front-end allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = f;
+  return CB_OK;
+}
+
+int cb_frontend_destroy(cb_frontend* f) {
+  if (!f) return CB_OK;
+  cb::DeviceGuard g(f->device);
+  if (f->stream) cudaStreamSynchronize(f->stream);
+  void* ps[] = {f->d1, f->d2, f->kp1, f->kp2, f->off1, f->off2, f->best, f->train_idx, f->dist, f->mask, f->n_inl,
+                f->X,  f->uv, f->uvd, f->Y,   f->Kinv, f->count, f->img_a, f->img_b};
+  for (void* p : ps)
+    if (p) cudaFree(p);
+  for (cudaEvent_t ev : f->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (f->stream) cudaStreamDestroy(f->stream);
+  delete f;
+  return CB_OK;
+}
+
+int cb_frontend_match_gms(cb_frontend* f, int n_pairs, const int32_t* off1, const int32_t* off2, const uint8_t* desc1,
+                          const uint8_t* desc2, const float* kp1, const float* kp2, int width1, int height1, int width2,
+                          int height2, int32_t* train_idx, int32_t* distance, uint8_t* inlier_mask, int32_t* n_inliers) {
+  if (!f || !off1 || !off2 || !desc1 || !desc2 || !kp1 || !kp2 || !train_idx || !inlier_mask || !n_inliers)
+    return cb::fail(CB_EINVAL, "NULL argument to cb_frontend_match_gms");
+  if (n_pairs < 1 || n_pairs > f->max_pairs) return cb::fail(CB_EINVAL, "n_pairs %d outside [1,%d]", n_pairs, f->max_pairs);
+  if (width1 < 1 || height1 < 1 || width2 < 1 || height2 < 1) return cb::fail(CB_EINVAL, "bad image size");
+  if (off1[0] != 0 || off2[0] != 0) return cb::fail(CB_EINVAL, "offsets must start at 0");
+  int max1 = 0, max2 = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    const int a = off1[p + 1] - off1[p], b = off2[p + 1] - off2[p];
+    if (a < 0 || b < 0 || a > f->max_features || b > f->max_features)
+      return cb::fail(CB_EINVAL, "pair %d has %d / %d features, outside [0,%d]", p, a, b, f->max_features);
+    max1 = a > max1 ? a : max1;
+    max2 = b > max2 ? b : max2;
+  }
+  const int tot1 = off1[n_pairs], tot2 = off2[n_pairs];
+  cb::DeviceGuard g(f->device);
+  cudaStream_t st = f->stream;
+  f->have_matches = false;
+  CB_CUDA(cudaMemcpyAsync(f->off1, off1, (size_t)(n_pairs + 1) * 4, cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(f->off2, off2, (size_t)(n_pairs + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (tot1) CB_CUDA(cudaMemcpyAsync(f->d1, desc1, (size_t)tot1 * 32, cudaMemcpyHostToDevice, st));
+  if (tot2) CB_CUDA(cudaMemcpyAsync(f->d2, desc2, (size_t)tot2 * 32, cudaMemcpyHostToDevice, st));
+  if (tot1) CB_CUDA(cudaMemcpyAsync(f->kp1, kp1, (size_t)tot1 * 8, cudaMemcpyHostToDevice, st));
+  if (tot2) CB_CUDA(cudaMemcpyAsync(f->kp2, kp2, (size_t)tot2 * 8, cudaMemcpyHostToDevice, st));
+  if (tot1) {
+    CB_CUDA(cudaEventRecord(f->ev[0], st));
+    CB_CUDA(cudaMemsetAsync(f->best, 0xff, (size_t)tot1 * 8, st));
+    if (max2 > 0) {
+      dim3 grid((unsigned)((max1 + kMatchThreads - 1) / kMatchThreads), (unsigned)((max2 + kTrainChunk - 1) / kTrainChunk),
+                (unsigned)n_pairs);
+      hamming_match_kernel<<<grid, kMatchThreads, 0, st>>>(f->d1, f->d2, f->off1, f->off2, f->best);
+      CB_LAUNCH_CHECK();
+    }
+    unpack_matches_kernel<<<(unsigned)((tot1 + 255) / 256), 256, 0, st>>>(f->best, tot1, f->train_idx, f->dist);
+    CB_LAUNCH_CHECK();
+  }
+  {
+    const size_t smem = (size_t)max1 * 6 + 8 + (size_t)(4 * kCells + 1) * 4;
+    CB_CUDA(cudaFuncSetAttribute(gms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gms_kernel<<<n_pairs, kGmsThreads, smem, st>>>(f->kp1, f->kp2, f->off1, f->off2, f->train_idx, width1, height1, width2, height2,
+                                                   max1, f->mask, f->n_inl);
+    CB_LAUNCH_CHECK();
+  }
+  if (tot1) {
+    CB_CUDA(cudaEventRecord(f->ev[1], st));
+    CB_CUDA(cudaMemcpyAsync(train_idx, f->train_idx, (size_t)tot1 * 4, cudaMemcpyDeviceToHost, st));
+    if (distance) CB_CUDA(cudaMemcpyAsync(distance, f->dist, (size_t)tot1 * 4, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaMemcpyAsync(inlier_mask, f->mask, (size_t)tot1, cudaMemcpyDeviceToHost, st));
+  }
+  CB_CUDA(cudaMemcpyAsync(n_inliers, f->n_inl, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  if (tot1) cudaEventElapsedTime(&f->last_match_ms, f->ev[0], f->ev[1]);
+  f->n_pairs = n_pairs;
+  f->total1 = tot1;
+  f->total2 = tot2;
+  f->have_matches = true;
+  return CB_OK;
+}
+
+float cb_frontend_last_match_ms(const cb_frontend* f) { return f ? f->last_match_ms : -1.f; }
+
+int cb_frontend_collect(cb_frontend* f, int mode, const float* img3d_a, const float* img3d_b, int rows, int cols,
+                        const double* K_inverse, int32_t* counts, double* X, double* uv, double* uv_d, double* Y) {
+  if (!f || !img3d_a || !counts || !X) return cb::fail(CB_EINVAL, "NULL argument to cb_frontend_collect");
+  if (!f->have_matches) return cb::fail(CB_EINVAL, "cb_frontend_collect needs a preceding cb_frontend_match_gms on this handle");
+  if (mode != 0 && mode != 1) return cb::fail(CB_EINVAL, "mode must be 0 (3D-2D) or 1 (3D-3D)");
+  if (mode == 0 && (!K_inverse || !uv || !uv_d)) return cb::fail(CB_EINVAL, "3D-2D mode needs K_inverse, uv and uv_d");
+  if (mode == 1 && (!img3d_b || !Y)) return cb::fail(CB_EINVAL, "3D-3D mode needs img3d_b and Y");
+  if (rows < 1 || cols < 1) return cb::fail(CB_EINVAL, "bad depth-image size");
+  cb::DeviceGuard g(f->device);
+  cudaStream_t st = f->stream;
+  const size_t img_bytes = (size_t)f->n_pairs * rows * cols * 3 * sizeof(float);
+  int rc = grow_dev((void**)&f->img_a, &f->img_bytes_a, img_bytes);
+  if (!rc && img3d_b) rc = grow_dev((void**)&f->img_b, &f->img_bytes_b, img_bytes);
+  if (rc) return rc;
+  CB_CUDA(cudaMemcpyAsync(f->img_a, img3d_a, img_bytes, cudaMemcpyHostToDevice, st));
+  if (img3d_b) CB_CUDA(cudaMemcpyAsync(f->img_b, img3d_b, img_bytes, cudaMemcpyHostToDevice, st));
+  if (K_inverse) CB_CUDA(cudaMemcpyAsync(f->Kinv, K_inverse, 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+  collect_kernel<<<f->n_pairs, 256, 0, st>>>(f->kp1, f->kp2, f->off1, f->off2, f->train_idx, f->mask, f->img_a,
+                                             img3d_b ? f->img_b : nullptr, rows, cols, f->Kinv, mode, f->X, f->uv, f->uvd, f->Y, f->count);
+  CB_LAUNCH_CHECK();
+  const size_t n = (size_t)f->total1;
+  CB_CUDA(cudaMemcpyAsync(counts, f->count, (size_t)f->n_pairs * 4, cudaMemcpyDeviceToHost, st));
+  if (n) {
+    CB_CUDA(cudaMemcpyAsync(X, f->X, n * 24, cudaMemcpyDeviceToHost, st));
+    if (mode == 0) {
+      CB_CUDA(cudaMemcpyAsync(uv, f->uv, n * 16, cudaMemcpyDeviceToHost, st));
+      CB_CUDA(cudaMemcpyAsync(uv_d, f->uvd, n * 16, cudaMemcpyDeviceToHost, st));
+    } else {
+      CB_CUDA(cudaMemcpyAsync(Y, f->Y, n * 24, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CB_CUDA(cudaStreamSynchronize(st));
+  return CB_OK;
+}
+
+}  // extern "C"

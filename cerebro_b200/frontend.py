@@ -1,0 +1,160 @@
+"""Host-side mirror of the correspondence front end, ``StaticPointFeatureMatching``
+(src/utils/PointFeatureMatching.cpp), over ``cb_frontend_*``:
+
+  gms_point_feature_matches        :5-75    ORB (OpenCV, host) -> BFMatcher(NORM_HAMMING).match -> gms_matcher -> u, ud
+  make_3d_2d_collection__using__pfmatches_and_disparity   :96-153
+  make_3d_3d_collection__using__pfmatches_and_disparity   :158-196
+
+The matcher, the GMS filter and the set builders run on the device for a whole batch of loop candidates at once; ORB
+detection / description and the stereo block matcher remain OpenCV calls on the host -- the
+batch entry points therefore take keypoints + descriptors, and ``gms_point_feature_matches`` (images in, like the
+reference) is a convenience that runs cv2.ORB first when OpenCV's Python module is importable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+
+
+class FrontEnd:
+    def __init__(self, max_pairs: int = 16, max_features: int = 5000, device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        check(self._lib.cb_frontend_create(C.byref(self._h), max_pairs, max_features, device))
+        self.max_pairs, self.max_features = max_pairs, max_features
+        self._off1 = None
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.cb_frontend_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- BFMatcher(NORM_HAMMING).match + gms_matcher(...).GetInlierMask(mask, false, false), batched
+    def match_gms(self, kp1: Sequence[np.ndarray], desc1: Sequence[np.ndarray], kp2: Sequence[np.ndarray],
+                  desc2: Sequence[np.ndarray], size1: Tuple[int, int], size2: Tuple[int, int]):
+        """Per pair p: kp1[p] [n1,2] float32 KeyPoint.pt, desc1[p] [n1,32] uint8 (query = frame a), kp2 / desc2 (train =
+        frame b); size = (width, height).  Returns a list of dicts with ``train_idx``, ``distance``, ``inliers`` (bool mask),
+        ``n_inliers`` -- one match per query descriptor, in query order, exactly what ``matcher.match(d1, d2)`` returns."""
+        n = len(kp1)
+        assert n == len(desc1) == len(kp2) == len(desc2) and n >= 1
+        off1 = np.zeros(n + 1, dtype=np.int32)
+        off2 = np.zeros(n + 1, dtype=np.int32)
+        off1[1:] = np.cumsum([len(k) for k in kp1])
+        off2[1:] = np.cumsum([len(k) for k in kp2])
+        cat = lambda xs, dt, w: (np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=dt).reshape(-1, w) for x in xs]))
+                                 if sum(len(x) for x in xs) else np.zeros((0, w), dtype=dt))
+        K1, K2 = cat(kp1, np.float32, 2), cat(kp2, np.float32, 2)
+        D1, D2 = cat(desc1, np.uint8, 32), cat(desc2, np.uint8, 32)
+        assert K1.shape[0] == D1.shape[0] == off1[-1] and K2.shape[0] == D2.shape[0] == off2[-1]
+        tot = max(int(off1[-1]), 1)
+        tidx = np.full(tot, -1, dtype=np.int32)
+        dist = np.full(tot, -1, dtype=np.int32)
+        mask = np.zeros(tot, dtype=np.uint8)
+        ninl = np.zeros(n, dtype=np.int32)
+        # zero-length inputs still need a valid pointer
+        pad = np.zeros(32, dtype=np.uint8)
+        check(self._lib.cb_frontend_match_gms(self._h, n, ptr(off1), ptr(off2), ptr(D1 if D1.size else pad), ptr(D2 if D2.size else pad),
+                                              ptr(K1 if K1.size else pad), ptr(K2 if K2.size else pad), int(size1[0]), int(size1[1]),
+                                              int(size2[0]), int(size2[1]), ptr(tidx), ptr(dist), ptr(mask), ptr(ninl)))
+        self._off1, self._K1, self._K2, self._off2 = off1, K1, K2, off2
+        self._tidx, self._mask = tidx, mask
+        out = []
+        for p in range(n):
+            a, b = off1[p], off1[p + 1]
+            out.append(dict(train_idx=tidx[a:b].copy(), distance=dist[a:b].copy(), inliers=mask[a:b].astype(bool), n_inliers=int(ninl[p])))
+        return out
+
+    def last_match_ms(self) -> float:
+        return float(self._lib.cb_frontend_last_match_ms(self._h))
+
+    def matched_points(self, p: int):
+        """``MiscUtils::dmatch_2_eigen(kp1, kp2, matches_gms, u, ud, true)`` (PointFeatureMatching.cpp:71): the GMS inliers
+        of pair p as 3xN homogeneous float64 pixel coordinates (u of frame a, ud of frame b)."""
+        a, b = self._off1[p], self._off1[p + 1]
+        sel = np.nonzero(self._mask[a:b])[0]
+        u = self._K1[a:b][sel].astype(np.float64)
+        ud = self._K2[self._off2[p] : self._off2[p + 1]][self._tidx[a:b][sel]].astype(np.float64)
+        one = np.ones((1, sel.size))
+        return np.concatenate([u.T, one]), np.concatenate([ud.T, one])
+
+    # ---- set builders over the batch matched last
+    def make_3d_2d_collection(self, K: np.ndarray, img3d_a: np.ndarray):
+        """make_3d_2d_collection__using__pfmatches_and_disparity for every pair of the last ``match_gms`` batch.
+        img3d_a [n_pairs, H, W, 3] float32.  Returns per pair (feature_position_uv [m,2], feature_position_uv_d [m,2],
+        world_point [m,3])."""
+        return self._collect(0, K, img3d_a, None)
+
+    def make_3d_3d_collection(self, img3d_a: np.ndarray, img3d_b: np.ndarray):
+        """make_3d_3d_collection__using__pfmatches_and_disparity: per pair (uv_X [m,3], uvd_Y [m,3])."""
+        return self._collect(1, None, img3d_a, img3d_b)
+
+    def _collect(self, mode, K, img_a, img_b):
+        assert self._off1 is not None, "call match_gms first"
+        n = len(self._off1) - 1
+        img_a = np.ascontiguousarray(img_a, dtype=np.float32)
+        assert img_a.ndim == 4 and img_a.shape[0] == n and img_a.shape[3] == 3
+        rows, cols = img_a.shape[1], img_a.shape[2]
+        if img_b is not None:
+            img_b = np.ascontiguousarray(img_b, dtype=np.float32)
+            assert img_b.shape == img_a.shape
+        tot = max(int(self._off1[-1]), 1)
+        counts = np.zeros(n, dtype=np.int32)
+        X = np.zeros((tot, 3))
+        uv = np.zeros((tot, 2))
+        uvd = np.zeros((tot, 2))
+        Y = np.zeros((tot, 3))
+        Kinv = np.ascontiguousarray(np.linalg.inv(np.asarray(K, dtype=np.float64))) if K is not None else None
+        check(self._lib.cb_frontend_collect(self._h, mode, ptr(img_a), ptr(img_b), rows, cols, ptr(Kinv), ptr(counts), ptr(X), ptr(uv),
+                                            ptr(uvd), ptr(Y)))
+        out = []
+        for p in range(n):
+            a = int(self._off1[p])
+            m = int(counts[p])
+            if mode == 0:
+                out.append((uv[a : a + m].copy(), uvd[a : a + m].copy(), X[a : a + m].copy()))
+            else:
+                out.append((X[a : a + m].copy(), Y[a : a + m].copy()))
+        return out
+
+
+class StaticPointFeatureMatching:
+    """Name-for-name entry points of the reference class, single image pair, images in."""
+
+    _fe = None
+
+    @classmethod
+    def _frontend(cls, n_feat):
+        if cls._fe is None or cls._fe.max_features < n_feat:
+            cls._fe = FrontEnd(max_pairs=1, max_features=max(n_feat, 5000))
+        return cls._fe
+
+    @classmethod
+    def gms_point_feature_matches(cls, imleft_undistorted: np.ndarray, imright_undistorted: np.ndarray, n_orb_feat: int = 5000):
+        """PointFeatureMatching.cpp:5-75: returns (u, ud), 3xN homogeneous pixel coordinates of the GMS matches (empty
+        arrays when there is none).  ORB = cv2.ORB_create(n_orb_feat) with FAST threshold 0 (:17-18), on the host."""
+        import cv2  # the reference's own dependency; only this convenience wrapper needs it
+
+        orb = cv2.ORB_create(n_orb_feat)
+        orb.setFastThreshold(0)
+        k1, d1 = orb.detectAndCompute(imleft_undistorted, None)
+        k2, d2 = orb.detectAndCompute(imright_undistorted, None)
+        if d1 is None or d2 is None or len(k1) == 0 or len(k2) == 0:
+            return np.zeros((3, 0)), np.zeros((3, 0))
+        fe = cls._frontend(max(len(k1), len(k2)))
+        kp1 = np.array([k.pt for k in k1], dtype=np.float32)
+        kp2 = np.array([k.pt for k in k2], dtype=np.float32)
+        h1, w1 = imleft_undistorted.shape[:2]
+        h2, w2 = imright_undistorted.shape[:2]
+        fe.match_gms([kp1], [d1], [kp2], [d2], (w1, h1), (w2, h2))
+        return fe.matched_points(0)

@@ -266,6 +266,44 @@ CB_API int cb_pnp_icp_batch_device(cb_pnp* p, int n_cand, const int32_t* offsets
 CB_API int cb_pnp_dls_minimal(cb_pnp* p, int n_sets, int m, const double* X, const double* uv,
                        int32_t* n_solutions, double* R, double* t);
 
+/* ------------------------------------------------------------------------------------
+ * frontend: ORB descriptors + keypoints + depth images of a loop candidate's two frames ->
+ * Hamming matches -> GMS inliers -> the 3D-2D / 3D-3D sets the pose solvers take
+ * (StaticPointFeatureMatching, src/utils/PointFeatureMatching.cpp; ORB detection and the
+ * stereo block matcher stay OpenCV's on the host)
+ * ---------------------------------------------------------------------------------- */
+typedef struct cb_frontend cb_frontend;
+
+CB_API int cb_frontend_create(cb_frontend** out, int max_pairs, int max_features /* per image, <= 16384 */, int device);
+CB_API int cb_frontend_destroy(cb_frontend* f);
+
+/* cv::BFMatcher(cv::NORM_HAMMING).match(d1, d2) (PointFeatureMatching.cpp:40-43) followed by
+ * gms_matcher(kp1, size1, kp2, size2, matches).GetInlierMask(mask, false, false) (:50-52;
+ * src/utils/GMSMatcher/gms_matcher.cpp:5-181) for a batch of image pairs.
+ *   off1, off2 [n_pairs+1]: pair p owns query features [off1[p], off1[p+1]) and train features
+ *                           [off2[p], off2[p+1]) of the concatenated arrays
+ *   desc1, desc2 : [total][32] bytes, 256-bit ORB descriptors; kp1, kp2: [total][2] float KeyPoint.pt (x, y) in pixels
+ * One match per query descriptor, in query order (what match() returns):
+ *   train_idx [total1] index local to the pair's train set (first minimum wins; -1 if the pair has no train features),
+ *   distance [total1] Hamming distance (may be NULL), inlier_mask [total1] 0/1, n_inliers [n_pairs]. */
+CB_API int cb_frontend_match_gms(cb_frontend* f, int n_pairs, const int32_t* off1, const int32_t* off2,
+                          const uint8_t* desc1, const uint8_t* desc2, const float* kp1, const float* kp2,
+                          int width1, int height1, int width2, int height2, int32_t* train_idx,
+                          int32_t* distance, uint8_t* inlier_mask, int32_t* n_inliers);
+/* device time (ms) of the matching + GMS kernels of the last cb_frontend_match_gms call (CUDA events) */
+CB_API float cb_frontend_last_match_ms(const cb_frontend* f);
+
+/* The correspondence sets of the batch matched last on this handle, from its GMS inliers, in match order:
+ *   mode 0: make_3d_2d_collection__using__pfmatches_and_disparity (PointFeatureMatching.cpp:96-153):
+ *           X = 3-D point of frame a looked up at ((int)v, (int)u) in img3d_a, kept iff 0.1 <= z <= 25;
+ *           uv / uv_d = K^-1 [u v 1]^T of the feature in frame a / b (normalised image coordinates)
+ *   mode 1: make_3d_3d_collection__using__pfmatches_and_disparity (:158-196): X from img3d_a, Y from img3d_b, both gated
+ *   img3d_a, img3d_b: [n_pairs][rows][cols][3] float32 (the CV_32FC3 "3d image" of the stereo pair); K_inverse 3x3 row-major.
+ * Outputs are laid out per pair at the pair's query offset: pair p's kept entries are rows
+ * [off1[p], off1[p] + counts[p]) of X [total1][3], uv / uv_d [total1][2], Y [total1][3]. */
+CB_API int cb_frontend_collect(cb_frontend* f, int mode, const float* img3d_a, const float* img3d_b, int rows, int cols,
+                        const double* K_inverse, int32_t* counts, double* X, double* uv, double* uv_d, double* Y);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,164 @@
+"""Correspondence front end: brute-force Hamming matching, GMS filtering and the 3D-2D / 3D-3D
+set builders.  The oracle is pinned against the UNMODIFIED reference GMS matcher (oracle/_ref/libgms_ref.so, built from
+/root/reference by oracle/Makefile) where it is present, against fixtures that matcher produced (tests/golden/gms_golden.npz)
+everywhere, and against the installed OpenCV's BFMatcher; the CUDA path is then compared with the oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import gms
+from tests import golden_io
+
+
+def _synthetic_pair(rng, n1, n2, w, h, inlier_frac=0.6):
+    """Keypoints + 256-bit descriptors of two 'images': a fraction of the query points reappears in the second image
+    under a small affine motion with a few bits flipped; the rest are unrelated."""
+    kp1 = np.stack([rng.uniform(0, w - 1e-3, n1), rng.uniform(0, h - 1e-3, n1)], 1).astype(np.float32)
+    d1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+    kp2 = np.stack([rng.uniform(0, w - 1e-3, n2), rng.uniform(0, h - 1e-3, n2)], 1).astype(np.float32)
+    d2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    m = int(min(n1, n2) * inlier_frac)
+    src = rng.choice(n1, m, replace=False)
+    dst = rng.choice(n2, m, replace=False)
+    A = np.array([[0.98, 0.03], [-0.03, 0.98]])
+    p = kp1[src] @ A.T + np.array([7.0, -4.0]) + rng.normal(0, 0.7, (m, 2))
+    p[:, 0] = np.clip(p[:, 0], 0, w - 1e-3)
+    p[:, 1] = np.clip(p[:, 1], 0, h - 1e-3)
+    kp2[dst] = p.astype(np.float32)
+    flip = rng.integers(0, 256, (m, 32), dtype=np.uint8) & rng.integers(0, 256, (m, 32), dtype=np.uint8) & rng.integers(0, 256, (m, 32), dtype=np.uint8)
+    d2[dst] = d1[src] ^ flip  # ~12 % of the bits flipped
+    return kp1, d1, kp2, d2
+
+
+# ------------------------------------------------------------------ oracle pinning (CPU)
+@pytest.mark.parametrize("case", ["easy", "hard"])
+def test_oracle_matches_reference_fixtures(case):
+    g = golden_io.load("gms_golden.npz")
+    w, h = g[case + "_size"]
+    idx, dist = gms.bf_match_hamming(g[case + "_d1"], g[case + "_d2"])
+    assert np.array_equal(idx, g[case + "_train"]) and np.array_equal(dist, g[case + "_dist"])  # cv2.BFMatcher's answer
+    mask, n = gms.gms_inlier_mask(g[case + "_kp1"], (w, h), g[case + "_kp2"], (w, h), np.arange(idx.size), idx)
+    assert np.array_equal(mask, g[case + "_mask"]) and n == int(g[case + "_mask"].sum()) and n > 100  # the reference's answer
+
+
+@pytest.mark.skipif(not gms.reference_available(), reason="oracle/_ref/libgms_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("seed,n1,n2,w,h", [(1, 1500, 1400, 640, 480), (2, 300, 900, 752, 480), (3, 40, 40, 320, 240), (4, 2500, 2500, 640, 480)])
+def test_oracle_matches_compiled_reference(seed, n1, n2, w, h):
+    rng = np.random.default_rng(seed)
+    kp1, d1, kp2, d2 = _synthetic_pair(rng, n1, n2, w, h)
+    idx, _ = gms.bf_match_hamming(d1, d2)
+    q = np.arange(n1)
+    for ws, wr in ((False, False), (True, False), (False, True), (True, True)):
+        mr, nr = gms.gms_reference(kp1, (w, h), kp2, (w, h), q, idx, ws, wr)
+        mo, no = gms.gms_inlier_mask(kp1, (w, h), kp2, (w, h), q, idx, ws, wr)
+        assert nr == no and np.array_equal(mr, mo), (ws, wr, nr, no)
+
+
+def test_bf_oracle_matches_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    d1 = rng.integers(0, 256, (700, 32), dtype=np.uint8)
+    d2 = rng.integers(0, 256, (650, 32), dtype=np.uint8)
+    d2[10] = d2[400] = d1[3]  # an exact tie: the first train index must win
+    m = cv2.BFMatcher(cv2.NORM_HAMMING).match(d1, d2)
+    idx, dist = gms.bf_match_hamming(d1, d2)
+    assert np.array_equal(idx, [x.trainIdx for x in m]) and np.array_equal(dist, [int(x.distance) for x in m])
+    assert idx[3] == 10 and dist[3] == 0
+
+
+def test_collection_builders_gate_depth_and_truncate():
+    K = np.array([[400.0, 0, 320.0], [0, 410.0, 240.0], [0, 0, 1]])
+    img = np.zeros((480, 640, 3), dtype=np.float32)
+    img[..., 2] = 5.0
+    img[100, 200] = (1.0, 2.0, 0.05)  # too close
+    img[101, 200] = (1.0, 2.0, 30.0)  # too far
+    img[102, 200] = (1.5, 2.5, 0.1)  # boundary: kept (the test is z < 0.1)
+    uv = np.array([[200.9, 100.9], [200.2, 101.7], [200.5, 102.99], [10.0, 20.0]])
+    uvd = uv + 3.0
+    a, b, X = gms.make_3d_2d_collection(K, uv, img, uvd)
+    assert X.shape == (2, 3) and np.allclose(X[0], (1.5, 2.5, 0.1), atol=1e-7) and X[1, 2] == 5.0
+    assert np.allclose(a[1], ((10.0 - 320) / 400, (20.0 - 240) / 410)) and np.allclose(b[1], ((13.0 - 320) / 400, (23.0 - 240) / 410))
+    img_b = img.copy()
+    img_b[23, 13, 2] = 26.0
+    P, Q = gms.make_3d_3d_collection(uv, img, uvd, img_b)
+    assert P.shape == (1, 3) and Q.shape == (1, 3)
+
+
+# ------------------------------------------------------------------ CUDA path vs oracle (GPU)
+@pytest.mark.gpu
+def test_device_match_gms_matches_golden_and_oracle(native_lib, cuda_device):
+    from cerebro_b200.frontend import FrontEnd
+
+    g = golden_io.load("gms_golden.npz")
+    fe = FrontEnd(max_pairs=8, max_features=3000)
+    rng = np.random.default_rng(11)
+    pairs = [(g["easy_kp1"], g["easy_d1"], g["easy_kp2"], g["easy_d2"])]
+    w, h = (int(v) for v in g["easy_size"])
+    pairs.append(_synthetic_pair(rng, 1700, 2100, w, h))
+    pairs.append(_synthetic_pair(rng, 130, 90, w, h, inlier_frac=0.9))
+    pairs.append((np.zeros((0, 2), np.float32), np.zeros((0, 32), np.uint8)) + _synthetic_pair(rng, 5, 60, w, h)[2:])  # no query features
+    pairs.append(_synthetic_pair(rng, 2999, 3000, w, h, inlier_frac=0.3))
+    res = fe.match_gms([p[0] for p in pairs], [p[1] for p in pairs], [p[2] for p in pairs], [p[3] for p in pairs], (w, h), (w, h))
+    assert np.array_equal(res[0]["train_idx"], g["easy_train"]) and np.array_equal(res[0]["distance"], g["easy_dist"])
+    assert np.array_equal(res[0]["inliers"], g["easy_mask"]), "GMS mask differs from the reference matcher's"
+    for p, r in zip(pairs, res):
+        if len(p[0]) == 0:
+            assert r["train_idx"].size == 0 and r["n_inliers"] == 0
+            continue
+        idx, dist = gms.bf_match_hamming(p[1], p[3])
+        assert np.array_equal(r["train_idx"], idx) and np.array_equal(r["distance"], dist)
+        mask, n = gms.gms_inlier_mask(p[0], (w, h), p[2], (w, h), np.arange(idx.size), idx)
+        assert np.array_equal(r["inliers"], mask) and r["n_inliers"] == n
+    assert res[1]["n_inliers"] > 300
+    assert fe.last_match_ms() > 0
+    # the second golden case has another image size
+    w2, h2 = (int(v) for v in g["hard_size"])
+    r = fe.match_gms([g["hard_kp1"]], [g["hard_d1"]], [g["hard_kp2"]], [g["hard_d2"]], (w2, h2), (w2, h2))[0]
+    assert np.array_equal(r["train_idx"], g["hard_train"]) and np.array_equal(r["inliers"], g["hard_mask"])
+    fe.close()
+
+
+@pytest.mark.gpu
+def test_device_collections_match_oracle(native_lib, cuda_device):
+    from cerebro_b200.frontend import FrontEnd
+
+    rng = np.random.default_rng(3)
+    w, h = 640, 480
+    K = np.array([[385.2, 0, 321.7], [0, 386.1, 238.4], [0, 0, 1]])
+    pairs = [_synthetic_pair(rng, 1200, 1300, w, h), _synthetic_pair(rng, 400, 380, w, h, inlier_frac=0.8)]
+    fe = FrontEnd(max_pairs=2, max_features=1500)
+    res = fe.match_gms([p[0] for p in pairs], [p[1] for p in pairs], [p[2] for p in pairs], [p[3] for p in pairs], (w, h), (w, h))
+    img_a = rng.uniform(-3, 3, (2, h, w, 3)).astype(np.float32)
+    img_b = rng.uniform(-3, 3, (2, h, w, 3)).astype(np.float32)
+    img_a[..., 2] = rng.uniform(-1, 30, (2, h, w))  # ~17 % outside the 0.1..25 m gate
+    img_b[..., 2] = rng.uniform(-1, 30, (2, h, w))
+    s2 = fe.make_3d_2d_collection(K, img_a)
+    s3 = fe.make_3d_3d_collection(img_a, img_b)
+    for p in range(2):
+        u, ud = fe.matched_points(p)
+        assert u.shape[0] == 3 and u.shape[1] == res[p]["n_inliers"] and np.all(u[2] == 1.0)
+        a, b, X = gms.make_3d_2d_collection(K, u[:2].T, img_a[p], ud[:2].T)
+        assert X.shape[0] > 50 and X.shape[0] < u.shape[1]
+        assert s2[p][2].shape == X.shape and np.array_equal(s2[p][2], X)  # fp32 -> fp64 widening is exact
+        assert np.allclose(s2[p][0], a, rtol=0, atol=1e-12) and np.allclose(s2[p][1], b, rtol=0, atol=1e-12)
+        P, Q = gms.make_3d_3d_collection(u[:2].T, img_a[p], ud[:2].T, img_b[p])
+        assert np.array_equal(s3[p][0], P) and np.array_equal(s3[p][1], Q)
+    fe.close()
+
+
+@pytest.mark.gpu
+def test_reference_call_shape_images_in(native_lib, cuda_device):
+    """StaticPointFeatureMatching::gms_point_feature_matches(imleft, imright, u, ud) with images in (ORB on the host)."""
+    cv2 = pytest.importorskip("cv2")
+    from cerebro_b200.frontend import StaticPointFeatureMatching
+
+    rng = np.random.default_rng(8)
+    a = cv2.GaussianBlur((rng.random((480, 640)) * 255).astype(np.uint8), (0, 0), 2.0)
+    a = cv2.normalize(a, None, 0, 255, cv2.NORM_MINMAX)
+    H = np.array([[1.01, 0.02, 5], [-0.02, 1.0, 3], [0, 0, 1.0]])
+    b = cv2.warpPerspective(a, H, (640, 480))
+    u, ud = StaticPointFeatureMatching.gms_point_feature_matches(a, b, n_orb_feat=2000)
+    assert u.shape[0] == 3 and u.shape == ud.shape and u.shape[1] > 300
+    proj = H @ u
+    proj /= proj[2]
+    err = np.linalg.norm(proj[:2] - ud[:2], axis=0)
+    assert np.median(err) < 2.0  # GMS keeps the matches that follow the homography
