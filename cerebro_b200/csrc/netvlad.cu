@@ -1271,45 +1271,85 @@ constexpr int kAggSmem = 128 * 64 * 4;
 __global__ void __launch_bounds__(256) vlad_aggregate_kernel(const __half* __restrict__ x, const float* __restrict__ a,
                                                             int P, int D, float* __restrict__ Vp /*[frames][split][16][D]*/,
                                                             float* __restrict__ Ap /*[frames][split][16]*/) {
-  extern __shared__ float red[];  // [128 accumulators][64 channel groups]
+  extern __shared__ float red[];  // [128 accumulators][64 channel groups]; during the pixel loop: the slice's soft-assignments
   const int f = blockIdx.y, sp = blockIdx.x;
   const int dq = threadIdx.x & 63, pl = threadIdx.x >> 6;
   const int d0 = dq * 8;
   const bool active = d0 < D;
   const int p_begin = (int)((long long)P * sp / kAggSplit), p_end = (int)((long long)P * (sp + 1) / kAggSplit);
+  const int n_s = p_end - p_begin;
   const __half* xf = x + (size_t)f * P * D + d0;
-  const float* af = a + (size_t)f * P * kK;
+  const float* af = a + ((size_t)f * P + p_begin) * kK;
+  // The slice's assignments a[p][16] go to shared memory once (coalesced), zero-padded by one unrolled step, so the pixel loop
+  // has a single kind of global load -- the 16-byte x vector -- and keeps kAggUnroll of them in flight per thread (the
+  // kernel is latency-bound: 8 warps per SM).  Slices too long for the buffer read the assignments from global memory.
+  constexpr int kAggUnroll = 8;
+  const bool a_in_smem = (size_t)(n_s + 4 * kAggUnroll) * kK * sizeof(float) <= (size_t)kAggSmem;
+  if (a_in_smem) {
+    const int n4 = n_s * (kK / 4);
+    for (int i = threadIdx.x; i < n4 + 4 * kAggUnroll * (kK / 4); i += 256)
+      reinterpret_cast<float4*>(red)[i] = i < n4 ? __ldg(reinterpret_cast<const float4*>(af) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
   unsigned long long acc[kK][4];
 #pragma unroll
   for (int k = 0; k < kK; ++k)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[k][j] = 0ull;
   if (active) {
-#pragma unroll 2
-    for (int p = p_begin + pl; p < p_end; p += 4) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xf + (size_t)p * D));
-      const float4* ap = reinterpret_cast<const float4*>(af + (size_t)p * kK);
-      float av[kK];
+#pragma unroll 1
+    for (int p = pl; p < n_s; p += 4 * kAggUnroll) {
+      uint4 raw[kAggUnroll];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 t = __ldg(ap + q);
-        av[4 * q] = t.x, av[4 * q + 1] = t.y, av[4 * q + 2] = t.z, av[4 * q + 3] = t.w;
-      }
-      const __half2* hv = reinterpret_cast<const __half2*>(&raw);
-      unsigned long long v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 fv = __half22float2(hv[j]);
-        v[j] = pack_f32x2(fv.x, fv.y);
+      for (int u = 0; u < kAggUnroll; ++u) {
+        const int pp = p + 4 * u;
+        raw[u] = pp < n_s ? __ldg(reinterpret_cast<const uint4*>(xf + (size_t)(p_begin + pp) * D)) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
-      for (int k = 0; k < kK; ++k) {
-        const unsigned long long ak = pack_f32x2(av[k], av[k]);
+      for (int u = 0; u < kAggUnroll; ++u) {
+        const int pp = p + 4 * u;
+        float av[kK];
+        if (a_in_smem) {  // padded with zeros: no bounds test
+          const float4* ap = reinterpret_cast<const float4*>(red + (size_t)pp * kK);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[k][j] = ffma2(ak, v[j], acc[k][j]);
+          for (int q = 0; q < 4; ++q) {
+            const float4 t = ap[q];
+            av[4 * q] = t.x, av[4 * q + 1] = t.y, av[4 * q + 2] = t.z, av[4 * q + 3] = t.w;
+          }
+        } else {
+          const float4* ap = reinterpret_cast<const float4*>(af + (size_t)(pp < n_s ? pp : 0) * kK);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 t = __ldg(ap + q);
+            av[4 * q] = t.x, av[4 * q + 1] = t.y, av[4 * q + 2] = t.z, av[4 * q + 3] = t.w;
+          }
+        }
+        const __half2* hv = reinterpret_cast<const __half2*>(&raw[u]);  // zero beyond the slice: contributes nothing
+        unsigned long long v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 fv = __half22float2(hv[j]);
+          v[j] = pack_f32x2(fv.x, fv.y);
+        }
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+          const unsigned long long ak = pack_f32x2(av[k], av[k]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[k][j] = ffma2(ak, v[j], acc[k][j]);
+        }
       }
     }
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kK) {  // sum_p a[p][k] of this slice, same order as before (ascending p)
+    const int k = threadIdx.x - 64;
+    float asum = 0.f;
+    if (a_in_smem)
+      for (int p = 0; p < n_s; ++p) asum += red[(size_t)p * kK + k];
+    else
+      for (int p = 0; p < n_s; ++p) asum += af[(size_t)p * kK + k];
+    Ap[((size_t)f * kAggSplit + sp) * kK + k] = asum;
+  }
+  __syncthreads();  // the assignments are dead: `red` becomes the reduction buffer
   float r[kK * 8];
 #pragma unroll
   for (int k = 0; k < kK; ++k)
@@ -1334,12 +1374,6 @@ __global__ void __launch_bounds__(256) vlad_aggregate_kernel(const __half* __res
       *reinterpret_cast<float4*>(vo) = make_float4(r[k * 8], r[k * 8 + 1], r[k * 8 + 2], r[k * 8 + 3]);
       *reinterpret_cast<float4*>(vo + 4) = make_float4(r[k * 8 + 4], r[k * 8 + 5], r[k * 8 + 6], r[k * 8 + 7]);
     }
-  }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + kK) {  // sum_p a[p][k] of this slice (warp 2: off the critical path of lane 0)
-    const int k = threadIdx.x - 64;
-    float asum = 0.f;
-    for (int p = p_begin; p < p_end; ++p) asum += af[(size_t)p * kK + k];
-    Ap[((size_t)f * kAggSplit + sp) * kK + k] = asum;
   }
 }
 
