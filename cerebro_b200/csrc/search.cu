@@ -334,6 +334,123 @@ topk_chunk_kernel(const float* __restrict__ partial, int n_slices, long long sli
   if (warp == 0) ckeys[((size_t)q * n_chunks + chunk) * kList + lane] = kl.key;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-pass variant of the chunk selection (used when the DB has enough rows for the bound to bite).  In
+// topk_chunk_kernel a warp only ever sees 1024 rows, so nearly every batch of 32 candidates beats the warp's own
+// 32nd best and pays a 15-step bitonic sort + merge (112 us for 64 x 100k scores).  Here:
+//   topk_bound_kernel  : every thread reduces its 32 rows to ONE key (its best row); the CTA keeps the best 32 of its 256
+//                        thread maxima (one sort per warp).  Any 32 distinct rows bound the query's 32nd best key from
+//                        below, and thread maxima are a good choice: the 32nd largest of ~3300 of them sits at the
+//                        ~0.9997 quantile of 100k scores.  The pass also folds the K-split slices into slice 0.
+//   topk_filter_kernel : merges the per-chunk bound lists -> T (the 32nd largest thread maximum of the whole query), then
+//                        runs the same selection as topk_chunk_kernel over keys >= T only: ~33 rows per query survive,
+//                        so almost no batch triggers a sort.  Output format unchanged (finalize_kernel follows).
+// Exact: a row below T cannot be among the query's 32 best keys (32 distinct rows with keys >= T exist).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cta_merge_and_store(KeyList& kl, unsigned long long* sk, int warp, int lane,
+                                                    unsigned long long* __restrict__ dst) {
+  sk[warp * kList + lane] = kl.key;
+  __syncthreads();
+#pragma unroll
+  for (int half = kWarps / 2; half >= 1; half >>= 1) {
+    if (warp < half) {
+      kl.merge_sorted(sk[(warp + half) * kList + lane], lane);
+      sk[warp * kList + lane] = kl.key;
+    }
+    __syncthreads();
+  }
+  if (warp == 0) dst[lane] = kl.key;
+}
+
+__global__ void __launch_bounds__(kThreads)
+topk_bound_kernel(float* __restrict__ partial, int n_slices, long long slice_stride, long long pstride, long long n_rows,
+                  int tie_high, unsigned long long* __restrict__ bkeys, int n_chunks) {
+  __shared__ unsigned long long sk[kWarps * kList];
+  const int q = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long r_begin = (long long)chunk * kChunkRows;
+  long long r_end = r_begin + kChunkRows;
+  if (r_end > n_rows) r_end = n_rows;
+  float* base = partial + (size_t)q * pstride;
+  const size_t sstride = (size_t)slice_stride;
+  constexpr int kPer = kChunkRows / kThreads;
+  unsigned long long best = 0ull;
+#pragma unroll 1
+  for (int j0 = 0; j0 < kPer; j0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long r = r_begin + tid + (long long)(j0 + j) * kThreads;
+      float a = 0.f;
+      if (r < r_end) {
+        for (int sl = 0; sl < n_slices; ++sl) a += base[sl * sstride + r];  // same order as topk_chunk_kernel
+        if (n_slices > 1) base[r] = a;                                       // the filter pass reads one slice
+      }
+      v[j] = a;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long r = r_begin + tid + (long long)(j0 + j) * kThreads;
+      if (r < r_end && v[j] == v[j]) best = umax64(best, pack_key(v[j], (unsigned int)r, tie_high));
+    }
+  }
+  KeyList kl;
+  kl.init();
+  kl.offer_batch(best, lane);
+  cta_merge_and_store(kl, sk, warp, lane, bkeys + ((size_t)q * n_chunks + chunk) * kList);
+}
+
+__global__ void __launch_bounds__(kThreads)
+topk_filter_kernel(const float* __restrict__ partial, long long pstride, long long n_rows, int tie_high,
+                   const unsigned long long* __restrict__ bkeys, unsigned long long* __restrict__ ckeys, int n_chunks) {
+  __shared__ unsigned long long sk[kWarps * kList];
+  __shared__ unsigned long long s_T;
+  const int q = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 0) {  // T = 32nd largest thread maximum of the whole query (0 while fewer than 32 exist: no filtering)
+    KeyList bl;
+    bl.init();
+    const unsigned long long* bq = bkeys + (size_t)q * n_chunks * kList + lane;
+    for (int c0 = 0; c0 < n_chunks; c0 += 8) {  // eight lists in flight, then merged
+      unsigned long long t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = (c0 + u < n_chunks) ? bq[(size_t)(c0 + u) * kList] : 0ull;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) bl.merge_sorted(t[u], lane);
+    }
+    if (lane == 31) s_T = bl.key;
+  }
+  __syncthreads();
+  const unsigned long long T = s_T;
+  const long long r_begin = (long long)chunk * kChunkRows;
+  long long r_end = r_begin + kChunkRows;
+  if (r_end > n_rows) r_end = n_rows;
+  KeyList kl;
+  kl.init();
+  const float* base = partial + (size_t)q * pstride;
+  constexpr int kPer = kChunkRows / kThreads;
+#pragma unroll 1
+  for (int j0 = 0; j0 < kPer; j0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long r = r_begin + tid + (long long)(j0 + j) * kThreads;
+      v[j] = r < r_end ? base[r] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long r = r_begin + tid + (long long)(j0 + j) * kThreads;
+      unsigned long long key = 0ull;
+      if (r < r_end && v[j] == v[j]) {
+        key = pack_key(v[j], (unsigned int)r, tie_high);
+        if (key < T) key = 0ull;
+      }
+      kl.offer_batch(key, lane);
+    }
+  }
+  cta_merge_and_store(kl, sk, warp, lane, ckeys + ((size_t)q * n_chunks + chunk) * kList);
+}
+
 // one CTA (32 warps) per query: merge chunk lists -> 32 survivors, fp64 re-score, rank, write top k
 __global__ void __launch_bounds__(1024)
 finalize_kernel(const unsigned long long* __restrict__ ckeys, int n_chunks, const float* __restrict__ rows, int d,
@@ -1068,8 +1185,9 @@ struct cb_index {
   // scratch (grown on demand)
   float* partial = nullptr;
   size_t partial_bytes = 0;
-  unsigned long long* chunk_k = nullptr;  // [qt][n_chunks][32] packed keys
+  unsigned long long* chunk_k = nullptr;  // [qt][n_chunks][32] packed keys, then the same again for the bound lists
   size_t chunk_elems = 0;
+  bool one_pass_topk = false;  // CB_TOPK_ONE_PASS=1: always the single-pass chunk selection
   float* q_dev = nullptr;  // host-API staging
   size_t q_bytes = 0;
   double* out_s = nullptr;
@@ -1259,7 +1377,7 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
       if (ix->chunk_k) cudaFree(ix->chunk_k);
       ix->chunk_k = nullptr;
       ix->chunk_elems = 0;
-      CB_CUDA(cudaMalloc(&ix->chunk_k, ce * sizeof(unsigned long long)));
+      CB_CUDA(cudaMalloc(&ix->chunk_k, 2 * ce * sizeof(unsigned long long)));
       ix->chunk_elems = ce;
     }
     for (int tq = 0; tq < gq; tq += p.qt) {
@@ -1330,8 +1448,18 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
       }
       if (e != cudaSuccess) return cb::fail(CB_ECUDA, "scores_kernel launch failed: %s", cudaGetErrorString(e));
     }
-    topk_chunk_kernel<<<dim3(n_chunks, gq), kThreads, 0, st>>>(ix->partial, p.n_slices, slice_stride, pstride, n_rows, tie_high,
-                                                               ix->chunk_k, n_chunks);
+    // two-pass selection once the query has >= 4 x 32 thread maxima to bound its 32nd best with (>= 4096 rows)
+    if (!ix->one_pass_topk && n_rows >= 4096) {
+      unsigned long long* bkeys = ix->chunk_k + ix->chunk_elems;
+      topk_bound_kernel<<<dim3(n_chunks, gq), kThreads, 0, st>>>(ix->partial, p.n_slices, slice_stride, pstride, n_rows, tie_high,
+                                                                 bkeys, n_chunks);
+      CB_LAUNCH_CHECK();
+      topk_filter_kernel<<<dim3(n_chunks, gq), kThreads, 0, st>>>(ix->partial, pstride, n_rows, tie_high, bkeys, ix->chunk_k,
+                                                                  n_chunks);
+    } else {
+      topk_chunk_kernel<<<dim3(n_chunks, gq), kThreads, 0, st>>>(ix->partial, p.n_slices, slice_stride, pstride, n_rows, tie_high,
+                                                                 ix->chunk_k, n_chunks);
+    }
     CB_LAUNCH_CHECK();
     finalize_kernel<<<gq, 1024, 0, st>>>(ix->chunk_k, n_chunks, ix->rows, ix->d, ix->rank, ix->world,
                                          xq_dev + (size_t)g0 * ix->d, k, tie_high, scores_dev + (size_t)g0 * k,
@@ -1371,6 +1499,8 @@ int cb_index_create(cb_index** out, int d, int64_t capacity, int device, int ran
     ix->no_tc = env3 && env3[0] == '1';
     const char* env4 = getenv("CB_TC_V1");
     ix->tc_v1 = env4 && env4[0] == '1';
+    const char* env5 = getenv("CB_TOPK_ONE_PASS");
+    ix->one_pass_topk = env5 && env5[0] == '1';
   }
   cudaError_t e = cudaMalloc(&ix->rows, (size_t)capacity * d * sizeof(float));
   if (e != cudaSuccess) {

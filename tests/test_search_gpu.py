@@ -194,8 +194,8 @@ def test_sweep_variants_agree(native_lib, cuda_device, monkeypatch, n, d, nq):
     q2 = synth.planted_queries(db, t2, seed=5)
     o = _oracle_index(db)
     o_half = _oracle_index(db[:half])
-    for env in ({}, {"CB_TC_V1": "1"}, {"CB_NO_TC": "1"}):
-        for key in ("CB_TC_V1", "CB_NO_TC"):
+    for env in ({}, {"CB_TC_V1": "1"}, {"CB_NO_TC": "1"}, {"CB_TOPK_ONE_PASS": "1"}, {"CB_NO_TC": "1", "CB_TOPK_ONE_PASS": "1"}):
+        for key in ("CB_TC_V1", "CB_NO_TC", "CB_TOPK_ONE_PASS"):
             monkeypatch.delenv(key, raising=False)
         for key, val in env.items():
             monkeypatch.setenv(key, val)
@@ -212,3 +212,25 @@ def test_sweep_variants_agree(native_lib, cuda_device, monkeypatch, n, d, nq):
         D, I = ix.search(q2, 5, limit_rows=lim)
         assert np.array_equal(I, o.search(q2, 5, limit_rows=lim)[1]), env
         ix.close()
+
+
+@pytest.mark.parametrize("nq", [3, 20])
+def test_many_exact_ties_above_the_bound(native_lib, cuda_device, nq):
+    """100 identical rows tie for the best score (more than the 32 candidates a list carries) in a DB large enough for
+    the two-pass selection: the returned labels must follow the requested tie rule exactly, as in the oracle."""
+    from cerebro_b200.index import TIE_HIGH_LABEL, TIE_LOW_LABEL, IndexFlatIP
+
+    n, d = 9000, 512
+    db = synth.unit_rows(n, d, seed=31)
+    db[4000:4100] = db[123]  # 101 copies of row 123 in total
+    db[8990:8995] = db[77]
+    xq = np.concatenate([db[123][None], db[77][None], synth.planted_queries(db, np.arange(nq - 2) * 50 + 5000, seed=3)])
+    ix = IndexFlatIP(d, capacity=n)
+    ix.add(db)
+    o = _oracle_index(db)
+    D, I = ix.search(xq, 8, tie=TIE_LOW_LABEL)
+    assert np.array_equal(I, o.search(xq, 8)[1])
+    assert list(I[0]) == [123] + list(range(4000, 4007)) and list(I[1][:6]) == [77, 8990, 8991, 8992, 8993, 8994]
+    D, I = ix.search(xq, 8, tie=TIE_HIGH_LABEL)
+    assert list(I[0]) == list(range(4099, 4091, -1)) and list(I[1][:6]) == [8994, 8993, 8992, 8991, 8990, 77]
+    ix.close()

@@ -6,11 +6,14 @@ tag=${1:-r1}
 out=gpurun_out
 mkdir -p $out
 export PYTHONUNBUFFERED=1
-K='regex:conv1|dwpw|dw_kernel|pw_gemm|vlad|scores|topk|finalize|merge_lists|split_|dls_|pnp_|icp_|copy_models'
+K='regex:conv1|dwpw|dw_kernel|pw_gemm|vlad|scores|topk|finalize|merge_lists|split_|dls_|pnp_|icp_|copy_models|hamming|gms_|collect_'
 
 timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1
 echo "pytest exit $?" | tee -a $out/${tag}_pytest_gpu.log
 tail -3 $out/${tag}_pytest_gpu.log
+
+timeout 300 python __graft_entry__.py --smoke > $out/${tag}_smoke.log 2>&1
+echo "smoke exit $?"; tail -2 $out/${tag}_smoke.log
 
 timeout 420 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 echo "bench exit $?"; cat $out/${tag}_bench.json
