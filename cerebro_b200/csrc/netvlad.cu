@@ -931,6 +931,43 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
 constexpr int kConvThreads = 160;
 constexpr int kConvTiles = 4;
 
+// Four image bytes -> four exact fp16 values (b - 128) as two half2 words: 0x6400 | b is the fp16 number 1024 + b, and
+// (1024 + b) - 1152 is exact.  One PRMT + one HSUB2 per pair instead of a byte load + I2F per value.
+__device__ __forceinline__ void bytes4_to_centered_h2(uint32_t w, uint32_t& lo, uint32_t& hi) {
+  const __half2 off = __floats2half2_rn(1152.f, 1152.f);
+  uint32_t a = __byte_perm(w, 0x64646464u, 0x4140), b = __byte_perm(w, 0x64646464u, 0x4342);
+  __half2 ha = __hsub2(*reinterpret_cast<__half2*>(&a), off), hb = __hsub2(*reinterpret_cast<__half2*>(&b), off);
+  lo = *reinterpret_cast<uint32_t*>(&ha);
+  hi = *reinterpret_cast<uint32_t*>(&hb);
+}
+
+// The 9 bytes (3 pixels x 3 channels) of one image row that feed output column x of the 3-channel stem, as bytes 0..8 of
+// (v0, v1, v2 & 0xff), through three aligned 32-bit loads.  `rowp` = start of the row, 4-byte aligned; `avail` = bytes
+// readable from rowp (to the end of the frame).  Taps beyond the right border read as 128 (-> 0 after centring).
+__device__ __forceinline__ void load_row9(const uint8_t* __restrict__ rowp, int x, int W, long long avail, uint32_t& v0,
+                                          uint32_t& v1, uint32_t& v2) {
+  const int o = 6 * x, a = o & ~3, sh = (o - a) * 8;
+  uint32_t w0, w1, w2;
+  if ((long long)a + 12 <= avail) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(rowp + a);
+    w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+  } else {  // the last few bytes of a frame: assemble the window from single bytes
+    uint32_t b[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) b[i] = (a + i < avail) ? (uint32_t)__ldg(rowp + a + i) : 128u;
+    w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+    w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+    w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+  }
+  v0 = __funnelshift_r(w0, w1, sh);
+  v1 = __funnelshift_r(w1, w2, sh);
+  v2 = w2 >> sh;
+  if (2 * x + 2 >= W) {  // third pixel is the zero padding column (ZeroPadding2D ((0,1),(0,1)))
+    v1 = (v1 & 0x0000ffffu) | 0x80800000u;
+    v2 = 0x80u;
+  }
+}
+
 template <int CIN>
 __global__ void __launch_bounds__(kConvThreads) conv1_tc_kernel(const uint8_t* __restrict__ img, int n, int H, int W, int Ho, int Wo,
                                                                const __half* __restrict__ w_hi /*[32][32] K-major*/,
@@ -960,6 +997,8 @@ __global__ void __launch_bounds__(kConvThreads) conv1_tc_kernel(const uint8_t* _
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   const uint32_t idesc = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // rows start 4-byte aligned: the 3-channel producers can use aligned 32-bit loads
+  const bool wide_loads = CIN == 3 && ((W * 3) & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0;
 
   for (int it = 0; it < kConvTiles; ++it) {
     const long long m0 = ((long long)blockIdx.x * kConvTiles + it) * 128;
@@ -986,7 +1025,39 @@ __global__ void __launch_bounds__(kConvThreads) conv1_tc_kernel(const uint8_t* _
       __half hv[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) hv[i] = __ushort_as_half((unsigned short)0);
-      if (ok) {
+      if (CIN == 3 && wide_loads) {
+        if (ok) {  // 9 aligned 32-bit loads + byte permutes instead of 27 byte loads + conversions
+          const int x = (int)(m % Wo);
+          const long long t2 = m / Wo;
+          const int y = (int)(t2 % Ho);
+          const long long frame_bytes = (long long)H * W * 3;
+          const uint8_t* base = img + (size_t)(t2 / Ho) * frame_bytes;
+          uint32_t rv[3][3];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int iy = 2 * y + ky;
+            if (iy < H) {
+              const long long roff = (long long)iy * W * 3;
+              load_row9(base + roff, x, W, frame_bytes - roff, rv[ky][0], rv[ky][1], rv[ky][2]);
+            } else {  // zero padding row
+              rv[ky][0] = rv[ky][1] = 0x80808080u;
+              rv[ky][2] = 0x80u;
+            }
+          }
+          // 27 bytes (+ one padding byte) as 7 words, tap order (ky, kx, ci)
+          uint32_t wd[7];
+          wd[0] = rv[0][0];
+          wd[1] = rv[0][1];
+          wd[2] = (rv[0][2] & 0xffu) | (rv[1][0] << 8);
+          wd[3] = (rv[1][0] >> 24) | (rv[1][1] << 8);
+          wd[4] = (rv[1][1] >> 24) | ((rv[1][2] & 0xffu) << 8) | (rv[2][0] << 16);
+          wd[5] = (rv[2][0] >> 16) | (rv[2][1] << 16);
+          wd[6] = (rv[2][1] >> 16) | ((rv[2][2] & 0xffu) << 16) | 0x80000000u;
+          uint32_t* hw = reinterpret_cast<uint32_t*>(hv);
+#pragma unroll
+          for (int i = 0; i < 7; ++i) bytes4_to_centered_h2(wd[i], hw[2 * i], hw[2 * i + 1]);
+        }
+      } else if (ok) {
         const int x = (int)(m % Wo);
         const long long t2 = m / Wo;
         const int y = (int)(t2 % Ho);

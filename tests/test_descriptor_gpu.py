@@ -141,15 +141,17 @@ def test_tcgen05_path_agrees_with_cuda_core_path(native_lib, cuda_device):
     assert np.linalg.norm(a - c_, axis=1).max() < 2e-3
 
 
-def test_odd_image_size_tail_tiles(native_lib, cuda_device):
+@pytest.mark.parametrize("h,w", [(120, 188), (97, 126), (99, 127)])
+def test_odd_image_size_tail_tiles(native_lib, cuda_device, h, w):
     """480x752 (EuRoC) gives feature maps whose pixel counts are not multiples of the 128-pixel tile
-    and widths not multiples of 4: exercises every tail path against the oracle."""
+    and widths not multiples of 4: exercises every tail path against the oracle.  Odd sizes also cover the stem's
+    byte-load producers (rows not 4-byte aligned), the zero-padding row / column and the last bytes of a frame."""
     from cerebro_b200.descriptor import NetvladDescriptor
     from oracle import netvlad as NV
 
     raw = golden_io.raw_weights("mobilenet_conv7")
-    imgs = synth.band_limited_images(1, 120, 188, 3, seed=77)
-    nd = NetvladDescriptor(_net("mobilenet_conv7"), 120, 188, 3, max_batch=1)
+    imgs = synth.band_limited_images(1, h, w, 3, seed=77)
+    nd = NetvladDescriptor(_net("mobilenet_conv7"), h, w, 3, max_batch=1)
     d = nd.compute(imgs)
     ref = NV.describe(imgs, raw, dtype="float64")
     assert np.linalg.norm(d - ref, axis=1).max() < L2_TOL
