@@ -371,7 +371,8 @@ def main():
             cpu_base = {"value": args.cpu_baseline_keyframes / secs, "unit": UNIT, "cores": ctx["cores"], "kind": "port",
                         "sample": "%d keyframes: torch-CPU fp32 NetVLAD (all cores) + fp32 BLAS top-5 search of the full 100k x 8192 DB + oracle DLS-PnP RANSAC (1 thread)" % args.cpu_baseline_keyframes}
         # stem + 7 fused blocks + VLAD head (3); per sweep: query split + tcgen05 sweep; per <=128 queries: top-k + finalize; PnP (6)
-        launches = (1 + 7 + 3) + (2 * sweeps + 2 * ((nq + 127) // 128)) + 6
+        # (two-pass top-k from 4096 rows: bound + filter + finalize per group of <= 128 queries)
+        launches = (1 + 7 + 3) + (2 * sweeps + (3 if n_mine >= 4096 else 2) * ((nq + 127) // 128)) + 6
         line = {
             "metric": METRIC,
             "value": value,
