@@ -977,13 +977,20 @@ scores_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
 // partial scores to slice s of `partial`, which topk_chunk_kernel already sums (the SIMT sweeps slice d the same way).
 // ---------------------------------------------------------------------------------------------
 constexpr int kT2KB = 32;                            // elements per K block
-constexpr int kT2Stages = 5;
 constexpr int kT2ASub = 128 * kT2KB * 2;             // one 128-row sub-tile of one plane (8 KB)
 constexpr int kT2ABytes = 4 * kT2ASub;               // hi rb0 | hi rb1 | lo rb0 | lo rb1
-constexpr int kT2BSub = kTcQ * kT2KB * 2;            // one query plane (4 KB)
-constexpr int kT2StageBytes = kT2ABytes + 2 * kT2BSub;
-constexpr int kT2Smem = kT2Stages * kT2StageBytes + 1024 + 256;
 constexpr int kT2MaxSplits = 8;
+// NQ = queries per sweep (N of the MMA): 64, or 128 when more than 64 queries wait (one pass over the database then serves
+// twice as many: the multi-GPU step searches world x 64 queries per rank).  128 queries = 16 KB of query planes per stage
+// -> four 48 KB stages instead of five 40 KB ones, 2 x 256 TMEM columns instead of 2 x 128.
+template <int NQ>
+struct T2Cfg {
+  static constexpr int kBSub = NQ * kT2KB * 2;  // one query plane of a K block
+  static constexpr int kStageBytes = kT2ABytes + 2 * kBSub;
+  static constexpr int kStages = NQ <= 64 ? 5 : 4;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kTmemCols = 4 * NQ;  // 2 accumulator stages x 2 row halves x NQ
+};
 
 // rows [row0, row0 + n_rows) of the fp32 database -> tiled hi/lo planes
 __global__ void split_tiled_kernel(const float* __restrict__ rows, long long row0, long long n_rows, int d, __half* __restrict__ hl) {
@@ -1007,24 +1014,28 @@ __global__ void split_tiled_kernel(const float* __restrict__ rows, long long row
   *reinterpret_cast<uint2*>(hl + base + 2 * 128 * kT2KB) = *reinterpret_cast<uint2*>(l);
 }
 
-// nq query rows -> qhl[kb][plane][kTcQ][kT2KB], rows >= nq zero
-__global__ void split_queries_tiled_kernel(const float* __restrict__ xq, int nq, int d, __half* __restrict__ qhl) {
+// nq query rows -> qhl[kb][plane][NQ][kT2KB], rows >= nq zero
+__global__ void split_queries_tiled_kernel(const float* __restrict__ xq, int nq, int d, int NQ, __half* __restrict__ qhl) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)kTcQ * d) return;
+  if (i >= (long long)NQ * d) return;
   const int q = (int)(i / d), e = (int)(i % d);
   const float f = q < nq ? xq[i] : 0.f;
   const __half h = __float2half_rn(f);
   const int kb = e / kT2KB, ee = e % kT2KB;
-  const size_t base = (((size_t)kb * 2) * kTcQ + q) * kT2KB + ee;
+  const size_t base = (((size_t)kb * 2) * NQ + q) * kT2KB + ee;
   qhl[base] = h;
-  qhl[base + kTcQ * kT2KB] = __float2half_rn(f - __half2float(h));
+  qhl[base + (size_t)NQ * kT2KB] = __float2half_rn(f - __half2float(h));
 }
 
+template <int NQ>
 __global__ void __launch_bounds__(kTcThreads, 1)
 scores_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, long long n_rows, int nkb,
                   int nq_valid, float* __restrict__ partial, long long pstride, long long slice_stride, int n_tiles,
                   int n_splits) {
   extern __shared__ uint8_t smem_raw[];
+  using Cfg = T2Cfg<NQ>;
+  constexpr int kT2Stages = Cfg::kStages, kT2StageBytes = Cfg::kStageBytes, kT2BSub = Cfg::kBSub;
+  constexpr int kAccCols = 2 * NQ;  // TMEM columns of one accumulator stage
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kT2Stages * kT2StageBytes);
   uint64_t* empty = full + kT2Stages;
@@ -1048,7 +1059,7 @@ scores_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     fence_barrier_init();
   }
   __syncwarp();
-  if (warp == 1) tmem_alloc(tmem_ptr, 256);
+  if (warp == 1) tmem_alloc(tmem_ptr, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1068,13 +1079,13 @@ scores_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int arow = (tile * nkb + kb) * 512;  // < 2^31: checked on the host
           tma_load_2d(&tmA, &full[s], st, 0, arow);
           tma_load_2d(&tmA, &full[s], st + 2 * kT2ASub, 0, arow + 256);
-          tma_load_2d(&tmB, &full[s], st + kT2ABytes, 0, kb * 2 * kTcQ);
+          tma_load_2d(&tmB, &full[s], st + kT2ABytes, 0, kb * 2 * NQ);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(kTcQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(NQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       uint32_t g = 0, ti = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
         const int tile = u / n_splits, sp = u - tile * n_splits;
@@ -1093,7 +1104,7 @@ scores_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t bh = make_kmajor_desc<64>(b_hi + k * 32), bl = make_kmajor_desc<64>(b_lo + k * 32);
 #pragma unroll
             for (int rb = 0; rb < 2; ++rb) {
-              const uint32_t dt = tmem_base + acc * 128 + rb * kTcQ;
+              const uint32_t dt = tmem_base + acc * kAccCols + rb * NQ;
               const uint64_t ah = make_kmajor_desc<64>(st + rb * kT2ASub + k * 32);
               const uint64_t al = make_kmajor_desc<64>(st + (2 + rb) * kT2ASub + k * 32);
               umma_f16(dt, ah, bh, idesc, (kb > kb0 || k) ? 1u : 0u);
@@ -1120,9 +1131,10 @@ scores_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const long long row = (long long)tile * kTcRows + rb * 128 + q * 32 + lane;
         const bool row_ok = row < n_rows;
 #pragma unroll 1
-        for (int c = 0; c < kTcQ; c += 32) {
+        for (int c = 0; c < NQ; c += 32) {
+          if (c >= nq_valid) break;  // warp-uniform: columns of absent queries are never read
           uint32_t v[32];
-          tmem_ld32(tmem_base + acc * 128 + rb * kTcQ + c + ((uint32_t)(q * 32) << 16), v);
+          tmem_ld32(tmem_base + acc * kAccCols + rb * NQ + c + ((uint32_t)(q * 32) << 16), v);
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -1139,7 +1151,7 @@ scores_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -1188,6 +1200,7 @@ struct cb_index {
   unsigned long long* chunk_k = nullptr;  // [qt][n_chunks][32] packed keys, then the same again for the bound lists
   size_t chunk_elems = 0;
   bool one_pass_topk = false;  // CB_TOPK_ONE_PASS=1: always the single-pass chunk selection
+  bool narrow_q = false;       // CB_TC_Q64=1: never use the 128-query sweep
   float* q_dev = nullptr;  // host-API staging
   size_t q_bytes = 0;
   double* out_s = nullptr;
@@ -1210,8 +1223,8 @@ struct cb_index {
   // tiled planes (scores_tc2_kernel, the default): one buffer, stage-contiguous; CB_TC_V1=1 keeps the row-major planes
   bool tc_v1 = false;
   __half* hl = nullptr;   // [capacity/256][d/32][4][128][32]
-  __half* qhl = nullptr;  // [d/32][2][64][32]
-  CUtensorMap tmA2, tmB2;
+  __half* qhl = nullptr;  // [d/32][2][NQ][32], allocated for NQ = 128
+  CUtensorMap tmA2, tmB2, tmB2w;  // tmB2: 64-query tile, tmB2w: 128-query tile
   // optional device-side timing of the sweep kernel (bench.py roofline)
   bool timing = false;
   cudaEvent_t ev[2 * 64] = {};
@@ -1284,13 +1297,17 @@ bool ensure_planes(cb_index* ix, cudaStream_t st) {
       int rc = arows < (1ull << 31) ? CB_OK : CB_ENOMEM;
       cudaError_t e = cudaSuccess;
       if (!rc) e = cudaMalloc((void**)&ix->hl, (size_t)arows * kT2KB * sizeof(__half));
-      if (!rc && e == cudaSuccess) e = cudaMalloc((void**)&ix->qhl, (size_t)2 * kTcQ * ix->d * sizeof(__half));
+      if (!rc && e == cudaSuccess) e = cudaMalloc((void**)&ix->qhl, (size_t)2 * 128 * ix->d * sizeof(__half));
       if (e != cudaSuccess) rc = CB_ENOMEM;
       if (!rc) rc = make_map_2d(&ix->tmA2, ix->hl, arows, kT2KB, 256, kT2KB);
-      if (!rc) rc = make_map_2d(&ix->tmB2, ix->qhl, (uint64_t)nkb * 2 * kTcQ, kT2KB, 2 * kTcQ, kT2KB);
-      if (!rc) rc = cudaFuncSetAttribute(scores_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2Smem) == cudaSuccess
-                        ? CB_OK
-                        : CB_ECUDA;
+      if (!rc) rc = make_map_2d(&ix->tmB2, ix->qhl, (uint64_t)nkb * 2 * 64, kT2KB, 2 * 64, kT2KB);
+      if (!rc) rc = make_map_2d(&ix->tmB2w, ix->qhl, (uint64_t)nkb * 2 * 128, kT2KB, 2 * 128, kT2KB);
+      if (!rc)
+        rc = cudaFuncSetAttribute(scores_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Cfg<64>::kSmem) == cudaSuccess &&
+                     cudaFuncSetAttribute(scores_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Cfg<128>::kSmem) ==
+                         cudaSuccess
+                 ? CB_OK
+                 : CB_ECUDA;
       if (rc) {
         cudaGetLastError();
         cudaFree(ix->hl), cudaFree(ix->qhl);
@@ -1364,7 +1381,7 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
     const bool use_tc = gq > 4 && ix->d % kTcKB == 0 && ensure_planes(ix, st);
     const int n_tc_tiles = (int)((n_rows + kTcRows - 1) / kTcRows);
     if (use_tc) {
-      p.qt = kTcQ;
+      p.qt = (!ix->tc_v1 && !ix->narrow_q && gq > kTcQ) ? 128 : kTcQ;  // one pass serves up to 128 queries
       p.n_slices = ix->tc_v1 ? 1 : pick_splits(n_tc_tiles, ix->d / kT2KB, ix->sm_count);  // K splits land in slices
       p.ds = ix->d;
     }
@@ -1386,11 +1403,11 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
       float* ptile = ix->partial + (size_t)tq * pstride;
       cudaError_t e = cudaSuccess;
       if (use_tc) {
-        const long long qelems = (long long)kTcQ * ix->d;
+        const long long qelems = (long long)p.qt * ix->d;
         if (ix->tc_v1)
           split_queries_kernel<<<(unsigned)((qelems + 255) / 256), 256, 0, st>>>(xq, nq_valid, ix->d, ix->q_hi, ix->q_lo);
         else
-          split_queries_tiled_kernel<<<(unsigned)((qelems + 255) / 256), 256, 0, st>>>(xq, nq_valid, ix->d, ix->qhl);
+          split_queries_tiled_kernel<<<(unsigned)((qelems + 255) / 256), 256, 0, st>>>(xq, nq_valid, ix->d, p.qt, ix->qhl);
         const int n_units = ix->tc_v1 ? n_tc_tiles : n_tc_tiles * p.n_slices;
         const int grid = n_units < ix->sm_count ? n_units : ix->sm_count;
         const bool rec_tc = ix->timing && ix->ev_used < 64;
@@ -1398,9 +1415,12 @@ int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t
         if (ix->tc_v1)
           scores_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(ix->tmAhi, ix->tmAlo, ix->tmBhi, ix->tmBlo, n_rows, ix->d, nq_valid,
                                                               ptile, pstride, n_tc_tiles);
+        else if (p.qt == 128)
+          scores_tc2_kernel<128><<<grid, kTcThreads, T2Cfg<128>::kSmem, st>>>(ix->tmA2, ix->tmB2w, n_rows, ix->d / kT2KB, nq_valid, ptile,
+                                                                              pstride, slice_stride, n_tc_tiles, p.n_slices);
         else
-          scores_tc2_kernel<<<grid, kTcThreads, kT2Smem, st>>>(ix->tmA2, ix->tmB2, n_rows, ix->d / kT2KB, nq_valid, ptile, pstride,
-                                                               slice_stride, n_tc_tiles, p.n_slices);
+          scores_tc2_kernel<64><<<grid, kTcThreads, T2Cfg<64>::kSmem, st>>>(ix->tmA2, ix->tmB2, n_rows, ix->d / kT2KB, nq_valid, ptile,
+                                                                            pstride, slice_stride, n_tc_tiles, p.n_slices);
         if (rec_tc) {
           cudaEventRecord(ix->ev[2 * ix->ev_used + 1], st);
           ++ix->ev_used;
@@ -1501,6 +1521,8 @@ int cb_index_create(cb_index** out, int d, int64_t capacity, int device, int ran
     ix->tc_v1 = env4 && env4[0] == '1';
     const char* env5 = getenv("CB_TOPK_ONE_PASS");
     ix->one_pass_topk = env5 && env5[0] == '1';
+    const char* env6 = getenv("CB_TC_Q64");
+    ix->narrow_q = env6 && env6[0] == '1';
   }
   cudaError_t e = cudaMalloc(&ix->rows, (size_t)capacity * d * sizeof(float));
   if (e != cudaSuccess) {

@@ -178,7 +178,7 @@ def test_full_size_properties(native_lib, cuda_device):
     assert torch.equal(S8, S1)  # fp64 re-scoring is shard-independent, bit for bit
 
 
-@pytest.mark.parametrize("n,d,nq", [(1500, 1024, 64), (300, 8192, 9), (5000, 4096, 40)])
+@pytest.mark.parametrize("n,d,nq", [(1500, 1024, 64), (300, 8192, 9), (5000, 4096, 40), (4500, 2048, 128), (2000, 1024, 200), (700, 512, 65)])
 def test_sweep_variants_agree(native_lib, cuda_device, monkeypatch, n, d, nq):
     """The tensor-core sweep on tiled planes (default), on row-major planes (CB_TC_V1=1) and the fp32 CUDA-core sweep
     (CB_NO_TC=1) must return the same labels and fp64 scores as the oracle -- with rows trickling in between searches
@@ -194,8 +194,8 @@ def test_sweep_variants_agree(native_lib, cuda_device, monkeypatch, n, d, nq):
     q2 = synth.planted_queries(db, t2, seed=5)
     o = _oracle_index(db)
     o_half = _oracle_index(db[:half])
-    for env in ({}, {"CB_TC_V1": "1"}, {"CB_NO_TC": "1"}, {"CB_TOPK_ONE_PASS": "1"}, {"CB_NO_TC": "1", "CB_TOPK_ONE_PASS": "1"}):
-        for key in ("CB_TC_V1", "CB_NO_TC", "CB_TOPK_ONE_PASS"):
+    for env in ({}, {"CB_TC_V1": "1"}, {"CB_NO_TC": "1"}, {"CB_TOPK_ONE_PASS": "1"}, {"CB_NO_TC": "1", "CB_TOPK_ONE_PASS": "1"}, {"CB_TC_Q64": "1"}):
+        for key in ("CB_TC_V1", "CB_NO_TC", "CB_TOPK_ONE_PASS", "CB_TC_Q64"):
             monkeypatch.delenv(key, raising=False)
         for key, val in env.items():
             monkeypatch.setenv(key, val)

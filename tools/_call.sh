@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_descriptor_gpu.py tests/test_pipeline_gpu.py -m gpu -x -q > gpurun_out/c11_pytest.log 2>&1; echo "pytest exit $?"; tail -15 gpurun_out/c11_pytest.log
-timeout 300 python tools/bench_desc.py
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:conv1 -c 3 python tools/bench_desc.py 2>&1 | grep -E "gpu__time" | head -5
+timeout 600 python -m pytest tests/test_search_gpu.py -m gpu -x -q > gpurun_out/c12_pytest.log 2>&1; echo "pytest exit $?"; tail -15 gpurun_out/c12_pytest.log
+timeout 300 python tools/bench_sweep_ab.py > gpurun_out/c12_ab.log 2>&1; cat gpurun_out/c12_ab.log

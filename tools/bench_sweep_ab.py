@@ -16,7 +16,7 @@ if os.path.exists("MEASURED_PEAKS.json"):
 
 
 def run(n, d, nq, env, iters=20):
-    for k in ("CB_TC_V1", "CB_NO_TC"):
+    for k in ("CB_TC_V1", "CB_NO_TC", "CB_TC_Q64"):
         os.environ.pop(k, None)
     os.environ.update(env)
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -49,6 +49,6 @@ def run(n, d, nq, env, iters=20):
 
 if __name__ == "__main__":
     for n, d in ((100_000, 8192), (12_500, 8192), (10_000, 4096)):
-        for nq in (64, 16):
-            for env in ({}, {"CB_TC_V1": "1"}):
+        for nq in (128, 64, 16):
+            for env in ({}, {"CB_TC_Q64": "1"}):
                 run(n, d, nq, env)
