@@ -326,22 +326,28 @@ def main():
     from concurrent.futures import ThreadPoolExecutor
 
     pool = ThreadPoolExecutor(max_workers=1)
-    desc_pool = ThreadPoolExecutor(max_workers=1)
+    desc_pool = ThreadPoolExecutor(max_workers=2)
     Xs = [X_host.numpy()[i * N_CORR : (i + 1) * N_CORR] for i in range(B)]
     uvs = [uv_host.numpy()[i * N_CORR : (i + 1) * N_CORR] for i in range(B)]
+    # Two descriptor handles (same weights), each driven by one call at a time: batch i+1 is uploaded on one handle's copy
+    # stream while batch i runs its forward pass on the other's -- every handle owns its streams and device buffers.
+    from cerebro_b200.descriptor import NetvladDescriptor
+
+    descs = [pipe.desc, NetvladDescriptor(net, ROWS, COLS, CHNLS, max_batch=B, device=local_rank)]
+    d_out = [torch.empty((B, DIM), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
 
     def run_host(n_steps):
-        """n_steps keyframe batches through the host C-ABI calls, organised like the reference node: a descriptor
-        thread (desc_th), the search thread (this one) and the verifier thread (loopcandidate_consumer_th) -- ctypes
+        """n_steps keyframe batches through the host C-ABI calls, organised like the reference node: descriptor
+        thread(s) (desc_th), the search thread (this one) and the verifier thread (loopcandidate_consumer_th) -- ctypes
         releases the GIL inside the calls and every handle owns its streams, so batch i+1 is uploaded and described
         while batch i is searched and verified.  Every batch's upload and read-back happens inside this function."""
-        fut_d = desc_pool.submit(pipe.desc.compute, imgs_host.numpy())
+        from collections import deque
+
+        futs = deque(desc_pool.submit(descs[j % 2].compute, imgs_host.numpy(), d_out[j % 2]) for j in range(min(2, n_steps)))
         res = None
         for i in range(n_steps):
             fut_p = pool.submit(pipe.pnp.solve, Xs, uvs, pipe.params)
-            d = fut_d.result()
-            if i + 1 < n_steps:
-                fut_d = desc_pool.submit(pipe.desc.compute, imgs_host.numpy())
+            d = futs.popleft().result()
             if world > 1:
                 dd = torch.from_numpy(d).to(dev)
                 dist.all_gather_into_tensor(bufs["queries"], dd)
@@ -349,6 +355,8 @@ def main():
                 res = (s.cpu(), l.cpu())
             else:
                 res = pipe.index.search(d, 5)
+            if i + 2 < n_steps:  # handle i % 2 and its output buffer are free again: batch i has been searched
+                futs.append(desc_pool.submit(descs[i % 2].compute, imgs_host.numpy(), d_out[i % 2]))
             res = (res, fut_p.result())
         return res
 

@@ -113,15 +113,18 @@ class NetvladDescriptor:
         except Exception:
             pass
 
-    def compute(self, images_u8: np.ndarray) -> np.ndarray:
-        """uint8 [n, rows, cols, chnls] (or [n, rows, cols] for 1 channel) -> float32 [n, dim]."""
+    def compute(self, images_u8: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """uint8 [n, rows, cols, chnls] (or [n, rows, cols] for 1 channel) -> float32 [n, dim].  ``out`` may be a
+        caller-owned (e.g. pinned) float32 [n, dim] array."""
         if images_u8.ndim == 3:
             images_u8 = images_u8[..., None]
         assert images_u8.dtype == np.uint8
         n = images_u8.shape[0]
         assert images_u8.shape[1:] == (self.rows, self.cols, self.chnls), images_u8.shape
         images_u8 = np.ascontiguousarray(images_u8)
-        out = np.empty((n, self.dim), dtype=np.float32)
+        if out is None:
+            out = np.empty((n, self.dim), dtype=np.float32)
+        assert out.dtype == np.float32 and out.shape == (n, self.dim) and out.flags["C_CONTIGUOUS"]
         check(self._lib.cb_descriptor_compute(self._h, n, ptr(images_u8), 0, ptr(out)))
         return out
 
