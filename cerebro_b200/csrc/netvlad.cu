@@ -1564,6 +1564,7 @@ struct cb_descriptor {
   std::vector<cudaEvent_t> ev_copy;
   bool force_simt = false;
   bool no_fuse = false;  // CB_NO_FUSE=1: separate depthwise + GEMM kernels
+  int upload_chunk = 64;  // frames per upload / forward chunk of the host API (CB_DESC_CHUNK): batches above it overlap upload and compute chunk by chunk
   bool no_halo = false;  // CB_NO_HALO=1: fused kernel whose producers read the activations straight from global memory
   int stop_layer = -1;  // CB_DEBUG_STOP_LAYER: stop the forward pass after this layer (bring-up / parity tests)
   int last_buf = 0;                 // ping-pong buffer holding the most recent layer output
@@ -1964,6 +1965,10 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
   d->no_halo = env4 && env4[0] == '1';
   const char* env2 = getenv("CB_DEBUG_STOP_LAYER");
   d->stop_layer = env2 ? atoi(env2) : -1;
+  if (const char* envc = getenv("CB_DESC_CHUNK")) {
+    const int c = atoi(envc);
+    if (c >= 1) d->upload_chunk = c;
+  }
   d->H1 = conv_out_s2(rows);
   d->W1 = conv_out_s2(cols);
   size_t max_elems = (size_t)d->H1 * d->W1 * 32;
@@ -2083,6 +2088,10 @@ int cb_descriptor_create_v2(cb_descriptor** out, const cb_netvlad_v2_weights* w,
   d->no_fuse = env3 && env3[0] == '1';
   const char* env2 = getenv("CB_DEBUG_STOP_LAYER");
   d->stop_layer = env2 ? atoi(env2) : -1;
+  if (const char* envc = getenv("CB_DESC_CHUNK")) {
+    const int c = atoi(envc);
+    if (c >= 1) d->upload_chunk = c;
+  }
   d->H1 = conv_out_s2(rows);
   d->W1 = conv_out_s2(cols);
   size_t max_elems = (size_t)d->H1 * d->W1 * 32;
@@ -2199,7 +2208,7 @@ int cb_descriptor_compute(cb_descriptor* d, int n, const uint8_t* images, int64_
   // server.py:614-619 asserts the image shape; here the shape is fixed at create time
   // Frames go up in chunks on a copy stream while the previous chunk is being processed: with pinned host images the
   // 0.9 MB/frame upload (the largest cost of the host path) overlaps the forward pass.
-  const int chunk = 16;
+  const int chunk = d->upload_chunk;
   const size_t frame_bytes = rowb * d->rows;
   int ci = 0;
   for (int c0 = 0; c0 < n; c0 += chunk, ++ci) {
