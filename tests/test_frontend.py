@@ -162,3 +162,73 @@ def test_reference_call_shape_images_in(native_lib, cuda_device):
     proj /= proj[2]
     err = np.linalg.norm(proj[:2] - ud[:2], axis=0)
     assert np.median(err) < 2.0  # GMS keeps the matches that follow the homography
+
+
+@pytest.mark.gpu
+def test_candidate_to_pose_chain(native_lib, cuda_device):
+    """Row a10 of the scope table end to end on the device, minus ORB / StereoBM: features of a synthetic scene seen from
+    two poses -> Hamming matches -> GMS -> 3D-2D set (Option A) -> DLS-PnP RANSAC recovers b_T_a within north_star's
+    1e-3 rad / 1e-2 m, and Option C (3D-3D Umeyama RANSAC) agrees with it (ProcessedLoopCandidate.cpp:40-125 thresholds)."""
+    from cerebro_b200.frontend import FrontEnd
+    from cerebro_b200.pnp import PnpBatch, default_params
+    from oracle import dls_pnp
+
+    rng = np.random.default_rng(12)
+    w, h = 640, 480
+    K = np.array([[420.0, 0, 320.0], [0, 420.0, 240.0], [0, 0, 1]])
+    # frame a: a smooth depth map, 3-D image = back-projected pixels (what the stereo pair's reprojectImageTo3D gives)
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    depth = 6.0 + 2.0 * np.sin(xs / 90.0) + 1.5 * np.cos(ys / 70.0)
+    img_a = np.stack([(xs - K[0, 2]) / K[0, 0] * depth, (ys - K[1, 2]) / K[1, 1] * depth, depth], -1).astype(np.float32)
+    # true relative pose b_T_a: ~4 degrees, 25 cm
+    ang = np.deg2rad([2.5, -3.0, 1.5])
+    Rx = np.array([[1, 0, 0], [0, np.cos(ang[0]), -np.sin(ang[0])], [0, np.sin(ang[0]), np.cos(ang[0])]])
+    Ry = np.array([[np.cos(ang[1]), 0, np.sin(ang[1])], [0, 1, 0], [-np.sin(ang[1]), 0, np.cos(ang[1])]])
+    Rz = np.array([[np.cos(ang[2]), -np.sin(ang[2]), 0], [np.sin(ang[2]), np.cos(ang[2]), 0], [0, 0, 1]])
+    R, t = Rz @ Ry @ Rx, np.array([0.2, -0.1, 0.12])
+    n = 2500
+    kp1 = np.stack([rng.uniform(20, w - 20, n), rng.uniform(20, h - 20, n)], 1).astype(np.float32)
+    # integer pixel positions so that the (int)-truncated depth lookup is the feature's own depth
+    kp1 = np.floor(kp1).astype(np.float32)
+    Xa = img_a[kp1[:, 1].astype(int), kp1[:, 0].astype(int)].astype(np.float64)
+    Xb = Xa @ R.T + t
+    proj = Xb @ K.T
+    kp2_true = proj[:, :2] / proj[:, 2:3]
+    inside = (kp2_true[:, 0] > 1) & (kp2_true[:, 0] < w - 2) & (kp2_true[:, 1] > 1) & (kp2_true[:, 1] < h - 2)
+    d1 = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    # frame b sees 80 % of the inside points (descriptors with ~10 % flipped bits) plus unrelated features
+    seen = np.nonzero(inside)[0]
+    seen = seen[rng.random(seen.size) < 0.8]
+    flip = rng.integers(0, 256, (seen.size, 32), dtype=np.uint8) & rng.integers(0, 256, (seen.size, 32), dtype=np.uint8) & rng.integers(0, 256, (seen.size, 32), dtype=np.uint8)
+    kp2 = np.concatenate([kp2_true[seen] + rng.normal(0, 0.15, (seen.size, 2)), np.stack([rng.uniform(0, w - 1, 700), rng.uniform(0, h - 1, 700)], 1)]).astype(np.float32)
+    d2 = np.concatenate([d1[seen] ^ flip, rng.integers(0, 256, (700, 32), dtype=np.uint8)])
+    perm = rng.permutation(kp2.shape[0])
+    kp2, d2 = kp2[perm], d2[perm]
+    # frame b's own 3-D image (for Option C): depth of the scene seen from b is not analytic; give b a 3-D image that is
+    # exact at the feature positions
+    img_b = np.zeros((h, w, 3), dtype=np.float32)
+    img_b[..., 2] = 50.0  # outside the gate everywhere else
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    pos = kp2[inv[: seen.size]]
+    img_b[pos[:, 1].astype(int), pos[:, 0].astype(int)] = Xb[seen].astype(np.float32)
+
+    fe = FrontEnd(max_pairs=1, max_features=4000)
+    r = fe.match_gms([kp1], [d1], [kp2], [d2], (w, h), (w, h))[0]
+    assert r["n_inliers"] > 800  # pf_matches > 800 is what makeLoopEdgeMsgWithConsistencyCheck asks for
+    uv_a, uv_b, X = fe.make_3d_2d_collection(K, img_a[None])[0]
+    assert X.shape[0] > 800
+    pb = PnpBatch(max_candidates=1, max_points_total=5000, max_hypotheses=50)
+    out = pb.solve([X], [uv_b], default_params(seed=5))
+    T = out["T"][0]
+    Ttrue = np.eye(4)
+    Ttrue[:3, :3], Ttrue[:3, 3] = R, t
+    e_rot, e_t = dls_pnp.pose_error(T, Ttrue)
+    assert out["confidence"][0] > 0.9 and e_rot < 1e-3 and e_t < 1e-2, (e_rot, e_t, out["confidence"][0])
+    P, Q = fe.make_3d_3d_collection(img_a[None], img_b[None])[0]
+    assert P.shape[0] > 500
+    icp = pb.icp([P], [Q], default_params(seed=6, error_thresh=0.1))
+    e_rot_c, e_t_c = dls_pnp.pose_error(icp["T"][0], Ttrue)
+    assert e_rot_c < 5e-3 and e_t_c < 3e-2, (e_rot_c, e_t_c)
+    fe.close()
+    pb.close()

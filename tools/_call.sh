@@ -1,8 +1,2 @@
 mkdir -p gpurun_out
-for c in 16 32 64; do
-CB_DESC_CHUNK=$c timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-for l in sys.stdin:
-    if l.startswith('{'):
-        b=json.loads(l);print('chunk $c', b['value'],b['e2e']['value'])"
-done
+timeout 600 python -m pytest tests/test_frontend.py -m gpu -x -q > gpurun_out/c17_pytest.log 2>&1; echo "pytest exit $?"; tail -25 gpurun_out/c17_pytest.log
