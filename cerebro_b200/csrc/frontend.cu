@@ -9,8 +9,9 @@
 //   make_3d_3d_collection__using__pfmatches_and_disparity                       :158-196
 // ORB detection and the stereo block matcher stay OpenCV's on the host.
 //
-// Kernels (integer / byte work; nothing here is a GEMM)
-//   hamming_match_kernel : thread = one query descriptor (8 x u32 in registers); the CTA stages 256 train descriptors at a
+// Kernels
+//   hamming_tc_kernel    : the all-pairs Hamming distance as a binary GEMM on tcgen05 (kind::i8), see below; default
+//   hamming_match_kernel : CUDA-core version (CB_MATCH_SIMT=1): thread = one query descriptor (8 x u32 in registers); the CTA stages 256 train descriptors at a
 //                          time in shared memory and every thread scans them with broadcast 128-bit loads, xor + popc.
 //                          The train set is split over gridDim.y; partial minima meet in a packed 64-bit atomicMin
 //                          (distance << 32 | train index), which also reproduces OpenCV's first-minimum tie rule.
@@ -22,6 +23,7 @@
 //   collect_kernel       : one CTA per pair: stable compaction of the GMS inliers (match order), K^-1 normalisation,
 //                          (int)-truncated depth-image lookup, 0.1 m <= z <= 25 m gate.
 #include "common.cuh"
+#include "ptx.cuh"
 
 #include <stdlib.h>
 
@@ -76,6 +78,175 @@ hamming_match_kernel(const uint32_t* __restrict__ d1, const uint32_t* __restrict
   }
   if (active && best_d != 0xffffffffu)
     atomicMin(best + q0 + qi, ((unsigned long long)best_d << 32) | (unsigned long long)best_i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core matcher.  For bit vectors  hamming(a, b) = |a| + |b| - 2 a.b, and a.b over all query x train pairs is a
+// GEMM: the descriptors are expanded once to one byte per bit (0 / 1), and  [128 queries x 256] x [256 x 256 train]
+// tiles run as tcgen05.mma.kind::i8 (unsigned 8-bit operands, exact s32 accumulators in TMEM).  The popc pipe
+// bounds the SIMT kernel (8 xor + 8 popc per pair of descriptors); here the per-pair work left for the CUDA cores is one
+// integer multiply-add and one compare in the epilogue.
+//   CTA = 192 threads: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue (thread = one query row = one TMEM lane).
+//   The 32 KB query tile stays resident; 64 KB train tiles (2 K blocks of 256 rows x 128 B, 128-byte swizzle) stream through
+//   a 2-stage ring; two 256-column accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+//   gridDim = (query tiles, train splits, pairs); partial minima meet in the same packed 64-bit atomicMin as the SIMT kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHtThreads = 192;
+constexpr int kHtM = 128, kHtN = 256;
+constexpr int kHtABytes = 2 * kHtM * 128;  // both K blocks of the query tile
+constexpr int kHtBBytes = 2 * kHtN * 128;  // both K blocks of one train tile
+constexpr int kHtSmem = kHtABytes + 2 * kHtBBytes + 1024 + 256 + 2 * kHtN * 4;
+
+// descriptor bits -> one byte per bit, |d| -> pop[]
+__global__ void expand_bits_kernel(const uint32_t* __restrict__ d, int n, uint8_t* __restrict__ e, int* __restrict__ pop) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one 32-bit word -> 32 bytes
+  const bool valid = i < n * kDescWords;                // no early exit: the warp shuffles below need every lane
+  const uint32_t w = valid ? d[i] : 0u;
+  uint32_t o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t nib = (w >> (4 * j)) & 0xfu;
+    o[j] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+  }
+  if (valid) {
+    uint4* dst = reinterpret_cast<uint4*>(e + (size_t)i * 32);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+  // eight consecutive threads hold one descriptor
+  int c = __popc(w);
+  c += __shfl_xor_sync(FULL, c, 1);
+  c += __shfl_xor_sync(FULL, c, 2);
+  c += __shfl_xor_sync(FULL, c, 4);
+  if (valid && (i & 7) == 0) pop[i >> 3] = c;
+}
+
+__global__ void __launch_bounds__(kHtThreads, 1)
+hamming_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmT, const int* __restrict__ off1,
+                  const int* __restrict__ off2, const int* __restrict__ pop1, const int* __restrict__ pop2, int tiles_per_split,
+                  unsigned long long* __restrict__ best) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kHtABytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + 2 * kHtBBytes);
+  uint64_t* full = a_full + 1;         // [2]
+  uint64_t* empty = full + 2;          // [2]
+  uint64_t* tmem_full_bar = empty + 2;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  int* nb_s = reinterpret_cast<int*>(sB + 2 * kHtBBytes + 256);  // [2][kHtN] |train descriptor|, huge beyond the pair's set
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.z;
+  const int q0 = off1[pair], n1 = off1[pair + 1] - q0;
+  const int t0 = off2[pair], n2 = off2[pair + 1] - t0;
+  const int m0 = blockIdx.x * kHtM;
+  const int n_tiles_all = (n2 + kHtN - 1) / kHtN;
+  const int tile_begin = blockIdx.y * tiles_per_split;
+  const int tile_end = min(tile_begin + tiles_per_split, n_tiles_all);
+  if (m0 >= n1 || tile_begin >= tile_end) return;  // CTA-uniform
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmT);
+    mbar_init(a_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(a_full, kHtABytes);
+      tma_load_2d(&tmQ, a_full, sA, 0, q0 + m0);
+      tma_load_2d(&tmQ, a_full, sA + kHtM * 128, 128, q0 + m0);
+      uint32_t g = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++g) {
+        const int st = g & 1;
+        mbar_wait(&empty[st], ((g >> 1) & 1) ^ 1);
+        mbar_expect_tx(&full[st], kHtBBytes);
+        uint8_t* dst = sB + st * kHtBBytes;
+        tma_load_2d(&tmT, &full[st], dst, 0, t0 + tile * kHtN);
+        tma_load_2d(&tmT, &full[st], dst + kHtN * 128, 128, t0 + tile * kHtN);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D = s32, A = B = unsigned 8-bit, both K-major, N = 256, M = 128
+      const uint32_t idesc = (2u << 4) | ((uint32_t)(kHtN >> 3) << 17) | ((uint32_t)(kHtM >> 4) << 24);
+      mbar_wait(a_full, 0);
+      tc_fence_after();
+      uint32_t g = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++g) {
+        const int st = g & 1, acc = g & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((g >> 1) & 1) ^ 1);
+        mbar_wait(&full[st], (g >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB + st * kHtBBytes);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_i8(tmem_base + acc * kHtN, make_kmajor_desc<128>(a_addr + kb * kHtM * 128 + k * 32),
+                    make_kmajor_desc<128>(b_addr + kb * kHtN * 128 + k * 32), idesc, (kb | k) ? 1u : 0u);
+        umma_commit(&empty[st]);
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    const int qtr = warp & 3;
+    const int et = threadIdx.x - 64;  // 0..127
+    const int row = m0 + qtr * 32 + lane;
+    int best_h = 0x7fffffff, best_i = 0;
+    uint32_t g = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++g) {
+      const int acc = g & 1;
+      int* nb = nb_s + acc * kHtN;
+      for (int c = et; c < kHtN; c += 128) {
+        const int col = tile * kHtN + c;
+        nb[c] = col < n2 ? pop2[t0 + col] : (1 << 24);  // columns beyond the pair's train set never win
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tmem_full_bar[acc], (g >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < kHtN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + acc * kHtN + c + ((uint32_t)(qtr * 32) << 16), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int h = nb[c + j] - 2 * (int)v[j];  // + |query| at the end
+          if (h < best_h) {  // strict and in ascending column order: the first minimum wins
+            best_h = h;
+            best_i = tile * kHtN + c + j;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+    if (row < n1 && best_h < (1 << 23)) {
+      const unsigned long long key = ((unsigned long long)(unsigned)(best_h + pop1[q0 + row]) << 32) | (unsigned long long)(unsigned)best_i;
+      atomicMin(best + q0 + row, key);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
 }
 
 __global__ void unpack_matches_kernel(const unsigned long long* __restrict__ best, int n, int* __restrict__ train_idx,
@@ -334,6 +505,14 @@ struct cb_frontend {
   int* off1 = nullptr;
   int* off2 = nullptr;
   unsigned long long* best = nullptr;
+  // tensor-core matcher: descriptors expanded to one byte per bit + their popcounts (CB_MATCH_SIMT=1 keeps the popc kernel)
+  bool match_simt = false;
+  uint8_t* e1 = nullptr;
+  uint8_t* e2 = nullptr;
+  int* pop1 = nullptr;
+  int* pop2 = nullptr;
+  CUtensorMap tmQ, tmT;
+  int sm_count = 0;
   int* train_idx = nullptr;
   int* dist = nullptr;
   unsigned char* mask = nullptr;
@@ -361,11 +540,15 @@ int cb_frontend_create(cb_frontend** out, int max_pairs, int max_features, int d
   *out = nullptr;
   if (max_pairs < 1 || max_features < 1 || max_features > 16384)
     return cb::fail(CB_EINVAL, "max_pairs must be >= 1 and max_features in [1, 16384]");
-  int rc = cb::select_device(device, nullptr);
+  int sm_count = 0;
+  int rc = cb::select_device(device, &sm_count);
   if (rc) return rc;
   cb::DeviceGuard g(device);
   cb_frontend* f = new cb_frontend();
   f->device = device;
+  f->sm_count = sm_count;
+  const char* env = getenv("CB_MATCH_SIMT");
+  f->match_simt = env && env[0] == '1';
   f->max_pairs = max_pairs;
   f->max_features = max_features;
   const size_t tot = (size_t)max_pairs * max_features;
@@ -380,6 +563,12 @@ int cb_frontend_create(cb_frontend** out, int max_pairs, int max_features, int d
   A((void**)&f->off1, (size_t)(max_pairs + 1) * 4);
   A((void**)&f->off2, (size_t)(max_pairs + 1) * 4);
   A((void**)&f->best, tot * 8);
+  if (!f->match_simt) {
+    A((void**)&f->e1, tot * 256);
+    A((void**)&f->e2, tot * 256);
+    A((void**)&f->pop1, tot * 4);
+    A((void**)&f->pop2, tot * 4);
+  }
   A((void**)&f->train_idx, tot * 4);
   A((void**)&f->dist, tot * 4);
   A((void**)&f->mask, tot);
@@ -396,6 +585,16 @@ int cb_frontend_create(cb_frontend** out, int max_pairs, int max_features, int d
     cb_frontend_destroy(f);
     return cb::fail(CB_ENOMEM, "front-end allocation failed: %s", cudaGetErrorString(e));
   }
+  if (!f->match_simt) {
+    rc = make_map_2d_u8(&f->tmQ, f->e1, (uint64_t)tot, 256, kHtM);
+    if (!rc) rc = make_map_2d_u8(&f->tmT, f->e2, (uint64_t)tot, 256, kHtN);
+    if (!rc && cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHtSmem) != cudaSuccess)
+      rc = cb::fail(CB_ECUDA, "cannot reserve %d bytes of shared memory for hamming_tc_kernel", kHtSmem);
+    if (rc) {
+      cb_frontend_destroy(f);
+      return rc;
+    }
+  }
   *out = f;
   return CB_OK;
 }
@@ -405,7 +604,7 @@ int cb_frontend_destroy(cb_frontend* f) {
   cb::DeviceGuard g(f->device);
   if (f->stream) cudaStreamSynchronize(f->stream);
   void* ps[] = {f->d1, f->d2, f->kp1, f->kp2, f->off1, f->off2, f->best, f->train_idx, f->dist, f->mask, f->n_inl,
-                f->X,  f->uv, f->uvd, f->Y,   f->Kinv, f->count, f->img_a, f->img_b};
+                f->X,  f->uv, f->uvd, f->Y,   f->Kinv, f->count, f->img_a, f->img_b, f->e1, f->e2, f->pop1, f->pop2};
   for (void* p : ps)
     if (p) cudaFree(p);
   for (cudaEvent_t ev : f->ev)
@@ -444,7 +643,20 @@ int cb_frontend_match_gms(cb_frontend* f, int n_pairs, const int32_t* off1, cons
   if (tot1) {
     CB_CUDA(cudaEventRecord(f->ev[0], st));
     CB_CUDA(cudaMemsetAsync(f->best, 0xff, (size_t)tot1 * 8, st));
-    if (max2 > 0) {
+    if (max2 > 0 && !f->match_simt) {
+      expand_bits_kernel<<<(unsigned)((tot1 * kDescWords + 255) / 256), 256, 0, st>>>(f->d1, tot1, f->e1, f->pop1);
+      CB_LAUNCH_CHECK();
+      expand_bits_kernel<<<(unsigned)((tot2 * kDescWords + 255) / 256), 256, 0, st>>>(f->d2, tot2, f->e2, f->pop2);
+      CB_LAUNCH_CHECK();
+      const int m_tiles = (max1 + kHtM - 1) / kHtM, n_tiles = (max2 + kHtN - 1) / kHtN;
+      // split the train tiles over gridDim.y until the grid fills the machine about twice
+      int splits = 1;
+      while (splits < n_tiles && (long long)m_tiles * n_pairs * splits < 2LL * f->sm_count) ++splits;
+      const int tiles_per_split = (n_tiles + splits - 1) / splits;
+      dim3 grid((unsigned)m_tiles, (unsigned)((n_tiles + tiles_per_split - 1) / tiles_per_split), (unsigned)n_pairs);
+      hamming_tc_kernel<<<grid, kHtThreads, kHtSmem, st>>>(f->tmQ, f->tmT, f->off1, f->off2, f->pop1, f->pop2, tiles_per_split, f->best);
+      CB_LAUNCH_CHECK();
+    } else if (max2 > 0) {
       dim3 grid((unsigned)((max1 + kMatchThreads - 1) / kMatchThreads), (unsigned)((max2 + kTrainChunk - 1) / kTrainChunk),
                 (unsigned)n_pairs);
       hamming_match_kernel<<<grid, kMatchThreads, 0, st>>>(f->d1, f->d2, f->off1, f->off2, f->best);

@@ -85,8 +85,12 @@ def test_collection_builders_gate_depth_and_truncate():
 
 # ------------------------------------------------------------------ CUDA path vs oracle (GPU)
 @pytest.mark.gpu
-def test_device_match_gms_matches_golden_and_oracle(native_lib, cuda_device):
+@pytest.mark.parametrize("simt", ["0", "1"])
+def test_device_match_gms_matches_golden_and_oracle(native_lib, cuda_device, monkeypatch, simt):
+    """simt=0: tcgen05 int8 binary-GEMM matcher (default); simt=1: the popc kernel (CB_MATCH_SIMT=1).  Bit-exact both."""
     from cerebro_b200.frontend import FrontEnd
+
+    monkeypatch.setenv("CB_MATCH_SIMT", simt)
 
     g = golden_io.load("gms_golden.npz")
     fe = FrontEnd(max_pairs=8, max_features=3000)
