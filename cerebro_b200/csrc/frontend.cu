@@ -286,11 +286,14 @@ __device__ __forceinline__ int nb9(int cell, int k) {
   return (x < 0 || x >= kGrid || y < 0 || y >= kGrid) ? -1 : x + y * kGrid;
 }
 
-// one CTA per pair.  Shared memory: rg[nm] u16 | sorted[nm] u16 | lgm[nm] i16 | count[400] | start[401] | cursor[400] | pairc[400]
+// grid (pairs, 4): one CTA per (pair, shifted grid) -- the four grid types of gms_matcher::run only meet in the OR of their
+// inlier marks, so they run in parallel; `mask` is zeroed beforehand, every CTA stores 1s, and the last of a pair's four
+// CTAs to finish (ticket counter) counts the inliers.
+// Shared memory: rg[nm] u16 | sorted[nm] u16 | lgm[nm] i16 | count[400] | start[401] | cursor[400] | pairc[400]
 __global__ void __launch_bounds__(kGmsThreads)
 gms_kernel(const float* __restrict__ kp1, const float* __restrict__ kp2, const int* __restrict__ off1, const int* __restrict__ off2,
            const int* __restrict__ train_idx, int w1, int h1, int w2, int h2, int max_nm, unsigned char* __restrict__ mask,
-           int* __restrict__ n_inliers) {
+           int* __restrict__ n_inliers, unsigned int* __restrict__ tickets) {
   extern __shared__ unsigned char gsm[];
   unsigned short* rg = reinterpret_cast<unsigned short*>(gsm);
   unsigned short* sorted = rg + max_nm;
@@ -300,6 +303,7 @@ gms_kernel(const float* __restrict__ kp1, const float* __restrict__ kp2, const i
   int* cursor = start + kCells + 1;
   int* pairc = cursor + kCells;
   __shared__ int s_total;
+  __shared__ unsigned int s_ticket;
   const int pair = blockIdx.x;
   const int q0 = off1[pair], nm = off1[pair + 1] - q0;  // one match per query descriptor
   const int t0 = off2[pair];
@@ -320,9 +324,9 @@ gms_kernel(const float* __restrict__ kp1, const float* __restrict__ kp2, const i
       if (g >= 0 && g < kCells && x >= 0 && x < kGrid) r = (unsigned short)g;
     }
     rg[i] = r;
-    mask[q0 + i] = 0;
   }
-  for (int type = 1; type <= 4; ++type) {
+  {
+    const int type = (int)blockIdx.y + 1;
     for (int i = tid; i < kCells; i += kGmsThreads) count[i] = 0, cursor[i] = 0;
     __syncthreads();
     // AssignMatchPairs, gms_matcher.cpp:75-100
@@ -395,17 +399,27 @@ gms_kernel(const float* __restrict__ kp1, const float* __restrict__ kp2, const i
       const int lg = lgm[i];
       if (lg >= 0 && rg[i] != kBad && pairc[lg] == (int)rg[i]) mask[q0 + i] = 1;
     }
-    __syncthreads();
   }
-  if (tid == 0) s_total = 0;
+  // the last of the pair's CTAs counts the union of the four grids' marks
+  __threadfence();
   __syncthreads();
+  if (tid == 0) {
+    s_ticket = atomicAdd(&tickets[pair], 1u);
+    s_total = 0;
+  }
+  __syncthreads();
+  if (s_ticket != gridDim.y - 1) return;
+  __threadfence();
   int c = 0;
-  for (int i = tid; i < nm; i += kGmsThreads) c += mask[q0 + i];
+  for (int i = tid; i < nm; i += kGmsThreads) c += __ldcg(mask + q0 + i);
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
   if (lane == 0) atomicAdd(&s_total, c);
   __syncthreads();
-  if (tid == 0) n_inliers[pair] = s_total;
+  if (tid == 0) {
+    n_inliers[pair] = s_total;
+    tickets[pair] = 0;  // ready for the next launch
+  }
 }
 
 // One CTA per pair.  Walks the matches in order, 256 at a time, and appends the kept ones (ballot + prefix) so the output
@@ -517,6 +531,7 @@ struct cb_frontend {
   int* dist = nullptr;
   unsigned char* mask = nullptr;
   int* n_inl = nullptr;
+  unsigned int* tickets = nullptr;
   double* X = nullptr;
   double* uv = nullptr;
   double* uvd = nullptr;
@@ -573,6 +588,8 @@ int cb_frontend_create(cb_frontend** out, int max_pairs, int max_features, int d
   A((void**)&f->dist, tot * 4);
   A((void**)&f->mask, tot);
   A((void**)&f->n_inl, (size_t)max_pairs * 4);
+  A((void**)&f->tickets, (size_t)max_pairs * 4);
+  if (e == cudaSuccess) e = cudaMemset(f->tickets, 0, (size_t)max_pairs * 4);
   A((void**)&f->X, tot * 24);
   A((void**)&f->uv, tot * 16);
   A((void**)&f->uvd, tot * 16);
@@ -604,7 +621,7 @@ int cb_frontend_destroy(cb_frontend* f) {
   cb::DeviceGuard g(f->device);
   if (f->stream) cudaStreamSynchronize(f->stream);
   void* ps[] = {f->d1, f->d2, f->kp1, f->kp2, f->off1, f->off2, f->best, f->train_idx, f->dist, f->mask, f->n_inl,
-                f->X,  f->uv, f->uvd, f->Y,   f->Kinv, f->count, f->img_a, f->img_b, f->e1, f->e2, f->pop1, f->pop2};
+                f->X,  f->uv, f->uvd, f->Y,   f->Kinv, f->count, f->img_a, f->img_b, f->e1, f->e2, f->pop1, f->pop2, f->tickets};
   for (void* p : ps)
     if (p) cudaFree(p);
   for (cudaEvent_t ev : f->ev)
@@ -668,8 +685,9 @@ int cb_frontend_match_gms(cb_frontend* f, int n_pairs, const int32_t* off1, cons
   {
     const size_t smem = (size_t)max1 * 6 + 8 + (size_t)(4 * kCells + 1) * 4;
     CB_CUDA(cudaFuncSetAttribute(gms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gms_kernel<<<n_pairs, kGmsThreads, smem, st>>>(f->kp1, f->kp2, f->off1, f->off2, f->train_idx, width1, height1, width2, height2,
-                                                   max1, f->mask, f->n_inl);
+    if (tot1) CB_CUDA(cudaMemsetAsync(f->mask, 0, (size_t)tot1, st));
+    gms_kernel<<<dim3((unsigned)n_pairs, 4), kGmsThreads, smem, st>>>(f->kp1, f->kp2, f->off1, f->off2, f->train_idx, width1, height1,
+                                                                      width2, height2, max1, f->mask, f->n_inl, f->tickets);
     CB_LAUNCH_CHECK();
   }
   if (tot1) {
