@@ -136,7 +136,9 @@ def main():
     traffic = {}
     for n, r in seen.items():
         if n.startswith("scores"):
-            traffic[n + "_dram_bytes_per_launch"] = (get(r, "dram__bytes_read.sum", "MB") + get(r, "dram__bytes_write.sum", "MB")) * 1e6
+            v = (get(r, "dram__bytes_read.sum", "MB") + get(r, "dram__bytes_write.sum", "MB")) * 1e6
+            traffic[n + "_dram_bytes_per_launch"] = v
+            traffic.setdefault(re.sub(r"<.*$", "", n) + "_dram_bytes_per_launch", v)  # template arguments stripped
     json.dump(traffic, open(os.path.join(dst, rnd + "_traffic.json"), "w"), indent=1)
     shutil.copy(os.path.join(src, tag + "_launches.csv"), os.path.join(dst, rnd + "_launches.csv"))
     shutil.copy(os.path.join(src, tag + "_prof_raw.csv"), os.path.join(dst, rnd + "_ncu_full_raw.csv"))
