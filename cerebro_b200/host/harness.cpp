@@ -23,6 +23,8 @@ struct Cbw {
   std::vector<std::vector<int>> shapes;
   std::vector<std::vector<float>> data;
   std::vector<int> strides;
+  std::vector<int> residual;  // MobileNetV2 containers: Add flag per inverted-residual block
+  bool v2 = false;            // header "arch": "mobilenetv2"
   const std::vector<float>* get(const std::string& n, std::vector<int>* shape = nullptr) const {
     for (size_t i = 0; i < names.size(); ++i)
       if (names[i] == n) {
@@ -56,9 +58,15 @@ bool load_cbw(const char* path, Cbw& w) {
   if (std::memcmp(magic, "CBW1", 4) != 0) return false;
   std::string h(hl, '\0');
   f.read(&h[0], hl);
+  w.v2 = h.find("\"arch\": \"mobilenetv2\"") != std::string::npos;
   size_t p = h.find("\"strides\"");
   p = h.find('[', p);
   w.strides = parse_int_list(h, p);
+  if (w.v2) {
+    p = h.find("\"residual\"");
+    p = h.find('[', p);
+    w.residual = parse_int_list(h, p);
+  }
   p = h.find("\"arrays\"");
   p = h.find('[', p) + 1;  // inside the outer list
   while (true) {
@@ -98,9 +106,50 @@ int main(int argc, char** argv) {
   }
   const int n = std::atoi(argv[3]), rows = std::atoi(argv[4]), cols = std::atoi(argv[5]), chnls = std::atoi(argv[6]);
   const int nb = (int)w.strides.size();
+  cb_descriptor* desc = nullptr;
+  std::vector<cb_ir_block> irb;
+  if (w.v2) {  // June2019 MobileNetV2 models: inverted-residual blocks through cb_descriptor_create_v2
+    int c_in = 32;
+    for (int i = 0; i < nb; ++i) {
+      const std::string b = "b" + std::to_string(i) + "_";
+      std::vector<int> sh;
+      cb_ir_block blk;
+      std::memset(&blk, 0, sizeof(blk));
+      const std::vector<float>* ew = w.get(b + "expand_w");
+      blk.expand_w = ew ? ew->data() : nullptr;
+      blk.expand_b = ew ? w.get(b + "expand_b")->data() : nullptr;
+      blk.dw_w = w.get(b + "dw_w", &sh)->data();
+      blk.dw_b = w.get(b + "dw_b")->data();
+      blk.c_exp = sh[2];
+      blk.project_w = w.get(b + "project_w", &sh)->data();
+      blk.project_b = w.get(b + "project_b")->data();
+      blk.c_out = sh[1];
+      blk.c_in = c_in;
+      blk.stride = w.strides[i];
+      blk.residual = w.residual[i];
+      c_in = blk.c_out;
+      irb.push_back(blk);
+    }
+    cb_netvlad_v2_weights w2;
+    std::vector<int> c1sh, vsh2;
+    w2.conv1_w = w.get("conv1_w", &c1sh)->data();
+    w2.in_channels = c1sh[2];
+    w2.conv1_b = w.get("conv1_b")->data();
+    w2.n_blocks = nb;
+    w2.blocks = irb.data();
+    w2.vlad_w = w.get("vlad_w", &vsh2)->data();
+    w2.vlad_d = vsh2[0];
+    w2.vlad_k = vsh2[1];
+    w2.vlad_b = w.get("vlad_b")->data();
+    w2.vlad_c = w.get("vlad_c")->data();
+    if (cb_descriptor_create_v2(&desc, &w2, rows, cols, chnls, 1, 0) != CB_OK) {
+      std::fprintf(stderr, "cb_descriptor_create_v2: %s\n", cb_last_error());
+      return 1;
+    }
+  }
   std::vector<const float*> dw_w(nb), dw_b(nb), pw_w(nb), pw_b(nb);
   std::vector<int> cout(nb);
-  for (int i = 0; i < nb; ++i) {
+  for (int i = 0; i < nb && !w.v2; ++i) {
     std::vector<int> sh;
     dw_w[i] = w.get("b" + std::to_string(i) + "_dw_w", &sh)->data();
     dw_b[i] = w.get("b" + std::to_string(i) + "_dw_b")->data();
@@ -129,8 +178,7 @@ int main(int argc, char** argv) {
   nw.vlad_b = w.get("vlad_b")->data();
   nw.vlad_c = w.get("vlad_c")->data();
 
-  cb_descriptor* desc = nullptr;
-  if (cb_descriptor_create(&desc, &nw, rows, cols, chnls, 1, 0) != CB_OK) {
+  if (!w.v2 && cb_descriptor_create(&desc, &nw, rows, cols, chnls, 1, 0) != CB_OK) {
     std::fprintf(stderr, "cb_descriptor_create: %s\n", cb_last_error());
     return 1;
   }

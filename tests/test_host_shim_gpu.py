@@ -20,15 +20,16 @@ def test_harness_binary_links_on_cpu(native_lib):
 
 
 @pytest.mark.gpu
-def test_cpp_shim_stream_matches_oracle(native_lib, cuda_device, tmp_path):
+@pytest.mark.parametrize("model,dim", [("gray_conv6", 4096), ("mobilenetv2_block9_gray", 1024)])
+def test_cpp_shim_stream_matches_oracle(native_lib, cuda_device, tmp_path, model, dim):
     from cerebro_b200 import build, keras_weights
     from oracle import dls_pnp as D
     from oracle import netvlad as NV
     from oracle.search import naive_stream
 
-    raw = golden_io.raw_weights("gray_conv6")
+    raw = golden_io.raw_weights(model)
     wpath = str(tmp_path / "gray.cbw")
-    keras_weights.save_cbw(wpath, keras_weights.fold_mobilenet_netvlad(raw))
+    keras_weights.save_cbw(wpath, keras_weights.fold_model(raw))  # either architecture; the harness reads the header's "arch"
     rows, cols, n = 96, 128, 90
     places = synth.band_limited_images(60, rows, cols, 1, seed=50)
     rng = np.random.default_rng(51)
@@ -46,7 +47,7 @@ def test_cpp_shim_stream_matches_oracle(native_lib, cuda_device, tmp_path):
     r = subprocess.run([build.HARNESS, wpath, ipath, str(n), str(rows), str(cols), "1", ppath, "180"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     out = json.loads(r.stdout.strip().splitlines()[-1])
-    assert out["descriptor_size"] == 4096 and out["n_computed"] == n
+    assert out["descriptor_size"] == dim and out["n_computed"] == n
     desc = NV.describe(imgs, raw, dtype="float32").astype(np.float64)
     expected = naive_stream(desc, list(range(3, n + 1, 3)))
     assert len(expected) >= 5
