@@ -218,7 +218,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner (NCCL_DEBUG=VERSION) to stdout; keep stdout for the one JSON line
+        # NCCL_DEBUG=VERSION makes NCCL printf its version banner to stdout (NCCL_DEBUG_FILE does not move it); keep stdout
+        # for the one JSON line.  Any other level (INFO, WARN ...) is the caller's choice and stays, routed to stderr.
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
