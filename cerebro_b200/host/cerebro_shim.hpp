@@ -167,8 +167,24 @@ class Cerebro {
       if (!node->isKeyFrame() || node->isWholeImageDescriptorAvailable()) continue;  // :189
       if (last_processed_set_ && !(last_processed_ < kv.first)) continue;
       if (node->getNumberOfSuccessfullyTrackedFeatures() < 20) continue;  // :206-210
-      if ((int)node->left_image.size() != rows_ * cols_ * chnls_) continue;
-      const int rc = cb_descriptor_compute(desc_, 1, node->left_image.data(), 0, out.data());  // replaces client.call(srv), :263
+      // :229-234: the stored image may have the other channel count (CV_GRAY2BGR replicates, CV_BGR2GRAY is OpenCV 4's 8-bit
+      // fixed point (3735 B + 19235 G + 9798 R + 2^14) >> 15; OpenCV 3 used (1868, 9617, 4899) >> 14, at most one level off)
+      const size_t px = (size_t)rows_ * cols_;
+      const uint8_t* img = node->left_image.data();
+      std::vector<uint8_t> conv;
+      if (node->left_image.size() == px && chnls_ == 3) {
+        conv.resize(px * 3);
+        for (size_t i = 0; i < px; ++i) conv[3 * i] = conv[3 * i + 1] = conv[3 * i + 2] = img[i];
+        img = conv.data();
+      } else if (node->left_image.size() == px * 3 && chnls_ == 1) {
+        conv.resize(px);
+        for (size_t i = 0; i < px; ++i)
+          conv[i] = (uint8_t)((3735 * (int)img[3 * i] + 19235 * (int)img[3 * i + 1] + 9798 * (int)img[3 * i + 2] + 16384) >> 15);
+        img = conv.data();
+      } else if (node->left_image.size() != px * (size_t)chnls_) {
+        continue;
+      }
+      const int rc = cb_descriptor_compute(desc_, 1, img, 0, out.data());  // replaces client.call(srv), :263
       if (rc != CB_OK) {
         std::fprintf(stderr, "[descriptor_computer_thread] %s\n", cb_last_error());  // ROS_ERROR and continue, :288-290
         continue;

@@ -92,6 +92,31 @@ class ProcessedLoopCandidate:
         return None
 
 
+# cv::cvtColor(CV_BGR2GRAY) on 8-bit images is fixed point: OpenCV 4 uses 15 bits, (3735 B + 19235 G + 9798 R + 2^14) >> 15
+# (bit-exact against the installed cv2, tests/test_host_logic.py); OpenCV 3 -- the reference's era -- used 14 bits,
+# (1868 B + 9617 G + 4899 R + 2^13) >> 14, which differs by one grey level on ~0.2 % of the pixels.
+_BGR2GRAY = {15: (3735, 19235, 9798), 14: (1868, 9617, 4899)}
+
+
+def convert_channels(images_u8: np.ndarray, n_channels: int, fixed_point_bits: int = 15) -> np.ndarray:
+    """The channel fix-up the descriptor thread applies before the service call (Cerebro.cpp:229-234): a 1-channel image
+    for a 3-channel model goes through ``cv::cvtColor(CV_GRAY2BGR)`` (replicate), a 3-channel (BGR) image for a
+    1-channel model through ``cv::cvtColor(CV_BGR2GRAY)`` (fixed point, see above) -- anything else passes through.
+    [n, rows, cols(, c)] uint8 in, [n, rows, cols, n_channels] out."""
+    x = np.asarray(images_u8)
+    if x.ndim == 3:
+        x = x[..., None]
+    assert x.dtype == np.uint8 and x.ndim == 4
+    c = x.shape[3]
+    if n_channels == 3 and c == 1:
+        return np.ascontiguousarray(np.repeat(x, 3, axis=3))
+    if n_channels == 1 and c == 3:
+        cb, cg, cr = _BGR2GRAY[fixed_point_bits]
+        b, g, r = (x[..., i].astype(np.int64) for i in range(3))
+        return ((cb * b + cg * g + cr * r + (1 << (fixed_point_bits - 1))) >> fixed_point_bits).astype(np.uint8)[..., None]
+    return np.ascontiguousarray(x)
+
+
 class Hypothesis:
     """HypothesisManager.h:26-131: a chain of (a, b, dot product) nodes with a time-to-live."""
 
@@ -215,7 +240,11 @@ class Cerebro:
         keep = [i for i in range(len(stamps)) if n_tracked is None or n_tracked[i] >= 20]
         if not keep:
             return 0
-        desc = self.descriptor.compute(np.ascontiguousarray(images_u8[keep]))
+        imgs = np.asarray(images_u8)[keep]
+        n_ch = getattr(self.descriptor, "chnls", None)
+        if n_ch in (1, 3):  # Cerebro.cpp:229-234: gray <-> BGR fix-up when the stored image and the model disagree
+            imgs = convert_channels(imgs, n_ch)
+        desc = self.descriptor.compute(np.ascontiguousarray(imgs))
         self.index.add(desc)
         for i in keep:
             self._whole.append(stamps[i])
