@@ -426,6 +426,7 @@ gms_kernel(const float* __restrict__ kp1, const float* __restrict__ kp2, const i
 // order is the reference's (match order = ascending query index).
 //   mode 0: 3D-2D  (world point of frame a at (int)uv, normalised uv of a and uv_d of b)   PointFeatureMatching.cpp:96-153
 //   mode 1: 3D-3D  (points of both frames, both depths gated)                               PointFeatureMatching.cpp:158-196
+//   mode 2: 3D-2D with the frames' roles swapped (Option B, Cerebro.cpp:1562-1565): world point of frame b at (int)uv_d
 __global__ void __launch_bounds__(256)
 collect_kernel(const float* __restrict__ kp1, const float* __restrict__ kp2, const int* __restrict__ off1, const int* __restrict__ off2,
                const int* __restrict__ train_idx, const unsigned char* __restrict__ mask, const float* __restrict__ img_a,
@@ -436,8 +437,9 @@ collect_kernel(const float* __restrict__ kp1, const float* __restrict__ kp2, con
   const int pair = blockIdx.x;
   const int q0 = off1[pair], nm = off1[pair + 1] - q0, t0 = off2[pair];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* ia = img_a + (size_t)pair * H * W * 3;
+  const float* ia = img_a ? img_a + (size_t)pair * H * W * 3 : nullptr;
   const float* ib = img_b ? img_b + (size_t)pair * H * W * 3 : nullptr;
+  const float* src3d = mode == 2 ? ib : ia;  // the frame whose 3-D image is looked up first
   if (tid == 0) s_base = 0;
   __syncthreads();
   for (int i0 = 0; i0 < nm; i0 += 256) {
@@ -449,9 +451,9 @@ collect_kernel(const float* __restrict__ kp1, const float* __restrict__ kp2, con
       const int t = train_idx[q0 + i];
       u = kp1[2 * (size_t)(q0 + i)], v = kp1[2 * (size_t)(q0 + i) + 1];
       ud = kp2[2 * (size_t)(t0 + t)], vd = kp2[2 * (size_t)(t0 + t) + 1];
-      const int xa = (int)u, ya = (int)v;  // (int)uv(1,k), (int)uv(0,k): truncation, :124
-      if (xa >= 0 && xa < W && ya >= 0 && ya < H) {
-        const float* p = ia + ((size_t)ya * W + xa) * 3;
+      const int xa = (int)(mode == 2 ? ud : u), ya = (int)(mode == 2 ? vd : v);  // (int)uv(1,k), (int)uv(0,k): truncation, :124
+      if (src3d && xa >= 0 && xa < W && ya >= 0 && ya < H) {
+        const float* p = src3d + ((size_t)ya * W + xa) * 3;
         pa = make_float3(p[0], p[1], p[2]);
         keep = !(pa.z < 0.1f || pa.z > 25.f);
       }
@@ -474,7 +476,7 @@ collect_kernel(const float* __restrict__ kp1, const float* __restrict__ kp2, con
     if (keep) {
       const size_t o = (size_t)q0 + pos;  // outputs are laid out per pair at the pair's query offset
       out_X[3 * o] = (double)pa.x, out_X[3 * o + 1] = (double)pa.y, out_X[3 * o + 2] = (double)pa.z;
-      if (mode == 0) {
+      if (mode != 1) {
         // K^-1 [u v 1]^T (stereogeom->get_K().inverse() * uv, :117-118): rows 0 and 1
         out_uv[2 * o] = Kinv[0] * (double)u + Kinv[1] * (double)v + Kinv[2];
         out_uv[2 * o + 1] = Kinv[3] * (double)u + Kinv[4] * (double)v + Kinv[5];
@@ -710,29 +712,31 @@ float cb_frontend_last_match_ms(const cb_frontend* f) { return f ? f->last_match
 
 int cb_frontend_collect(cb_frontend* f, int mode, const float* img3d_a, const float* img3d_b, int rows, int cols,
                         const double* K_inverse, int32_t* counts, double* X, double* uv, double* uv_d, double* Y) {
-  if (!f || !img3d_a || !counts || !X) return cb::fail(CB_EINVAL, "NULL argument to cb_frontend_collect");
+  if (!f || !counts || !X) return cb::fail(CB_EINVAL, "NULL argument to cb_frontend_collect");
   if (!f->have_matches) return cb::fail(CB_EINVAL, "cb_frontend_collect needs a preceding cb_frontend_match_gms on this handle");
-  if (mode != 0 && mode != 1) return cb::fail(CB_EINVAL, "mode must be 0 (3D-2D) or 1 (3D-3D)");
-  if (mode == 0 && (!K_inverse || !uv || !uv_d)) return cb::fail(CB_EINVAL, "3D-2D mode needs K_inverse, uv and uv_d");
-  if (mode == 1 && (!img3d_b || !Y)) return cb::fail(CB_EINVAL, "3D-3D mode needs img3d_b and Y");
+  if (mode < 0 || mode > 2) return cb::fail(CB_EINVAL, "mode must be 0 (3D-2D), 1 (3D-3D) or 2 (3D-2D, frames swapped)");
+  if (mode != 2 && !img3d_a) return cb::fail(CB_EINVAL, "modes 0 and 1 need img3d_a");
+  if (mode != 1 && (!K_inverse || !uv || !uv_d)) return cb::fail(CB_EINVAL, "3D-2D modes need K_inverse, uv and uv_d");
+  if (mode == 1 && !Y) return cb::fail(CB_EINVAL, "3D-3D mode needs Y");
+  if (mode != 0 && !img3d_b) return cb::fail(CB_EINVAL, "modes 1 and 2 need img3d_b");
   if (rows < 1 || cols < 1) return cb::fail(CB_EINVAL, "bad depth-image size");
   cb::DeviceGuard g(f->device);
   cudaStream_t st = f->stream;
   const size_t img_bytes = (size_t)f->n_pairs * rows * cols * 3 * sizeof(float);
-  int rc = grow_dev((void**)&f->img_a, &f->img_bytes_a, img_bytes);
+  int rc = img3d_a ? grow_dev((void**)&f->img_a, &f->img_bytes_a, img_bytes) : CB_OK;
   if (!rc && img3d_b) rc = grow_dev((void**)&f->img_b, &f->img_bytes_b, img_bytes);
   if (rc) return rc;
-  CB_CUDA(cudaMemcpyAsync(f->img_a, img3d_a, img_bytes, cudaMemcpyHostToDevice, st));
+  if (img3d_a) CB_CUDA(cudaMemcpyAsync(f->img_a, img3d_a, img_bytes, cudaMemcpyHostToDevice, st));
   if (img3d_b) CB_CUDA(cudaMemcpyAsync(f->img_b, img3d_b, img_bytes, cudaMemcpyHostToDevice, st));
   if (K_inverse) CB_CUDA(cudaMemcpyAsync(f->Kinv, K_inverse, 9 * sizeof(double), cudaMemcpyHostToDevice, st));
-  collect_kernel<<<f->n_pairs, 256, 0, st>>>(f->kp1, f->kp2, f->off1, f->off2, f->train_idx, f->mask, f->img_a,
+  collect_kernel<<<f->n_pairs, 256, 0, st>>>(f->kp1, f->kp2, f->off1, f->off2, f->train_idx, f->mask, img3d_a ? f->img_a : nullptr,
                                              img3d_b ? f->img_b : nullptr, rows, cols, f->Kinv, mode, f->X, f->uv, f->uvd, f->Y, f->count);
   CB_LAUNCH_CHECK();
   const size_t n = (size_t)f->total1;
   CB_CUDA(cudaMemcpyAsync(counts, f->count, (size_t)f->n_pairs * 4, cudaMemcpyDeviceToHost, st));
   if (n) {
     CB_CUDA(cudaMemcpyAsync(X, f->X, n * 24, cudaMemcpyDeviceToHost, st));
-    if (mode == 0) {
+    if (mode != 1) {
       CB_CUDA(cudaMemcpyAsync(uv, f->uv, n * 16, cudaMemcpyDeviceToHost, st));
       CB_CUDA(cudaMemcpyAsync(uv_d, f->uvd, n * 16, cudaMemcpyDeviceToHost, st));
     } else {

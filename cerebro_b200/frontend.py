@@ -89,11 +89,13 @@ class FrontEnd:
         return np.concatenate([u.T, one]), np.concatenate([ud.T, one])
 
     # ---- set builders over the batch matched last
-    def make_3d_2d_collection(self, K: np.ndarray, img3d_a: np.ndarray):
+    def make_3d_2d_collection(self, K: np.ndarray, img3d: np.ndarray, swapped: bool = False):
         """make_3d_2d_collection__using__pfmatches_and_disparity for every pair of the last ``match_gms`` batch.
-        img3d_a [n_pairs, H, W, 3] float32.  Returns per pair (feature_position_uv [m,2], feature_position_uv_d [m,2],
+        img3d [n_pairs, H, W, 3] float32 = the 3-D image of frame a -- or, with ``swapped=True``, of frame b: the Option-B
+        call ``make_3d_2d_collection(stereogeom, uv_d, b_3dImage, uv, ...)`` of Cerebro.cpp:1562-1565, whose world points
+        come from frame b.  Returns per pair (feature_position_uv [m,2] of frame a, feature_position_uv_d [m,2] of frame b,
         world_point [m,3])."""
-        return self._collect(0, K, img3d_a, None)
+        return self._collect(2, K, None, img3d) if swapped else self._collect(0, K, img3d, None)
 
     def make_3d_3d_collection(self, img3d_a: np.ndarray, img3d_b: np.ndarray):
         """make_3d_3d_collection__using__pfmatches_and_disparity: per pair (uv_X [m,3], uvd_Y [m,3])."""
@@ -102,12 +104,14 @@ class FrontEnd:
     def _collect(self, mode, K, img_a, img_b):
         assert self._off1 is not None, "call match_gms first"
         n = len(self._off1) - 1
-        img_a = np.ascontiguousarray(img_a, dtype=np.float32)
-        assert img_a.ndim == 4 and img_a.shape[0] == n and img_a.shape[3] == 3
-        rows, cols = img_a.shape[1], img_a.shape[2]
+        if img_a is not None:
+            img_a = np.ascontiguousarray(img_a, dtype=np.float32)
+            assert img_a.ndim == 4 and img_a.shape[0] == n and img_a.shape[3] == 3
         if img_b is not None:
             img_b = np.ascontiguousarray(img_b, dtype=np.float32)
-            assert img_b.shape == img_a.shape
+            assert img_b.ndim == 4 and img_b.shape[0] == n and img_b.shape[3] == 3
+            assert img_a is None or img_b.shape == img_a.shape
+        rows, cols = (img_a if img_a is not None else img_b).shape[1:3]
         tot = max(int(self._off1[-1]), 1)
         counts = np.zeros(n, dtype=np.int32)
         X = np.zeros((tot, 3))
@@ -121,7 +125,7 @@ class FrontEnd:
         for p in range(n):
             a = int(self._off1[p])
             m = int(counts[p])
-            if mode == 0:
+            if mode != 1:
                 out.append((uv[a : a + m].copy(), uvd[a : a + m].copy(), X[a : a + m].copy()))
             else:
                 out.append((X[a : a + m].copy(), Y[a : a + m].copy()))

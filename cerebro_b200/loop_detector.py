@@ -92,6 +92,47 @@ class ProcessedLoopCandidate:
         return None
 
 
+def consistent_pose_compute(fe, pnp, K, img3d_a, img3d_b, match_results, stamps, node_indices=None, seed=0):
+    """``Cerebro::process_loop_candidate_imagepair_consistent_pose_compute`` (src/Cerebro.cpp:1414-1771) for a BATCH of
+    loop candidates, from the point where both frames' ORB features and stereo 3-D images exist.
+
+    ``fe`` is a ``FrontEnd`` on which ``match_gms`` has just been called for the batch (``match_results`` = its return
+    value); img3d_a / img3d_b [n, H, W, 3] float32; stamps[p] = (t_a, t_b) in seconds; node_indices[p] = (idx_1, idx_2).
+    Per candidate, as the reference: reject when fewer than 150 GMS matches (:1484-1491); Option A
+    ``PNP(3d(a), uv(b)) -> b_T_a`` (:1514-1522), Option B ``PNP(3d(b), uv(a)) -> a_T_b``, inverted (:1562-1575), Option C
+    ``P3P_ICP(3d(a), 3d(b)) -> b_T_a`` (:1617-1626); reject on NaN (:1672); then
+    ``ProcessedLoopCandidate::makeLoopEdgeMsgWithConsistencyCheck``.  The three solves of the whole batch are two device
+    calls (one PnP batch of 2n candidates, one ICP batch of n).  Returns a list of (ProcessedLoopCandidate | None,
+    LoopEdge | None)."""
+    n = len(match_results)
+    sets_a = fe.make_3d_2d_collection(K, img3d_a)                 # (uv_a, uv_b, X_a)
+    sets_b = fe.make_3d_2d_collection(K, img3d_b, swapped=True)   # (uv_a, uv_b, X_b)
+    sets_c = fe.make_3d_3d_collection(img3d_a, img3d_b)           # (X_a, Y_b)
+    r_pnp = pnp.solve([sa[2] for sa in sets_a] + [sb[2] for sb in sets_b], [sa[1] for sa in sets_a] + [sb[0] for sb in sets_b],
+                      default_params(seed=seed))
+    r_icp = pnp.icp([sc[0] for sc in sets_c], [sc[1] for sc in sets_c], default_params(seed=seed + 1, error_thresh=0.1))
+    out = []
+    for p in range(n):
+        pf = int(match_results[p]["n_inliers"])
+        if pf < 150:  # "too few gms matches ... rejecting this loopcandidate"
+            out.append((None, None))
+            continue
+        op1 = r_pnp["T"][p]
+        op2 = np.linalg.inv(r_pnp["T"][n + p])
+        icp = r_icp["T"][p]
+        if np.isnan(op1).any() or np.isnan(op2).any() or np.isnan(icp).any():
+            out.append((None, None))
+            continue
+        i1, i2 = node_indices[p] if node_indices is not None else (-1, -1)
+        cand = ProcessedLoopCandidate(p, stamps[p][0], stamps[p][1], i1, i2)
+        cand.pf_matches = pf
+        cand.opX_b_T_a = [op1, op2, icp]
+        cand.opX_goodness = [float(r_pnp["confidence"][p]), float(r_pnp["confidence"][n + p]), float(r_icp["confidence"][p])]
+        cand.opX_b_T_a_name = ["op1__b_T_a", "op2__b_T_a", "icp_b_T_a"]
+        out.append((cand, cand.makeLoopEdgeMsgWithConsistencyCheck()))
+    return out
+
+
 # cv::cvtColor(CV_BGR2GRAY) on 8-bit images is fixed point: OpenCV 4 uses 15 bits, (3735 B + 19235 G + 9798 R + 2^14) >> 15
 # (bit-exact against the installed cv2, tests/test_host_logic.py); OpenCV 3 -- the reference's era -- used 14 bits,
 # (1868 B + 9617 G + 4899 R + 2^13) >> 14, which differs by one grey level on ~0.2 % of the pixels.

@@ -298,6 +298,9 @@ CB_API float cb_frontend_last_match_ms(const cb_frontend* f);
  *           X = 3-D point of frame a looked up at ((int)v, (int)u) in img3d_a, kept iff 0.1 <= z <= 25;
  *           uv / uv_d = K^-1 [u v 1]^T of the feature in frame a / b (normalised image coordinates)
  *   mode 1: make_3d_3d_collection__using__pfmatches_and_disparity (:158-196): X from img3d_a, Y from img3d_b, both gated
+ *   mode 2: mode 0 with the frames' roles swapped -- the Option-B call of src/Cerebro.cpp:1562-1565: X = 3-D point of
+ *           frame b looked up at ((int)v_d, (int)u_d) in img3d_b (img3d_a may be NULL); uv / uv_d keep their meaning
+ *           (frame a / frame b), so Option B solves PNP(X, uv) for a_T_b
  *   img3d_a, img3d_b: [n_pairs][rows][cols][3] float32 (the CV_32FC3 "3d image" of the stereo pair); K_inverse 3x3 row-major.
  * Outputs are laid out per pair at the pair's query offset: pair p's kept entries are rows
  * [off1[p], off1[p] + counts[p]) of X [total1][3], uv / uv_d [total1][2], Y [total1][3]. */

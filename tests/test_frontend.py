@@ -222,7 +222,7 @@ def test_candidate_to_pose_chain(native_lib, cuda_device):
     assert r["n_inliers"] > 800  # pf_matches > 800 is what makeLoopEdgeMsgWithConsistencyCheck asks for
     uv_a, uv_b, X = fe.make_3d_2d_collection(K, img_a[None])[0]
     assert X.shape[0] > 800
-    pb = PnpBatch(max_candidates=1, max_points_total=5000, max_hypotheses=50)
+    pb = PnpBatch(max_candidates=2, max_points_total=10000, max_hypotheses=50)
     out = pb.solve([X], [uv_b], default_params(seed=5))
     T = out["T"][0]
     Ttrue = np.eye(4)
@@ -234,5 +234,25 @@ def test_candidate_to_pose_chain(native_lib, cuda_device):
     icp = pb.icp([P], [Q], default_params(seed=6, error_thresh=0.1))
     e_rot_c, e_t_c = dls_pnp.pose_error(icp["T"][0], Ttrue)
     assert e_rot_c < 5e-3 and e_t_c < 3e-2, (e_rot_c, e_t_c)
+    # Option B's set (frames swapped) against the oracle, then the whole a10 orchestration -> a published LoopEdge
+    u, ud = fe.matched_points(0)
+    ud_n, u_n, Xb_o = gms.make_3d_2d_collection(K, ud[:2].T, img_b, u[:2].T)
+    uv_a2, uv_b2, Xb_d = fe.make_3d_2d_collection(K, img_b[None], swapped=True)[0]
+    assert Xb_d.shape == Xb_o.shape and Xb_d.shape[0] > 500 and np.array_equal(Xb_d, Xb_o)
+    assert np.allclose(uv_a2, u_n, rtol=0, atol=1e-12) and np.allclose(uv_b2, ud_n, rtol=0, atol=1e-12)
+    from cerebro_b200.loop_detector import consistent_pose_compute
+
+    cand, edge = consistent_pose_compute(fe, pb, K, img_a[None], img_b[None], [r], [(500.0, 100.0)], [(812, 140)], seed=3)[0]
+    assert cand is not None and cand.pf_matches == r["n_inliers"] and len(cand.opX_b_T_a) == 3
+    for T_op in cand.opX_b_T_a:
+        er, et = dls_pnp.pose_error(T_op, Ttrue)
+        assert er < 5e-3 and et < 3e-2, (er, et)
+    assert edge is not None and edge.timestamp0 == 500.0 and edge.timestamp1 == 100.0
+    assert edge.weight == pytest.approx(max(cand.opX_goodness)) and edge.description.startswith("812<=>140")
+    er, et = dls_pnp.pose_error(edge.pose_1T0, Ttrue)
+    assert er < 1e-3 and et < 1e-2
+    # same candidate seen 5 s apart: the consistency check refuses it (ProcessedLoopCandidate.cpp:49-56)
+    _, edge2 = consistent_pose_compute(fe, pb, K, img_a[None], img_b[None], [r], [(105.0, 100.0)], seed=3)[0]
+    assert edge2 is None
     fe.close()
     pb.close()
