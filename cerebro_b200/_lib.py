@@ -113,6 +113,9 @@ _SIGNATURES = {
     "cb_frontend_destroy": (C.c_int, [_vp]),
     "cb_frontend_match_gms": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "cb_frontend_last_match_ms": (C.c_float, [_vp]),
+    "cb_frontend_stereo_bm": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "cb_frontend_last_stereo_ms": (C.c_float, [_vp]),
+    "cb_frontend_disparity_to_3d": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
     "cb_frontend_collect": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cb_descriptor_create": (C.c_int, [C.POINTER(_vp), C.POINTER(NetvladWeights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "cb_descriptor_create_v2": (C.c_int, [C.POINTER(_vp), C.POINTER(NetvladV2Weights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -12,6 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_native")
 LIB = os.path.join(OUT_DIR, "libcerebro_b200.so")
 HARNESS = os.path.join(OUT_DIR, "cerebro_harness")
+STEREO_EMUL = os.path.join(OUT_DIR, "libstereo_emul.so")
 SOURCES = ["capi.cu", "search.cu", "pnp.cu", "netvlad.cu", "frontend.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -68,6 +69,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("host harness build failed")
+    # CPU emulation of the stereo kernels' thread space over the shared per-thread bodies (tests only, never a fallback)
+    esrc = [os.path.join(host, "stereo_emul.cpp"), os.path.join(CSRC, "stereo_core.h")]
+    if force or _stale(STEREO_EMUL, esrc):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", esrc[0], "-o", STEREO_EMUL]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("stereo emulation build failed")
     return LIB
 
 

@@ -24,6 +24,7 @@
 //                          (int)-truncated depth-image lookup, 0.1 m <= z <= 25 m gate.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "stereo_core.h"
 
 #include <stdlib.h>
 
@@ -497,6 +498,75 @@ collect_kernel(const float* __restrict__ kp1, const float* __restrict__ kp2, con
   if (tid == 0) out_count[pair] = s_base;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stereo block matching (cv::StereoBM::create(ndisp, wsz)->compute, src/utils/CameraGeometry.cpp:81, :410-418) and the
+// reference's disparity -> 3-D image loop (:459-520).  Integer SAD work; the per-thread bodies live in stereo_core.h and
+// are also run on the CPU by host/stereo_emul.cpp.
+//   sbm_prefilter_kernel : thread per pixel (x-Sobel, clamp, row-pair borders)
+//   sbm_hsad_kernel      : grid (column segments, rows, pairs), block = ndisp threads (one candidate each): sliding
+//                          horizontal window sums -> hsad[row][column][candidate] (u16, candidate fastest: coalesced)
+//   sbm_vsad_kernel      : grid (columns, row stripes, pairs), block = ndisp threads: sliding vertical window sums with
+//                          clamped rows; per pixel the candidates' SADs meet in shared memory and thread 0 takes the
+//                          decision (first minimum, texture / uniqueness tests, parabola fit, ROI)
+//   sbm_to3d_kernel      : thread per pixel
+// ---------------------------------------------------------------------------------------------
+constexpr int kSbmSeg = 32;     // output columns per horizontal-pass thread
+constexpr int kSbmStripe = 60;  // rows per vertical-pass block
+
+__global__ void sbm_fill_kernel(int16_t* __restrict__ disp, size_t n, int16_t v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) disp[i] = v;
+}
+
+__global__ void sbm_prefilter_kernel(const uint8_t* __restrict__ img, int n_img, int h, int w, int cap, uint8_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per = (size_t)h * w;
+  if (i >= per * n_img) return;
+  const size_t im = i / per, r = i % per;
+  out[i] = sbm_prefilter_px(img + im * per, h, w, (int)(r / w), (int)(r % w), cap);
+}
+
+__global__ void sbm_hsad_kernel(const uint8_t* __restrict__ PL, const uint8_t* __restrict__ PR, SbmGeom g, uint16_t* __restrict__ hsad,
+                                int* __restrict__ htext) {
+  const int pair = blockIdx.z, y = blockIdx.y, d = threadIdx.x;
+  const int x0 = blockIdx.x * kSbmSeg, x1 = min(x0 + kSbmSeg, g.width1);
+  const size_t img = (size_t)pair * g.h * g.w, hs = (size_t)pair * g.h * g.width1;
+  sbm_hsad_thread(PL + img, PR + img, g, y, d, x0, x1, hsad + hs * g.ndisp, htext + hs);
+}
+
+__global__ void sbm_vsad_kernel(const uint16_t* __restrict__ hsad, const int* __restrict__ htext, SbmGeom g, int16_t* __restrict__ disp) {
+  extern __shared__ int s_sad_raw[];  // [ndisp + 2]: one guard element on either side for the sub-pixel fit
+  int* s_sad = s_sad_raw + 1;
+  const int pair = blockIdx.z, x = blockIdx.x, d = threadIdx.x;
+  const int y0 = blockIdx.y * kSbmStripe, y1 = min(y0 + kSbmStripe, g.h);
+  const size_t hs = (size_t)pair * g.h * g.width1;
+  const uint16_t* H = hsad + hs * g.ndisp;
+  const int* T = htext + hs;
+  int16_t* out = disp + (size_t)pair * g.h * g.w;
+  int run = sbm_vsad_init(H, g, x, d, y0);
+  int tsum = d == 0 ? sbm_vtext_init(T, g, x, y0) : 0;
+  for (int y = y0; y < y1; ++y) {
+    s_sad[d] = run;
+    __syncthreads();
+    if (d == 0) {
+      const int v = sbm_decide(s_sad, g, tsum);
+      out[(size_t)y * g.w + g.lofs + x] = (int16_t)(sbm_in_roi(g, y, g.lofs + x) ? v : g.filtered);
+      tsum = sbm_vtext_step(T, g, x, y, tsum);
+    }
+    __syncthreads();
+    run = sbm_vsad_step(H, g, x, d, y, run);
+  }
+}
+
+__global__ void sbm_to3d_kernel(const int16_t* __restrict__ disp, int n, int h, int w, float Q03, float Q13, float Q23, float Q32,
+                                float Q33, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per = (size_t)h * w;
+  if (i >= per * n) return;
+  const size_t r = i % per;
+  sbm_point3d(disp[i], (int)(r / w), (int)(r % w), Q03, Q13, Q23, Q32, Q33, out + i * 3);
+}
+
 int grow_dev(void** p, size_t* cur, size_t need) {
   if (*cur >= need) return CB_OK;
   if (*p) cudaFree(*p);
@@ -548,6 +618,15 @@ struct cb_frontend {
   bool have_matches = false;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   float last_match_ms = 0.f;
+  // stereo block matching scratch (grown on demand)
+  uint8_t* sb_img = nullptr;   // left | right of the current chunk
+  uint8_t* sb_pre = nullptr;   // pre-filtered left | right
+  uint16_t* sb_hsad = nullptr;
+  int* sb_htext = nullptr;
+  int16_t* sb_disp = nullptr;
+  float* sb_3d = nullptr;
+  size_t sb_img_bytes = 0, sb_pre_bytes = 0, sb_hsad_bytes = 0, sb_htext_bytes = 0, sb_disp_bytes = 0, sb_3d_bytes = 0;
+  float last_stereo_ms = 0.f;
 };
 
 extern "C" {
@@ -580,11 +659,12 @@ int cb_frontend_create(cb_frontend** out, int max_pairs, int max_features, int d
   A((void**)&f->off1, (size_t)(max_pairs + 1) * 4);
   A((void**)&f->off2, (size_t)(max_pairs + 1) * 4);
   A((void**)&f->best, tot * 8);
+  const size_t tot_tm = tot < (size_t)kHtN ? (size_t)kHtN : tot;  // the TMA boxes are up to 256 rows tall
   if (!f->match_simt) {
-    A((void**)&f->e1, tot * 256);
-    A((void**)&f->e2, tot * 256);
-    A((void**)&f->pop1, tot * 4);
-    A((void**)&f->pop2, tot * 4);
+    A((void**)&f->e1, tot_tm * 256);
+    A((void**)&f->e2, tot_tm * 256);
+    A((void**)&f->pop1, tot_tm * 4);
+    A((void**)&f->pop2, tot_tm * 4);
   }
   A((void**)&f->train_idx, tot * 4);
   A((void**)&f->dist, tot * 4);
@@ -605,8 +685,8 @@ int cb_frontend_create(cb_frontend** out, int max_pairs, int max_features, int d
     return cb::fail(CB_ENOMEM, "front-end allocation failed: %s", cudaGetErrorString(e));
   }
   if (!f->match_simt) {
-    rc = make_map_2d_u8(&f->tmQ, f->e1, (uint64_t)tot, 256, kHtM);
-    if (!rc) rc = make_map_2d_u8(&f->tmT, f->e2, (uint64_t)tot, 256, kHtN);
+    rc = make_map_2d_u8(&f->tmQ, f->e1, (uint64_t)tot_tm, 256, kHtM);
+    if (!rc) rc = make_map_2d_u8(&f->tmT, f->e2, (uint64_t)tot_tm, 256, kHtN);
     if (!rc && cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHtSmem) != cudaSuccess)
       rc = cb::fail(CB_ECUDA, "cannot reserve %d bytes of shared memory for hamming_tc_kernel", kHtSmem);
     if (rc) {
@@ -623,7 +703,8 @@ int cb_frontend_destroy(cb_frontend* f) {
   cb::DeviceGuard g(f->device);
   if (f->stream) cudaStreamSynchronize(f->stream);
   void* ps[] = {f->d1, f->d2, f->kp1, f->kp2, f->off1, f->off2, f->best, f->train_idx, f->dist, f->mask, f->n_inl,
-                f->X,  f->uv, f->uvd, f->Y,   f->Kinv, f->count, f->img_a, f->img_b, f->e1, f->e2, f->pop1, f->pop2, f->tickets};
+                f->X,  f->uv, f->uvd, f->Y,   f->Kinv, f->count, f->img_a, f->img_b, f->e1, f->e2, f->pop1, f->pop2, f->tickets, f->sb_img, f->sb_pre, f->sb_hsad, f->sb_htext,
+                f->sb_disp, f->sb_3d};
   for (void* p : ps)
     if (p) cudaFree(p);
   for (cudaEvent_t ev : f->ev)
@@ -709,6 +790,78 @@ int cb_frontend_match_gms(cb_frontend* f, int n_pairs, const int32_t* off1, cons
 }
 
 float cb_frontend_last_match_ms(const cb_frontend* f) { return f ? f->last_match_ms : -1.f; }
+
+int cb_frontend_stereo_bm(cb_frontend* f, int n, const uint8_t* left, const uint8_t* right, int rows, int cols, int ndisp, int wsz,
+                          int16_t* disparity) {
+  if (!f || !left || !right || !disparity) return cb::fail(CB_EINVAL, "NULL argument to cb_frontend_stereo_bm");
+  if (n < 1 || rows < 2 || cols < 2) return cb::fail(CB_EINVAL, "bad batch / image size");
+  if (ndisp < 16 || ndisp > 256 || ndisp % 16) return cb::fail(CB_EINVAL, "numDisparities must be a multiple of 16 in [16, 256]");
+  if (wsz < 5 || wsz > 255 || wsz % 2 == 0 || wsz >= rows || wsz >= cols)
+    return cb::fail(CB_EINVAL, "SADWindowSize must be odd, within 5..255 and smaller than the image");
+  cb::DeviceGuard gd(f->device);
+  cudaStream_t st = f->stream;
+  const SbmGeom g = sbm_make_geom(rows, cols, ndisp, wsz);
+  const size_t per = (size_t)rows * cols;
+  if (g.lofs >= cols || g.rofs >= cols || g.width1 < 1) {  // OpenCV: everything FILTERED
+    for (size_t i = 0; i < per * n; ++i) disparity[i] = (int16_t)g.filtered;
+    return CB_OK;
+  }
+  // pairs per chunk: keep the horizontal sums below ~1 GB
+  const size_t hsad_per = (size_t)rows * g.width1 * ndisp * sizeof(uint16_t);
+  int chunk = (int)((size_t)(1u << 30) / hsad_per);
+  chunk = chunk < 1 ? 1 : (chunk > n ? n : chunk);
+  int rc = grow_dev((void**)&f->sb_img, &f->sb_img_bytes, 2 * per * chunk);
+  if (!rc) rc = grow_dev((void**)&f->sb_pre, &f->sb_pre_bytes, 2 * per * chunk);
+  if (!rc) rc = grow_dev((void**)&f->sb_hsad, &f->sb_hsad_bytes, hsad_per * chunk);
+  if (!rc) rc = grow_dev((void**)&f->sb_htext, &f->sb_htext_bytes, (size_t)rows * g.width1 * sizeof(int) * chunk);
+  if (!rc) rc = grow_dev((void**)&f->sb_disp, &f->sb_disp_bytes, per * sizeof(int16_t) * chunk);
+  if (rc) return rc;
+  float total_ms = 0.f;
+  for (int c0 = 0; c0 < n; c0 += chunk) {
+    const int nc = n - c0 < chunk ? n - c0 : chunk;
+    CB_CUDA(cudaMemcpyAsync(f->sb_img, left + (size_t)c0 * per, per * nc, cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(f->sb_img + per * nc, right + (size_t)c0 * per, per * nc, cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaEventRecord(f->ev[0], st));
+    sbm_fill_kernel<<<(unsigned)((per * nc + 255) / 256), 256, 0, st>>>(f->sb_disp, per * nc, (int16_t)g.filtered);
+    CB_LAUNCH_CHECK();
+    sbm_prefilter_kernel<<<(unsigned)((2 * per * nc + 255) / 256), 256, 0, st>>>(f->sb_img, 2 * nc, rows, cols, g.cap, f->sb_pre);
+    CB_LAUNCH_CHECK();
+    sbm_hsad_kernel<<<dim3((unsigned)((g.width1 + kSbmSeg - 1) / kSbmSeg), (unsigned)rows, (unsigned)nc), ndisp, 0, st>>>(
+        f->sb_pre, f->sb_pre + per * nc, g, f->sb_hsad, f->sb_htext);
+    CB_LAUNCH_CHECK();
+    sbm_vsad_kernel<<<dim3((unsigned)g.width1, (unsigned)((rows + kSbmStripe - 1) / kSbmStripe), (unsigned)nc), ndisp,
+                      (size_t)(ndisp + 2) * sizeof(int), st>>>(f->sb_hsad, f->sb_htext, g, f->sb_disp);
+    CB_LAUNCH_CHECK();
+    CB_CUDA(cudaEventRecord(f->ev[1], st));
+    CB_CUDA(cudaMemcpyAsync(disparity + (size_t)c0 * per, f->sb_disp, per * sizeof(int16_t) * nc, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, f->ev[0], f->ev[1]);
+    total_ms += ms;
+  }
+  f->last_stereo_ms = total_ms;
+  return CB_OK;
+}
+
+float cb_frontend_last_stereo_ms(const cb_frontend* f) { return f ? f->last_stereo_ms : -1.f; }
+
+int cb_frontend_disparity_to_3d(cb_frontend* f, int n, const int16_t* disparity, int rows, int cols, float Q03, float Q13, float Q23,
+                                float Q32, float Q33, float* out3d) {
+  if (!f || !disparity || !out3d) return cb::fail(CB_EINVAL, "NULL argument to cb_frontend_disparity_to_3d");
+  if (n < 1 || rows < 1 || cols < 1) return cb::fail(CB_EINVAL, "bad batch / image size");
+  cb::DeviceGuard gd(f->device);
+  cudaStream_t st = f->stream;
+  const size_t per = (size_t)rows * cols;
+  int rc = grow_dev((void**)&f->sb_disp, &f->sb_disp_bytes, per * sizeof(int16_t) * n);
+  if (!rc) rc = grow_dev((void**)&f->sb_3d, &f->sb_3d_bytes, per * 3 * sizeof(float) * n);
+  if (rc) return rc;
+  CB_CUDA(cudaMemcpyAsync(f->sb_disp, disparity, per * sizeof(int16_t) * n, cudaMemcpyHostToDevice, st));
+  sbm_to3d_kernel<<<(unsigned)((per * n + 255) / 256), 256, 0, st>>>(f->sb_disp, n, rows, cols, Q03, Q13, Q23, Q32, Q33, f->sb_3d);
+  CB_LAUNCH_CHECK();
+  CB_CUDA(cudaMemcpyAsync(out3d, f->sb_3d, per * 3 * sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  return CB_OK;
+}
 
 int cb_frontend_collect(cb_frontend* f, int mode, const float* img3d_a, const float* img3d_b, int rows, int cols,
                         const double* K_inverse, int32_t* counts, double* X, double* uv, double* uv_d, double* Y) {

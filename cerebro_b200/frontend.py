@@ -88,6 +88,32 @@ class FrontEnd:
         one = np.ones((1, sel.size))
         return np.concatenate([u.T, one]), np.concatenate([ud.T, one])
 
+    # ---- stereo depth of the frames (StereoGeometry, src/utils/CameraGeometry.cpp:81, :410-418, :459-520)
+    def stereo_bm(self, left: np.ndarray, right: np.ndarray, ndisp: int = 64, wsz: int = 21) -> np.ndarray:
+        """``cv::StereoBM::create(ndisp, wsz)->compute(left, right)`` for a batch of rectified pairs: uint8 [n, rows, cols]
+        (or [rows, cols]) -> int16 disparity * 16 of the same shape, -16 where rejected."""
+        single = left.ndim == 2
+        L = np.ascontiguousarray(left[None] if single else left, dtype=np.uint8)
+        R = np.ascontiguousarray(right[None] if single else right, dtype=np.uint8)
+        assert L.ndim == 3 and L.shape == R.shape
+        out = np.empty(L.shape, dtype=np.int16)
+        check(self._lib.cb_frontend_stereo_bm(self._h, L.shape[0], ptr(L), ptr(R), L.shape[1], L.shape[2], int(ndisp), int(wsz), ptr(out)))
+        return out[0] if single else out
+
+    def last_stereo_ms(self) -> float:
+        return float(self._lib.cb_frontend_last_stereo_ms(self._h))
+
+    def disparity_to_3d(self, disparity: np.ndarray, Q: np.ndarray) -> np.ndarray:
+        """``StereoGeometry::disparity_to_3DPoints``: int16 disparity * 16 [n, rows, cols] (or [rows, cols]) and the 4x4
+        reprojection matrix Q -> the CV_32FC3 "3d image" float32 [..., 3] that the set builders take."""
+        single = disparity.ndim == 2
+        D = np.ascontiguousarray(disparity[None] if single else disparity, dtype=np.int16)
+        Q = np.asarray(Q, dtype=np.float64)
+        out = np.empty(D.shape + (3,), dtype=np.float32)
+        check(self._lib.cb_frontend_disparity_to_3d(self._h, D.shape[0], ptr(D), D.shape[1], D.shape[2], float(Q[0, 3]), float(Q[1, 3]),
+                                                    float(Q[2, 3]), float(Q[3, 2]), float(Q[3, 3]), ptr(out)))
+        return out[0] if single else out
+
     # ---- set builders over the batch matched last
     def make_3d_2d_collection(self, K: np.ndarray, img3d: np.ndarray, swapped: bool = False):
         """make_3d_2d_collection__using__pfmatches_and_disparity for every pair of the last ``match_gms`` batch.

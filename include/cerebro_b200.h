@@ -307,6 +307,18 @@ CB_API float cb_frontend_last_match_ms(const cb_frontend* f);
 CB_API int cb_frontend_collect(cb_frontend* f, int mode, const float* img3d_a, const float* img3d_b, int rows, int cols,
                         const double* K_inverse, int32_t* counts, double* X, double* uv, double* uv_d, double* Y);
 
+/* Stereo depth of the two frames (src/utils/CameraGeometry.cpp): `bm = cv::StereoBM::create(ndisp, wsz)` (:81, the
+ * reference uses 64, 21) and `bm->compute(left, right, disparity)` (:410-418) with OpenCV's default parameters, for n
+ * rectified pairs: left, right [n][rows][cols] uint8 -> disparity [n][rows][cols] int16 = disparity * 16, -16 where the
+ * matcher rejects the pixel or outside the valid ROI.  Bit-exact against cv2.StereoBM (tests/test_stereo.py). */
+CB_API int cb_frontend_stereo_bm(cb_frontend* f, int n, const uint8_t* left, const uint8_t* right, int rows, int cols,
+                          int ndisp, int wsz, int16_t* disparity);
+CB_API float cb_frontend_last_stereo_ms(const cb_frontend* f); /* device time of the last cb_frontend_stereo_bm */
+/* StereoGeometry::disparity_to_3DPoints (CameraGeometry.cpp:459-520): the CV_32FC3 "3d image"
+ * ((j + Q03) pw, (i + Q13) pw, Q23 pw), pw = 1 / (disparity / 16 * Q32 + Q33 + 1e-6); Q?? = entries of the 4x4 Q matrix. */
+CB_API int cb_frontend_disparity_to_3d(cb_frontend* f, int n, const int16_t* disparity, int rows, int cols, float Q03,
+                                float Q13, float Q23, float Q32, float Q33, float* out3d);
+
 #ifdef __cplusplus
 }
 #endif

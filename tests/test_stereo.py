@@ -42,3 +42,60 @@ def test_disparity_to_3d_restates_the_reference_loop():
     f, b = 420.0, 0.12
     z = stereo.disparity_to_3d(np.full((1, 1), 16 * 16, np.int16), 0, 0, f, 1.0 / b, 0.0)[0, 0, 2]
     assert abs(z - f * b / 16.0) < 1e-3
+
+
+def _emul():
+    import ctypes
+
+    from cerebro_b200 import build
+
+    build.build()
+    lib = ctypes.CDLL(build.STEREO_EMUL)
+    P = ctypes.c_void_p
+    lib.sbm_emulate.argtypes = [P, P] + [ctypes.c_int] * 6 + [P]
+    lib.sbm_emulate_3d.argtypes = [P, ctypes.c_int, ctypes.c_int] + [ctypes.c_float] * 5 + [P]
+    return lib
+
+
+@pytest.mark.parametrize("h,w,nd,ws,seg,stripe", [(120, 200, 32, 9, 32, 60), (97, 211, 64, 21, 32, 60), (150, 260, 64, 21, 17, 33),
+                                                  (121, 203, 16, 5, 64, 500), (60, 90, 64, 21, 32, 60)])
+def test_kernel_bodies_emulated_on_cpu_match_oracle(h, w, nd, ws, seg, stripe):
+    """csrc/stereo_core.h (the per-thread bodies the CUDA kernels run) walked over the kernels' (block, thread) space by
+    host/stereo_emul.cpp -- (32, 60) is the kernels' own segment / stripe size -- against the oracle, bit-exact."""
+    lib = _emul()
+    for kind in range(3):
+        left, right = stereo_scene(h, w, kind, seed=5 + kind)
+        out = np.zeros((h, w), np.int16)
+        lib.sbm_emulate(left.ctypes.data, right.ctypes.data, h, w, nd, ws, seg, stripe, out.ctypes.data)
+        assert np.array_equal(out, stereo.stereo_bm(left, right, ndisp=nd, wsz=ws)), kind
+    disp = stereo.stereo_bm(*stereo_scene(h, w, 0, seed=5), ndisp=nd, wsz=ws)
+    o3 = np.zeros((h, w, 3), np.float32)
+    lib.sbm_emulate_3d(disp.ctypes.data, h, w, -160.5, -120.25, 421.3, 8.33, 0.0, o3.ctypes.data)
+    assert np.array_equal(o3, stereo.disparity_to_3d(disp, -160.5, -120.25, 421.3, 8.33, 0.0))
+
+
+@pytest.mark.gpu
+def test_device_stereo_matches_oracle(native_lib, cuda_device):
+    """cb_frontend_stereo_bm / cb_frontend_disparity_to_3d against the oracle (itself bit-exact against cv2.StereoBM)."""
+    from cerebro_b200.frontend import FrontEnd
+
+    fe = FrontEnd(max_pairs=1, max_features=512)
+    pairs = [stereo_scene(150, 260, kind, seed=20 + kind) for kind in range(3)]
+    L, R = np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+    d = fe.stereo_bm(L, R, ndisp=64, wsz=21)
+    for k in range(3):
+        assert np.array_equal(d[k], stereo.stereo_bm(L[k], R[k], ndisp=64, wsz=21)), k
+    assert fe.last_stereo_ms() > 0 and (d >= 0).mean() > 0.3
+    left, right = stereo_scene(97, 211, 1, seed=3)
+    d2 = fe.stereo_bm(left, right, ndisp=16, wsz=5)
+    assert np.array_equal(d2, stereo.stereo_bm(left, right, ndisp=16, wsz=5))
+    g = golden_io.load("stereo_golden.npz")  # cv2's own answer
+    h, w, nd, ws, kind, seed = (int(v) for v in g["b_cfg"])
+    assert np.array_equal(fe.stereo_bm(*stereo_scene(h, w, kind, seed), ndisp=nd, wsz=ws), g["b_disp"])
+    Q = np.array([[1, 0, 0, -130.5], [0, 1, 0, -75.25], [0, 0, 0, 421.3], [0, 0, 8.33, 0.0]])
+    p3 = fe.disparity_to_3d(d, Q)
+    for k in range(3):
+        assert np.array_equal(p3[k], stereo.disparity_to_3d(d[k], Q[0, 3], Q[1, 3], Q[2, 3], Q[3, 2], Q[3, 3])), k
+    with pytest.raises(Exception):
+        fe.stereo_bm(left, right, ndisp=20, wsz=5)
+    fe.close()
