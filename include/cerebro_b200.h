@@ -161,7 +161,7 @@ typedef struct cb_netvlad_weights {
 CB_API int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int rows, int cols,
                          int chnls, int max_batch, int device);
 CB_API int cb_descriptor_destroy(cb_descriptor* d);
-/* The June2019 models (scripts/keras.models/June2019/*mobilenetv2-block_9_add*, selected at
+/* The June2019 models (scripts/keras.models/June2019/ ...mobilenetv2-block_9_add..., selected at
  * launch/mynteye_vinsfusion.launch:100 and built by keras_helpers.py from keras_applications'
  * MobileNetV2): Conv1 3x3 s2 (pad bottom/right) + ReLU6, then inverted-residual blocks
  * [expand 1x1 + ReLU6] -> depthwise 3x3 (s1 'same' | pad bottom/right + s2 'valid') + ReLU6 ->

@@ -47,3 +47,15 @@ def test_header_cites_reference():
     src = open(os.path.join(ROOT, "include", "cerebro_b200.h")).read()
     for cite in ("src/Cerebro.cpp:390", "src/DlsPnpWithRansac.cpp:132-245", "WholeImageDescriptorCompute.srv"):
         assert cite in src
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (cgo / FFI consumers) and as C++11, warning-free."""
+    import subprocess
+
+    src = tmp_path / "cabi.c"
+    src.write_text('#include "cerebro_b200.h"\nint main(void){ cb_ransac_params p; cb_ir_block b; (void)p; (void)b; return cb_version() > 0 ? 0 : 1; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror"], ["g++", "-std=c++11", "-Wall", "-Werror", "-x", "c++"]):
+        r = subprocess.run(cmd + ["-I" + inc, "-c", str(src), "-o", str(tmp_path / "cabi.o")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
