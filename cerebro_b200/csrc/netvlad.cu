@@ -621,7 +621,21 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dwpw_kernel(const __half* __
 constexpr int kHaloThreads = 224 + kProdThreads;  // 736
 constexpr int kTH = 16, kTW = 8;
 
-template <int CIN, int COUT, int S>
+// MODE bits of the halo kernel (the "precise" descriptor path):
+//   kInQ   the block input is stored as q15 (unsigned 15-bit fixed point of the ReLU6 range: u = round(x * 32767 / 6));
+//          a PRMT drops u into the mantissa of a float in [2, 4) (f = 2 + u * 2^-14) -- on the ALU pipe, where the fp16
+//          decode (HADD2.F32) competes with the FFMA2 taps for the FMA pipe -- and the affine map back to x is folded
+//          into the depthwise weights and bias on the host (w' = w * 2^14 * 6 / 32767, b' = b - 2 * sum w').  TMA's
+//          zero fill of the padding decodes to f = 2, i.e. x = 0.
+//   kSplit the depthwise output (MMA A operand) and the pointwise weights (B operand) are each kept as fp16 hi + lo;
+//          three accumulating MMAs  A_hi B_hi + A_lo B_hi + A_hi B_lo  (A_lo is stored negated: h - x is one FHADD;
+//          the instruction descriptor's a_negate bit flips it back)
+//   kOutQ  the epilogue writes q15 instead of fp16
+constexpr int kInQ = 1, kSplit = 2, kOutQ = 4;
+constexpr float kQ15Scale = 32767.0f / 6.0f;          // x -> u
+constexpr double kQ15DecodeW = 16384.0 * 6.0 / 32767.0;  // (f - 2) -> x
+
+template <int CIN, int COUT, int S, bool SPLIT = false>
 struct HaloCfg {
   static constexpr int KB = 32;  // channels per K block (= per halo box): 64-byte pixels, 64-byte swizzled A/B rows
   static constexpr int NKB = CIN / KB;
@@ -629,15 +643,18 @@ struct HaloCfg {
   static constexpr int HH = (kTH - 1) * S + 3, HW = (kTW - 1) * S + 3;
   static constexpr int kHaloTx = HH * HW * KB * 2;                 // bytes one box delivers
   static constexpr int kHaloBytes = (kHaloTx + 127) / 128 * 128;   // ring stride (TMA destinations are 128B aligned)
-  static constexpr int kABytes = 128 * KB * 2;
-  static constexpr int kBBytes = COUT * KB * 2;
+  static constexpr int kATile = 128 * KB * 2;
+  static constexpr int kABytes = (SPLIT ? 2 : 1) * kATile;          // [hi | -lo]
+  static constexpr int kBTile = COUT * KB * 2;
+  static constexpr int kBBytes = (SPLIT ? 2 : 1) * kBTile;          // [hi | lo]
   static constexpr bool kResident = NKB * kBBytes <= 64 * 1024;    // whole [COUT][CIN] matrix in smem, else a ring
   static constexpr int kBS = kResident ? NKB : ((S == 2 && kBBytes >= 32 * 1024) ? 2 : 3);
   static constexpr int kStrip = S == 2 ? 2 : 4;                    // output rows per producer task
   static constexpr int kTasks = (KB / 8) * kTW * (kTH / kStrip);   // producer tasks per K block (128 or 256)
   static constexpr int kTeams = kProdThreads / kTasks;             // K blocks in production concurrently (4 or 2)
   static constexpr int kTeamWarps = kTasks / 32;
-  static constexpr int kAS = kTeams > 3 ? kTeams : 3;
+  static constexpr int kASmin = (SPLIT && S == 2) ? 2 : 3;          // the big stride-2 halos need the room
+  static constexpr int kAS = kTeams > kASmin ? kTeams : kASmin;
   static constexpr int kStageBytes = 4 * 32 * 128;                 // epilogue staging: 32 pixels x 64 channels per warp
   static constexpr int kBudget = 232448 - 1024 - 512 - kStageBytes;
   static constexpr int kFit = (kBudget - kBS * kBBytes - kAS * kABytes) / kHaloBytes;
@@ -648,10 +665,50 @@ struct HaloCfg {
   // a team waits on ring slot g % K with parity (g / K) & 1: that is only well defined while it cannot run more than one
   // phase ahead of the slot, i.e. while the number of teams does not exceed the ring depth
   static_assert(kTeams <= kAS && kTeams <= kHS, "more producer teams than ring slots");
+  static_assert(!SPLIT || COUT <= 256, "operand split is built for the blocks up to 256 output channels");
   static constexpr int kTotal = kAS * kABytes + kBS * kBBytes + kStageBytes + kHS * kHaloBytes + 1024 + 512;
 };
 
-template <int CIN, int COUT, int S>
+// two fp32 accumulators (acc * scale + bias * scale already applied) -> two q15 values: clamp to [0, 32767], round to
+// nearest-even through the 2^23 magic add, keep the low 16 bits of each
+__device__ __forceinline__ uint32_t q15_pack(unsigned long long y) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(y));
+  lo = fminf(fmaxf(lo, 0.f), 32767.f);
+  hi = fminf(fmaxf(hi, 0.f), 32767.f);
+  const unsigned long long m = fadd2(pack_f32x2(lo, hi), pack_f32x2(8388608.f, 8388608.f));
+  uint32_t a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(m));
+  return __byte_perm(a, b, 0x5410);
+}
+
+// eight q15 values (one 16-byte chunk) -> four packed float pairs f = 2 + u * 2^-14
+__device__ __forceinline__ void q15_decode8(const uint4& raw, unsigned long long v[4]) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t lo = __byte_perm(w[j], 0x40000000u, 0x7104), hi = __byte_perm(w[j], 0x40000000u, 0x7324);
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v[j]) : "r"(lo), "r"(hi));
+  }
+}
+
+// ReLU6 of two fp32 values -> fp16 hi pair and the NEGATED fp16 lo pair (h - x: one mixed-precision FHADD per value)
+__device__ __forceinline__ void relu6_split_h2(unsigned long long v, uint32_t& hi_out, uint32_t& nlo_out) {
+  float x0, x1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(v));
+  x0 = fminf(fmaxf(x0, 0.f), 6.f);
+  x1 = fminf(fmaxf(x1, 0.f), 6.f);
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const unsigned short h0 = __half_as_ushort(__low2half(h)), h1 = __half_as_ushort(__high2half(h));
+  float n0, n1;
+  asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(n0) : "h"(h0), "f"(x0));
+  asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(n1) : "h"(h1), "f"(x1));
+  const __half2 nl = __floats2half2_rn(n0, n1);
+  hi_out = *reinterpret_cast<const uint32_t*>(&h);
+  nlo_out = *reinterpret_cast<const uint32_t*>(&nl);
+}
+
+template <int CIN, int COUT, int S, int MODE>
 __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid_constant__ CUtensorMap tmH,
                                                                    const float* __restrict__ dw_w /*[3][3][CIN]*/,
                                                                    const float* __restrict__ dw_b,
@@ -659,7 +716,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
                                                                    const float* __restrict__ bias,
                                                                    const __grid_constant__ CUtensorMap tmO, int tiles_x,
                                                                    int tiles_per_frame, int n_tiles) {
-  using SM = HaloCfg<CIN, COUT, S>;
+  constexpr bool INQ = (MODE & kInQ) != 0, SPLIT = (MODE & kSplit) != 0, OUTQ = (MODE & kOutQ) != 0;
+  using SM = HaloCfg<CIN, COUT, S, SPLIT>;
   constexpr int KB = SM::KB, NKB = SM::NKB, SWZ = SM::SWZ;
   constexpr int kAS = SM::kAS, kHS = SM::kHS, kAcc = SM::kAcc;
   constexpr int N_MMA = COUT > 256 ? 256 : COUT;
@@ -716,6 +774,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
           uint8_t* sb = smem_b + kb * SM::kBBytes;
           tma_load_2d(&tmB, &b_full[0], sb, kb * KB, 0);
           if (COUT > 256) tma_load_2d(&tmB, &b_full[0], sb + 256 * KB * 2, kb * KB, 256);
+          if (SPLIT) tma_load_2d(&tmB, &b_full[0], sb + SM::kBTile, kb * KB, COUT);  // lo rows follow the hi rows
         }
       } else {
         uint32_t g = 0;
@@ -727,6 +786,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
             uint8_t* sb = smem_b + s * SM::kBBytes;
             tma_load_2d(&tmB, &b_full[s], sb, kb * KB, 0);
             if (COUT > 256) tma_load_2d(&tmB, &b_full[s], sb + 256 * KB * 2, kb * KB, 256);
+            if (SPLIT) tma_load_2d(&tmB, &b_full[s], sb + SM::kBTile, kb * KB, COUT);
           }
         }
       }
@@ -756,6 +816,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
             for (int h = 0; h < COUT / N_MMA; ++h) {
               const uint64_t bd = make_kmajor_desc<SWZ>(b_addr + h * (256 * KB * 2) + k * 32);
               umma_f16(d_tmem + h * 256, ad, bd, idesc, (kb | k) ? 1u : 0u);
+              if (SPLIT) {  // + A_lo B_hi (A_lo is stored negated: a_negate, descriptor bit 13) + A_hi B_lo
+                umma_f16(d_tmem + h * 256, make_kmajor_desc<SWZ>(a_addr + SM::kATile + k * 32), bd, idesc | (1u << 13), 1u);
+                umma_f16(d_tmem + h * 256, ad, make_kmajor_desc<SWZ>(b_addr + SM::kBTile + k * 32), idesc, 1u);
+              }
             }
           }
           umma_commit(&a_empty[sa]);
@@ -790,10 +854,18 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
             const ulonglong2 b0 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c + hh * 32 + j));
             const ulonglong2 b1 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c + hh * 32 + j + 4));
             uint4 o;
-            o.x = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1])), b0.x));
-            o.y = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), b0.y));
-            o.z = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])), b1.x));
-            o.w = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])), b1.y));
+            if (OUTQ) {  // `bias` is pre-multiplied by 32767 / 6
+              const unsigned long long sc = pack_f32x2(kQ15Scale, kQ15Scale);
+              o.x = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1])), sc, b0.x));
+              o.y = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), sc, b0.y));
+              o.z = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])), sc, b1.x));
+              o.w = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])), sc, b1.y));
+            } else {
+              o.x = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1])), b0.x));
+              o.y = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), b0.y));
+              o.z = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])), b1.x));
+              o.w = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])), b1.y));
+            }
             const int chunk = hh * 4 + (j >> 3);
             sts128(srow + ((chunk ^ (lane & 7)) << 4), o);
           }
@@ -876,12 +948,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
 #pragma unroll
         for (int ir = 0; ir < NR; ++ir) {
           const uint4 raw = lds128(hb + (ir * SM::HW + kx) * PXB);
-          const __half2* hv = reinterpret_cast<const __half2*>(&raw);
           unsigned long long v[4];
+          if (INQ) {
+            q15_decode8(raw, v);
+          } else {
+            const __half2* hv = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 fv = __half22float2(hv[j]);
-            v[j] = pack_f32x2(fv.x, fv.y);
+            for (int j = 0; j < 4; ++j) {
+              const float2 fv = __half22float2(hv[j]);
+              v[j] = pack_f32x2(fv.x, fv.y);
+            }
           }
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
@@ -898,10 +974,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
 #pragma unroll
       for (int i = 0; i < kStrip; ++i) {
         uint4 o;
-        o.x = relu6_pack_h2(acc[i][0]);
-        o.y = relu6_pack_h2(acc[i][1]);
-        o.z = relu6_pack_h2(acc[i][2]);
-        o.w = relu6_pack_h2(acc[i][3]);
+        if (SPLIT) {
+          uint4 l;
+          relu6_split_h2(acc[i][0], o.x, l.x);
+          relu6_split_h2(acc[i][1], o.y, l.y);
+          relu6_split_h2(acc[i][2], o.z, l.z);
+          relu6_split_h2(acc[i][3], o.w, l.w);
+          sts128(at + SM::kATile + aoff[i], l);
+        } else {
+          o.x = relu6_pack_h2(acc[i][0]);
+          o.y = relu6_pack_h2(acc[i][1]);
+          o.z = relu6_pack_h2(acc[i][2]);
+          o.w = relu6_pack_h2(acc[i][3]);
+        }
         sts128(at + aoff[i], o);
       }
       fence_proxy_async();
@@ -968,7 +1053,7 @@ __device__ __forceinline__ void load_row9(const uint8_t* __restrict__ rowp, int 
   }
 }
 
-template <int CIN>
+template <int CIN, bool OUTQ>
 __global__ void __launch_bounds__(kConvThreads) conv1_tc_kernel(const uint8_t* __restrict__ img, int n, int H, int W, int Ho, int Wo,
                                                                const __half* __restrict__ w_hi /*[32][32] K-major*/,
                                                                const __half* __restrict__ w_lo, const float* __restrict__ bias,
@@ -1098,12 +1183,22 @@ __global__ void __launch_bounds__(kConvThreads) conv1_tc_kernel(const uint8_t* _
         for (int j = 0; j < 32; j += 8) {
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + j));
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + j + 4));
-          __half2 h[4];
-          h[0] = __floats2half2_rn(relu6(__uint_as_float(v[j + 0]) + b0.x), relu6(__uint_as_float(v[j + 1]) + b0.y));
-          h[1] = __floats2half2_rn(relu6(__uint_as_float(v[j + 2]) + b0.z), relu6(__uint_as_float(v[j + 3]) + b0.w));
-          h[2] = __floats2half2_rn(relu6(__uint_as_float(v[j + 4]) + b1.x), relu6(__uint_as_float(v[j + 5]) + b1.y));
-          h[3] = __floats2half2_rn(relu6(__uint_as_float(v[j + 6]) + b1.z), relu6(__uint_as_float(v[j + 7]) + b1.w));
-          *reinterpret_cast<uint4*>(orow + j) = *reinterpret_cast<uint4*>(h);
+          if (OUTQ) {  // q15 output for the halo kernel; `bias` is pre-multiplied by 32767 / 6
+            const unsigned long long sc = pack_f32x2(kQ15Scale, kQ15Scale);
+            uint4 o;
+            o.x = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1])), sc, pack_f32x2(b0.x, b0.y)));
+            o.y = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), sc, pack_f32x2(b0.z, b0.w)));
+            o.z = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])), sc, pack_f32x2(b1.x, b1.y)));
+            o.w = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])), sc, pack_f32x2(b1.z, b1.w)));
+            *reinterpret_cast<uint4*>(orow + j) = o;
+          } else {
+            __half2 h[4];
+            h[0] = __floats2half2_rn(relu6(__uint_as_float(v[j + 0]) + b0.x), relu6(__uint_as_float(v[j + 1]) + b0.y));
+            h[1] = __floats2half2_rn(relu6(__uint_as_float(v[j + 2]) + b0.z), relu6(__uint_as_float(v[j + 3]) + b0.w));
+            h[2] = __floats2half2_rn(relu6(__uint_as_float(v[j + 4]) + b1.x), relu6(__uint_as_float(v[j + 5]) + b1.y));
+            h[3] = __floats2half2_rn(relu6(__uint_as_float(v[j + 6]) + b1.z), relu6(__uint_as_float(v[j + 7]) + b1.w));
+            *reinterpret_cast<uint4*>(orow + j) = *reinterpret_cast<uint4*>(h);
+          }
         }
       }
     }
@@ -1510,6 +1605,14 @@ struct Block {
   CUtensorMap tmH[2];  // 4-D halo maps of the block's input, one per ping-pong buffer
   CUtensorMap tmO[2];  // 4-D store maps of the block's output (64 ch x 8 x 4 boxes, 128B swizzle)
   CUtensorMap tmBh;    // weight map with the halo kernel's K block
+  // "precise" halo path (MODE bits of dwpw_halo_kernel)
+  int mode = 0;              // kInQ | kSplit | kOutQ, fixed at create time
+  bool runs_halo = false;    // this block is executed by dwpw_halo_kernel (decides the storage format of its input)
+  float* dw_wq = nullptr;    // depthwise weights / bias with the q15 decode folded in
+  float* dw_bq = nullptr;
+  float* pw_bq = nullptr;    // pointwise bias * 32767 / 6 (q15 epilogue)
+  __half* pw_whl = nullptr;  // [2][Cout][C]: fp16 hi rows, then lo rows
+  CUtensorMap tmBs;          // map over pw_whl
 };
 
 // One 1x1 convolution of the MobileNetV2 path (channel counts padded to multiples of 64 with zero weights / biases, so
@@ -1542,6 +1645,11 @@ struct cb_descriptor {
   float* conv1_b = nullptr;
   __half* conv1_hi = nullptr;  // [32][32] K-major, scale 2/255 folded in, hi/lo split (tcgen05 stem)
   __half* conv1_lo = nullptr;
+  float* conv1_bq = nullptr;   // stem bias * 32767 / 6 (q15 output)
+  bool stem_q = false;         // the stem writes q15 (block 0 runs on the halo kernel in precise mode)
+  bool fp16_legacy = false;    // CB_DESC_FP16=1: round-1 arithmetic (fp16 storage and operands everywhere)
+  int split_blocks = 4;        // CB_DESC_SPLIT: leading blocks whose MMA operands are split hi + lo
+  std::vector<uint8_t> layer_q;  // per layer: output stored as q15
   std::vector<Block> blocks;
   bool v2 = false;            // MobileNetV2 prefix (cb_descriptor_create_v2): `ir` instead of `blocks`, three buffers
   std::vector<IrBlock> ir;
@@ -1620,20 +1728,38 @@ int run_fused(const Block& b, int n, int sm, const __half* in, __half* out, cuda
   return launch_fused<512, 512, 1>(b, n, sm, in, out, st);
 }
 
-template <int CIN, int COUT, int S>
-int launch_halo(const Block& b, int n, int sm_count, int in_buf, cudaStream_t st) {
-  using SM = HaloCfg<CIN, COUT, S>;
-  auto kern = dwpw_halo_kernel<CIN, COUT, S>;
+template <int CIN, int COUT, int S, int MODE>
+int launch_halo_mode(const Block& b, int n, int sm_count, int in_buf, cudaStream_t st) {
+  using SM = HaloCfg<CIN, COUT, S, (MODE & kSplit) != 0>;
+  auto kern = dwpw_halo_kernel<CIN, COUT, S, MODE>;
   CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
   const int tiles_x = (b.Wo + kTW - 1) / kTW, tiles_y = (b.Ho + kTH - 1) / kTH;
   const int per_frame = tiles_x * tiles_y;
   const int n_tiles = n * per_frame;
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;  // persistent: one CTA per SM
-  kern<<<grid, kHaloThreads, SM::kTotal, st>>>(b.tmH[in_buf], b.dw_w, b.dw_b, b.tmBh, b.pw_b, b.tmO[in_buf ^ 1], tiles_x, per_frame,
-                                               n_tiles);
+  kern<<<grid, kHaloThreads, SM::kTotal, st>>>(b.tmH[in_buf], (MODE & kInQ) ? b.dw_wq : b.dw_w, (MODE & kInQ) ? b.dw_bq : b.dw_b,
+                                               (MODE & kSplit) ? b.tmBs : b.tmBh, (MODE & kOutQ) ? b.pw_bq : b.pw_b,
+                                               b.tmO[in_buf ^ 1], tiles_x, per_frame, n_tiles);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
+
+template <int CIN, int COUT, int S>
+int launch_halo(const Block& b, int n, int sm_count, int in_buf, cudaStream_t st) {
+  switch (b.mode) {
+    case 0: return launch_halo_mode<CIN, COUT, S, 0>(b, n, sm_count, in_buf, st);
+    case kInQ: return launch_halo_mode<CIN, COUT, S, kInQ>(b, n, sm_count, in_buf, st);
+    case kInQ | kOutQ: return launch_halo_mode<CIN, COUT, S, kInQ | kOutQ>(b, n, sm_count, in_buf, st);
+    default: break;
+  }
+  if constexpr (COUT <= 256) {
+    if (b.mode == (kInQ | kSplit)) return launch_halo_mode<CIN, COUT, S, kInQ | kSplit>(b, n, sm_count, in_buf, st);
+    if (b.mode == (kInQ | kSplit | kOutQ)) return launch_halo_mode<CIN, COUT, S, kInQ | kSplit | kOutQ>(b, n, sm_count, in_buf, st);
+  }
+  return cb::fail(CB_EINVAL, "halo kernel mode %d is not built for %d -> %d channels", b.mode, CIN, COUT);
+}
+
+bool split_shape_supported(int cout) { return cout <= 256; }
 
 int run_halo(const Block& b, int n, int sm, int in_buf, cudaStream_t st) {
   if (b.C == 32) return launch_halo<32, 64, 1>(b, n, sm, in_buf, st);
@@ -1672,12 +1798,18 @@ int run_stem(cb_descriptor* d, int n, const uint8_t* img_dev, int cur, cudaStrea
   if (!d->force_simt && !d->no_fuse) {
     const long long M = (long long)n * d->H1 * d->W1;
     const unsigned grid = (unsigned)((M + 128 * kConvTiles - 1) / (128 * kConvTiles));
-    if (d->chnls == 1)
-      conv1_tc_kernel<1><<<grid, kConvThreads, 0, st>>>(img_dev, n, d->rows, d->cols, d->H1, d->W1, d->conv1_hi, d->conv1_lo,
-                                                        d->conv1_b, d->act[cur], (int)M);
+    if (d->chnls == 1 && d->stem_q)
+      conv1_tc_kernel<1, true><<<grid, kConvThreads, 0, st>>>(img_dev, n, d->rows, d->cols, d->H1, d->W1, d->conv1_hi, d->conv1_lo,
+                                                              d->conv1_bq, d->act[cur], (int)M);
+    else if (d->chnls == 1)
+      conv1_tc_kernel<1, false><<<grid, kConvThreads, 0, st>>>(img_dev, n, d->rows, d->cols, d->H1, d->W1, d->conv1_hi, d->conv1_lo,
+                                                               d->conv1_b, d->act[cur], (int)M);
+    else if (d->stem_q)
+      conv1_tc_kernel<3, true><<<grid, kConvThreads, 0, st>>>(img_dev, n, d->rows, d->cols, d->H1, d->W1, d->conv1_hi, d->conv1_lo,
+                                                              d->conv1_bq, d->act[cur], (int)M);
     else
-      conv1_tc_kernel<3><<<grid, kConvThreads, 0, st>>>(img_dev, n, d->rows, d->cols, d->H1, d->W1, d->conv1_hi, d->conv1_lo,
-                                                        d->conv1_b, d->act[cur], (int)M);
+      conv1_tc_kernel<3, false><<<grid, kConvThreads, 0, st>>>(img_dev, n, d->rows, d->cols, d->H1, d->W1, d->conv1_hi, d->conv1_lo,
+                                                               d->conv1_b, d->act[cur], (int)M);
     CB_LAUNCH_CHECK();
   } else {
     const long long threads = (long long)n * d->H1 * ((d->W1 + kPX - 1) / kPX) * 4;
@@ -1708,8 +1840,8 @@ int forward(cb_descriptor* d, int n, const uint8_t* img_dev, float* out_dev, cud
     const int dw_layer = layer + 1, pw_layer = layer + 2;
     if (b.has_pw && b.use_tc && b.fused && !d->no_fuse && !d->force_simt && d->stop_layer != dw_layer) {
       // fused depthwise -> pointwise: one kernel, one ping-pong flip (the depthwise output never exists)
-      int rc = (b.halo && !d->no_halo) ? run_halo(b, n, d->sm_count, cur, st)
-                                       : run_fused(b, n, d->sm_count, d->act[cur], d->act[cur ^ 1], st);
+      int rc = b.runs_halo ? run_halo(b, n, d->sm_count, cur, st)
+                           : run_fused(b, n, d->sm_count, d->act[cur], d->act[cur ^ 1], st);
       if (rc) return rc;
       cur ^= 1;
       d->last_buf = cur;
@@ -1963,6 +2095,12 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
   d->no_fuse = env3 && env3[0] == '1';
   const char* env4 = getenv("CB_NO_HALO");
   d->no_halo = env4 && env4[0] == '1';
+  const char* env5 = getenv("CB_DESC_FP16");
+  d->fp16_legacy = env5 && env5[0] == '1';
+  if (const char* env6 = getenv("CB_DESC_SPLIT")) {
+    const int nsp = atoi(env6);
+    if (nsp >= 0) d->split_blocks = nsp;
+  }
   const char* env2 = getenv("CB_DEBUG_STOP_LAYER");
   d->stop_layer = env2 ? atoi(env2) : -1;
   if (const char* envc = getenv("CB_DESC_CHUNK")) {
@@ -2050,7 +2188,71 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
                                4, true);
           b.halo = rh == CB_OK;  // a frame too small for the box keeps the global-memory producers
         }
+        if (b.fused && b.halo && !rc) {
+          // precise path: q15 decode folded into the depthwise weights (f = 2 + u 2^-14 -> x = (f - 2) * kQ15DecodeW),
+          // q15-scaled pointwise bias, hi / lo split of the pointwise weights
+          std::vector<float> wq((size_t)9 * b.C), bq((size_t)b.C), pbq((size_t)b.Cout);
+          for (int ch = 0; ch < b.C; ++ch) {
+            double sum = 0.0;
+            for (int t9 = 0; t9 < 9; ++t9) {
+              const float v = (float)((double)w->dw_w[i][(size_t)t9 * b.C + ch] * kQ15DecodeW);
+              wq[(size_t)t9 * b.C + ch] = v;
+              sum += (double)v;
+            }
+            bq[ch] = (float)((double)w->dw_b[i][ch] - 2.0 * sum);
+          }
+          for (int nn = 0; nn < b.Cout; ++nn) pbq[nn] = (float)((double)w->pw_b[i][nn] * (32767.0 / 6.0));
+          rc = upload_f32(&b.dw_wq, wq.data(), wq.size());
+          if (!rc) rc = upload_f32(&b.dw_bq, bq.data(), bq.size());
+          if (!rc) rc = upload_f32(&b.pw_bq, pbq.data(), pbq.size());
+          if (!rc && split_shape_supported(b.Cout)) {
+            std::vector<__half> hl((size_t)2 * b.C * b.Cout);
+            for (int k = 0; k < b.C; ++k)
+              for (int nn = 0; nn < b.Cout; ++nn) {
+                const float v = w->pw_w[i][(size_t)k * b.Cout + nn];
+                const __half h = __float2half_rn(v);
+                hl[(size_t)nn * b.C + k] = h;
+                hl[(size_t)(b.Cout + nn) * b.C + k] = __float2half_rn(v - __half2float(h));
+              }
+            e = cudaMalloc((void**)&b.pw_whl, hl.size() * sizeof(__half));
+            if (e == cudaSuccess) e = cudaMemcpy(b.pw_whl, hl.data(), hl.size() * sizeof(__half), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) rc = cb::fail(CB_ENOMEM, "pointwise hi/lo weight upload failed: %s", cudaGetErrorString(e));
+            if (!rc) rc = make_map_2d(&b.tmBs, b.pw_whl, (uint64_t)2 * b.Cout, (uint64_t)b.C, (uint32_t)b.Cout, 32);
+          }
+        }
       }
+    }
+  }
+  if (!rc) {
+    // which blocks run on the halo kernel, and from that the storage format of every tensor between them
+    const bool precise = !d->fp16_legacy && !d->no_fuse && !d->force_simt && !d->no_halo;
+    int layer = 0;
+    for (Block& b : d->blocks) {
+      const int dw_layer = layer + 1;
+      b.runs_halo = b.has_pw && b.use_tc && b.fused && b.halo && !d->no_fuse && !d->force_simt && !d->no_halo && d->stop_layer != dw_layer;
+      layer += b.has_pw ? 2 : 1;
+    }
+    d->layer_q.assign(d->layer_elems.size(), 0);
+    bool prev_q = precise;
+    layer = 0;
+    for (size_t i = 0; i < d->blocks.size(); ++i) {
+      Block& b = d->blocks[i];
+      b.mode = 0;
+      if (b.runs_halo && prev_q) {
+        b.mode = kInQ;
+        if ((int)i < d->split_blocks && split_shape_supported(b.Cout) && b.pw_whl) b.mode |= kSplit;
+        if (i + 1 < d->blocks.size() && d->blocks[i + 1].runs_halo) b.mode |= kOutQ;
+        d->layer_q[layer] = 1;  // this block's input
+      } else {
+        prev_q = false;
+      }
+      layer += b.has_pw ? 2 : 1;
+    }
+    d->stem_q = !d->blocks.empty() && (d->blocks[0].mode & kInQ);
+    if (d->stem_q) {
+      std::vector<float> bq(32);
+      for (int nn = 0; nn < 32; ++nn) bq[nn] = (float)((double)w->conv1_b[nn] * (32767.0 / 6.0));
+      rc = upload_f32(&d->conv1_bq, bq.data(), 32);
     }
   }
   if (rc) {
@@ -2177,7 +2379,11 @@ int cb_descriptor_destroy(cb_descriptor* d) {
     cudaFree(b.dw_b);
     cudaFree(b.pw_w);
     cudaFree(b.pw_b);
+    void* qs[] = {b.dw_wq, b.dw_bq, b.pw_bq, b.pw_whl};
+    for (void* q : qs)
+      if (q) cudaFree(q);
   }
+  if (d->conv1_bq) cudaFree(d->conv1_bq);
   void* ptrs[] = {d->vlad_whi, d->vlad_wlo, d->conv1_hi, d->conv1_lo, d->conv1_w, d->conv1_b, d->vlad_w, d->vlad_b, d->vlad_c, d->act[0], d->act[1],
                   d->act[2], d->assign,  d->Vraw,    d->img_dev, d->out_dev};
   for (void* p : ptrs)
@@ -2241,7 +2447,13 @@ int64_t cb_descriptor_get_activation(cb_descriptor* d, int layer, float* out, in
   std::vector<__half> tmp(ne);
   CB_CUDA(cudaStreamSynchronize(d->stream));
   CB_CUDA(cudaMemcpy(tmp.data(), d->act[d->last_buf], ne * sizeof(__half), cudaMemcpyDeviceToHost));
-  for (size_t i = 0; i < ne; ++i) out[i] = __half2float(tmp[i]);
+  const bool q = (size_t)layer < d->layer_q.size() && d->layer_q[layer];  // q15 storage between halo blocks
+  if (q) {
+    const uint16_t* u = reinterpret_cast<const uint16_t*>(tmp.data());
+    for (size_t i = 0; i < ne; ++i) out[i] = (float)((double)u[i] * (6.0 / 32767.0));
+  } else {
+    for (size_t i = 0; i < ne; ++i) out[i] = __half2float(tmp[i]);
+  }
   return (int64_t)ne;
 }
 

@@ -1,10 +1,12 @@
 """GPU parity: NetVLAD forward (through the C ABI) vs the torch-CPU oracle.
 
-Floating-point path: activations and pointwise weights are fp16 on the device (fp32 accumulate in
-TMEM), the oracle is fp64.  north_star states no tolerance for the descriptor ("L2 error reported");
-the bound asserted here -- L2 distance < 2e-2 between unit vectors (cosine > 0.9998; measured 6e-4 on the
-gray 4096-D model, 3e-3..1.2e-2 on the 8192-D model), i.e. a dot-product perturbation far below the 0.85 / 0.9
-decision thresholds -- is this repo's own and is dominated by fp16 activation storage."""
+Floating-point path.  The oracle is fp64; the reference (Keras) computes in fp32.  The device keeps the activations
+between the fused blocks as q15 fixed point of the ReLU6 range (step 1.8e-4) and splits the tensor-core operands of
+the first four blocks into fp16 hi + lo, so that the descriptor is within **2e-3** (L2 distance of
+unit vectors; measured 4e-4 .. 1e-3) of the oracle on all four shipped models, including the benchmarked
+480x640x3 -> 8192-D configuration and EuRoC's 480x752.  north_star's criterion -- identical top-k candidates -- is
+asserted on top of that in tests/test_pipeline_gpu.py.  The cross-check paths (CB_DESC_FP16 / CB_NO_HALO / CB_NO_FUSE /
+CB_PW_SIMT) keep round 1's fp16 arithmetic and its 2e-2 bound."""
 import os
 
 import numpy as np
@@ -14,7 +16,8 @@ from tests import golden_io, synth
 
 pytestmark = pytest.mark.gpu
 
-L2_TOL = 2e-2
+L2_TOL = 2e-3
+L2_TOL_FP16 = 2e-2  # the fp16 cross-check paths
 
 
 def _net(model):
@@ -24,12 +27,16 @@ def _net(model):
 
 
 @pytest.mark.parametrize("model,c", [("gray_conv6", 1), ("mobilenet_conv7", 3), ("mobilenetv2_block9_gray", 1), ("mobilenet_pw6", 3)])
-@pytest.mark.parametrize("h,w", [(96, 128), (240, 320)])
+@pytest.mark.parametrize("h,w", [(96, 128), (240, 320), (480, 640), (480, 752)])
 def test_descriptor_matches_golden(native_lib, cuda_device, model, c, h, w):
     from cerebro_b200.descriptor import NetvladDescriptor
 
-    gold = golden_io.load("netvlad_golden.npz")["%s_%dx%d_desc64" % (model, h, w)]
-    imgs = synth.band_limited_images(2, h, w, c, seed=h + c)
+    key = "%s_%dx%d_desc64" % (model, h, w)
+    z = golden_io.load("netvlad_golden.npz")
+    if key not in z.files:
+        pytest.skip("no golden for %s" % key)  # 480-row goldens: the benchmarked model + the 4096-D gray model
+    gold = z[key]
+    imgs = synth.band_limited_images(2, h, w, c, seed=h + c + (w if h == 480 else 0))
     nd = NetvladDescriptor(_net(model), h, w, c, max_batch=2)
     d = nd.compute(imgs)
     assert d.shape == gold.shape
@@ -129,7 +136,7 @@ def test_tcgen05_path_agrees_with_cuda_core_path(native_lib, cuda_device):
         nd.close()
     finally:
         os.environ.pop("CB_PW_SIMT", None)
-    assert np.linalg.norm(a - b, axis=1).max() < 2e-3
+    assert np.linalg.norm(a - b, axis=1).max() < L2_TOL_FP16
     # the fused depthwise->pointwise kernel (default) vs separate depthwise + TMA-fed GEMM kernels
     os.environ["CB_NO_FUSE"] = "1"
     try:
@@ -138,7 +145,27 @@ def test_tcgen05_path_agrees_with_cuda_core_path(native_lib, cuda_device):
         nd.close()
     finally:
         os.environ.pop("CB_NO_FUSE", None)
-    assert np.linalg.norm(a - c_, axis=1).max() < 2e-3
+    assert np.linalg.norm(a - c_, axis=1).max() < L2_TOL_FP16
+    assert np.linalg.norm(b - c_, axis=1).max() < 4e-3  # the two fp16 paths agree closely with each other
+    # round 1's arithmetic on the halo kernel (fp16 storage and operands) and a 7-block split
+    for var, tol in (("CB_DESC_FP16", L2_TOL_FP16), ("CB_NO_HALO", L2_TOL_FP16)):
+        os.environ[var] = "1"
+        try:
+            nd = NetvladDescriptor(net, h, w, c, max_batch=3)
+            e_ = nd.compute(imgs)
+            nd.close()
+        finally:
+            os.environ.pop(var, None)
+        assert np.linalg.norm(a - e_, axis=1).max() < tol, var
+        assert np.linalg.norm(c_ - e_, axis=1).max() < 4e-3, var
+    os.environ["CB_DESC_SPLIT"] = "5"
+    try:
+        nd = NetvladDescriptor(net, h, w, c, max_batch=3)
+        f_ = nd.compute(imgs)
+        nd.close()
+    finally:
+        os.environ.pop("CB_DESC_SPLIT", None)
+    assert np.linalg.norm(a - f_, axis=1).max() < L2_TOL
 
 
 @pytest.mark.parametrize("h,w", [(120, 188), (97, 126), (99, 127)])

@@ -36,8 +36,14 @@ def main():
         w = load_keras_file(path)
         np.savez(os.path.join(OUT, "keras_raw_%s.npz" % name), **{k.replace("/", "__"): v for k, v in w.items()})
         c = (w["conv1/kernel"] if "conv1/kernel" in w else w["Conv1/kernel"]).shape[2]
-        for (h, wd) in ((96, 128), (240, 320)):
-            imgs = synth.band_limited_images(2, h, wd, c, seed=h + c)
+        sizes = [(96, 128), (240, 320)]
+        # the benchmarked configuration (480x640, BASELINE configs 2/4) and EuRoC's 480x752 (config 1)
+        if name in ("mobilenet_conv7", "gray_conv6"):
+            sizes.append((480, 640))
+        if name == "mobilenet_conv7":
+            sizes.append((480, 752))
+        for (h, wd) in sizes:
+            imgs = synth.band_limited_images(2, h, wd, c, seed=h + c + (wd if h == 480 else 0))
             d64 = netvlad.describe(imgs, w, dtype="float64")
             gold["%s_%dx%d_desc64" % (name, h, wd)] = d64
     np.savez_compressed(os.path.join(OUT, "netvlad_golden.npz"), **gold)
