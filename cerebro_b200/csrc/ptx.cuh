@@ -177,7 +177,7 @@ int encode_fn(EncodeTiledFn* out) {
 // NHWC fp16 activation [frames][H][W][C] as a 4-D tensor (C, W, H, frames); box = one K block of channels of a
 // halo patch.  No swizzle: the depthwise producers read 16-byte channel groups of consecutive pixels.
 int make_map_halo(CUtensorMap* map, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t frames, uint32_t box_c,
-                  uint32_t box_w, uint32_t box_h, bool swizzle128 = false) {
+                  uint32_t box_w, uint32_t box_h, int swizzle_bytes = 0) {
   EncodeTiledFn fn = nullptr;
   int rc = encode_fn(&fn);
   if (rc) return rc;
@@ -186,7 +186,8 @@ int make_map_halo(CUtensorMap* map, const void* base, uint64_t C, uint64_t W, ui
   const cuuint32_t box[4] = {box_c, box_w, box_h, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cb::fail(CB_ECUDA, "cuTensorMapEncodeTiled (halo) failed with CUresult %d", (int)r);
   return CB_OK;

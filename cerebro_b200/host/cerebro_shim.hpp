@@ -13,6 +13,9 @@
 // tracked-feature count, image, VectorXd descriptor as std::vector<double>).  No Eigen/OpenCV/ROS needed.
 #pragma once
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
+#include <functional>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -166,7 +169,17 @@ class Cerebro {
       DataNode* node = kv.second;
       if (!node->isKeyFrame() || node->isWholeImageDescriptorAvailable()) continue;  // :189
       if (last_processed_set_ && !(last_processed_ < kv.first)) continue;
+      // :189-203 "dynamic skip": keyframes arriving faster than a descriptor takes are dropped at random.  With the
+      // device path the estimate is 0-1 ms, so skip_frac <= 0 at any realistic keyframe rate and nothing is dropped.
+      ++n_considered_;
+      const double diff_ms = (kv.first.toSec() - (last_processed_set_ ? last_processed_.toSec() : 0.0)) * 1000.;
+      const int incoming_diff_ms = diff_ms > 2147483647. ? 2147483647 : (int)diff_ms;  // first keyframe: ros::Time() = 0
+      const float skip_frac = 1.0f - incoming_diff_ms / float(estimated_descriptor_compute_time_ms);
+      last_processed_ = kv.first;  // advances for skipped keyframes too (:196)
+      last_processed_set_ = true;
+      if (dynamic_skip_enabled && n_considered_ > 4 && (rand_fn_() / float(RAND_MAX)) < skip_frac) continue;
       if (node->getNumberOfSuccessfullyTrackedFeatures() < 20) continue;  // :206-210
+      const auto t_begin = std::chrono::steady_clock::now();
       // :229-234: the stored image may have the other channel count (CV_GRAY2BGR replicates, CV_BGR2GRAY is OpenCV 4's 8-bit
       // fixed point (3735 B + 19235 G + 9798 R + 2^14) >> 15; OpenCV 3 used (1868, 9617, 4899) >> 14, at most one level off)
       const size_t px = (size_t)rows_ * cols_;
@@ -195,8 +208,8 @@ class Cerebro {
         std::lock_guard<std::mutex> lk(m_wholeImageComputedList);
         wholeImageComputedList.push_back(kv.first);  // :275
       }
-      last_processed_ = kv.first;
-      last_processed_set_ = true;
+      estimated_descriptor_compute_time_ms =
+          (int)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t_begin).count();  // :281
       ++done;
     }
     return done;
@@ -207,9 +220,16 @@ class Cerebro {
     auto* data_map = dataManager->getDataMapRef();
     const int l = wholeImageComputedList_size();
     if (l - last_l_ < 3) return false;  // :962
-    for (int s = last_l_; s < l; ++s) {  // "Fill descriptors [last_l, l) into M" :1005-1012 -> device DB
-      std::vector<double> v = data_map->at(wholeImageComputedList_at(s))->getWholeImageDescriptor();
-      if (cb_index_add_f64(index_, 1, v.data()) != CB_OK) return false;
+    // "Fill descriptors [last_l, l) into M" :1005-1012 -> device DB.  Rows are counted as they go in, so a failure part-way
+    // (e.g. the index is full: the reference's M has 29000 columns) neither re-adds rows on the next wake-up nor lets
+    // index labels drift from wholeImageComputedList; it is reported, not swallowed.
+    for (; n_added_ < l; ++n_added_) {
+      std::vector<double> v = data_map->at(wholeImageComputedList_at(n_added_))->getWholeImageDescriptor();
+      if (cb_index_add_f64(index_, 1, v.data()) != CB_OK) {
+        last_status_ = CB_EINVAL;
+        std::fprintf(stderr, "[descrip_N__dot__descrip_0_N] row %d not added: %s\n", n_added_, cb_last_error());
+        return false;
+      }
     }
     int found = 0;
     int64_t prev = -1, am[3];
@@ -217,7 +237,12 @@ class Cerebro {
     const int rc = cb_index_naive_candidate(index_, l, start_adding_descriptors_to_index_after, LOCALITY_THRESH,
                                             DOT_PROD_THRESH, &found, &prev, &score, am);  // :1019-1056
     last_l_ = l;
-    if (rc != CB_OK || !found) return false;
+    last_status_ = rc;
+    if (rc != CB_OK) {
+      std::fprintf(stderr, "[descrip_N__dot__descrip_0_N] %s\n", cb_last_error());
+      return false;
+    }
+    if (!found) return false;
     std::lock_guard<std::mutex> lk(m_foundLoops);
     foundLoops.push_back(std::make_tuple(wholeImageComputedList_at(l - 1), wholeImageComputedList_at((int)prev), score));  // :1078-1081
     return true;
@@ -232,6 +257,10 @@ class Cerebro {
 
   int descriptor_size = -1;
   bool descriptor_size_available = false;
+  int estimated_descriptor_compute_time_ms = 0;  // Cerebro.cpp:117, :281
+  bool dynamic_skip_enabled = true;
+  void set_rand(std::function<int()> f) { rand_fn_ = std::move(f); }
+  int last_status() const { return last_status_; }  // CB_OK, or the error of the last run_step
 
  private:
   cb_descriptor* desc_ = nullptr;
@@ -248,6 +277,10 @@ class Cerebro {
   Time last_processed_;
   bool last_processed_set_ = false;
   int last_l_ = 0;
+  int n_added_ = 0;       // rows of wholeImageComputedList already in the device index
+  int last_status_ = 0;
+  int n_considered_ = 0;  // n_computed of Cerebro.cpp:168
+  std::function<int()> rand_fn_ = [] { return std::rand(); };
 };
 
 }  // namespace cerebro_b200

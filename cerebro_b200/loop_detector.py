@@ -16,6 +16,7 @@ desc -> search -> PnP on one GPU, optionally with the DB sharded over the ranks 
 from __future__ import annotations
 
 import json
+import math
 
 import numpy as np
 
@@ -71,7 +72,8 @@ class ProcessedLoopCandidate:
     def makeLoopEdgeMsgWithConsistencyCheck(self):  # ProcessedLoopCandidate.cpp:40-125
         if len(self.opX_b_T_a) != 3:
             return None
-        if abs(int(self.t_1 - self.t_2)) < 10:  # :49-56, ros::Duration::sec
+        # :49-56 -- ros::Duration::sec is floor-normalised (nsec >= 0): -9.5 s reads as sec = -10
+        if abs(math.floor(self.t_1 - self.t_2)) < 10:
             return None
         op1, op2, icp = self.opX_b_T_a
         op1_m_op2 = np.linalg.inv(op1) @ op2
@@ -115,6 +117,16 @@ def consistent_pose_compute(fe, pnp, K, img3d_a, img3d_b, match_results, stamps,
     for p in range(n):
         pf = int(match_results[p]["n_inliers"])
         if pf < 150:  # "too few gms matches ... rejecting this loopcandidate"
+            out.append((None, None))
+            continue
+        # A solver that refused (< 20 valid-depth points: confidence -1, DlsPnpWithRansac.cpp:136-139) or found no model
+        # (best_hyp < 0) leaves the reference's output matrix uninitialised, which then fails its NaN / consistency test;
+        # the device returns identity for both cases, so they are rejected here explicitly.
+        solved = all(
+            float(r["confidence"][q]) >= 0.0 and int(r["best_hyp"][q]) >= 0
+            for r, q in ((r_pnp, p), (r_pnp, n + p), (r_icp, p))
+        )
+        if not solved:
             out.append((None, None))
             continue
         op1 = r_pnp["T"][p]
@@ -221,6 +233,10 @@ class Cerebro:
         self._found = []  # foundLoops (Cerebro.h:157-158): (t_curr, t_prev, score)
         self._processed = []  # processedloopcandi_list (Cerebro.h:199-200)
         self._last_l = 0
+        # dynamic-skip state of descriptor_computer_thread (Cerebro.cpp:117, 166-170)
+        self.estimated_descriptor_compute_time_ms = 0
+        self._last_proc_timestamp = 0.0  # ros::Time()
+        self._n_considered = 0
         self._last_consumed = 0
         self.hyp_manager = HypothesisManager()  # faiss_multihypothesis_tracking's (Cerebro.cpp:757)
 
@@ -275,12 +291,39 @@ class Cerebro:
         return state_io.save_state(save_folder_name, self._whole, rows.astype(np.float64))
 
     # ---- descriptor_computer_thread body (Cerebro.cpp:169-298), for the keyframes handed in
-    def descriptor_step(self, stamps, images_u8, n_tracked=None):
-        """images_u8 [n, rows, cols, chnls]; keyframes with < 20 tracked features are skipped
-        (Cerebro.cpp:206-210).  Descriptors are appended to the device DB in arrival order."""
-        keep = [i for i in range(len(stamps)) if n_tracked is None or n_tracked[i] >= 20]
+    RAND_MAX = 2147483647
+
+    def _dynamic_skip(self, stamp, rand):
+        """The reference's "dynamic skip" (Cerebro.cpp:189-203): when keyframes arrive faster than a descriptor takes,
+        drop them with probability ``1 - incoming_diff_ms / estimated_descriptor_compute_time_ms`` (after the first four;
+        ``last_proc_timestamp`` advances for skipped keyframes too).  Stamps in seconds.  An estimate of 0 ms -- a batch
+        that took less than a millisecond per keyframe -- gives skip_frac = -inf, i.e. never skip."""
+        self._n_considered += 1
+        incoming_diff_ms = min(int((stamp - self._last_proc_timestamp) * 1000.0), 2147483647)  # :193, int truncation
+        est = np.float32(self.estimated_descriptor_compute_time_ms)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            skip_frac = np.float32(1.0) - np.float32(incoming_diff_ms) / est  # :194
+        self._last_proc_timestamp = stamp  # :196
+        return self._n_considered > 4 and np.float32(rand() / np.float32(self.RAND_MAX)) < skip_frac  # :199
+
+    def descriptor_step(self, stamps, images_u8, n_tracked=None, rand=None):
+        """images_u8 [n, rows, cols, chnls].  Per keyframe, in arrival order: the dynamic random skip when ``rand`` is given
+        (a ``rand()`` stand-in returning 0..RAND_MAX, Cerebro.cpp:193-203; without it nothing is skipped -- one batched
+        device call outruns any keyframe rate), then keyframes with < 20 tracked features are dropped
+        (Cerebro.cpp:206-210).  Descriptors are appended to the device DB in arrival order;
+        ``estimated_descriptor_compute_time_ms`` becomes the batch's wall time per keyframe (int ms, :281)."""
+        import time
+
+        keep = []
+        for i in range(len(stamps)):
+            if rand is not None and self._dynamic_skip(stamps[i], rand):
+                continue
+            if n_tracked is not None and n_tracked[i] < 20:
+                continue
+            keep.append(i)
         if not keep:
             return 0
+        t0 = time.perf_counter()
         imgs = np.asarray(images_u8)[keep]
         n_ch = getattr(self.descriptor, "chnls", None)
         if n_ch in (1, 3):  # Cerebro.cpp:229-234: gray <-> BGR fix-up when the stored image and the model disagree
@@ -289,6 +332,7 @@ class Cerebro:
         self.index.add(desc)
         for i in keep:
             self._whole.append(stamps[i])
+        self.estimated_descriptor_compute_time_ms = int((time.perf_counter() - t0) * 1000.0 / len(keep))
         return len(keep)
 
     # ---- one wake-up of descrip_N__dot__descrip_0_N (Cerebro.cpp:956-1100)

@@ -68,3 +68,42 @@ def loop_candidate(rng, n=200, noise=1e-3, outlier_frac=0.2, max_angle_deg=30.0,
     T[:3, :3] = R
     T[:3, 3] = t
     return Xa, uv, T, mask
+
+
+def textured_scenes(n, h, w, c, seed):
+    """uint8 images whose LOCAL statistics differ from image to image (so that whole-image descriptors differ, which
+    band-limited noise does not achieve): a few regions (nearest-seed cells), each filled with an oriented grating /
+    checkerboard / block noise / ramp of random scale, orientation, contrast and colour, plus sensor-like noise."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    out = np.empty((n, h, w, c), dtype=np.uint8)
+    for i in range(n):
+        k = int(rng.integers(3, 7))
+        cy, cx = rng.uniform(0, h, k), rng.uniform(0, w, k)
+        cell = np.argmin((yy[None] - cy[:, None, None]) ** 2 + (xx[None] - cx[:, None, None]) ** 2, axis=0)
+        img = np.zeros((h, w, c), dtype=np.float32)
+        for r in range(k):
+            kind = int(rng.integers(0, 4))
+            scale = float(rng.uniform(3.0, 40.0))
+            th = float(rng.uniform(0, np.pi))
+            u = (xx * np.cos(th) + yy * np.sin(th)) / scale
+            v = (-xx * np.sin(th) + yy * np.cos(th)) / scale
+            if kind == 0:
+                t = 0.5 + 0.5 * np.sin(2 * np.pi * u + rng.uniform(0, 6.28))
+            elif kind == 1:
+                t = ((np.floor(u) + np.floor(v)) % 2).astype(np.float32)
+            elif kind == 2:
+                lo = rng.standard_normal((int(h / scale) + 3, int(w / scale) + 3)).astype(np.float32)
+                iy = np.clip((yy / scale).astype(int), 0, lo.shape[0] - 1)
+                ix = np.clip((xx / scale).astype(int), 0, lo.shape[1] - 1)
+                t = (lo[iy, ix] > 0).astype(np.float32)
+            else:
+                t = (u - u.min()) / (u.max() - u.min() + 1e-6)
+            base = rng.uniform(20, 200, c).astype(np.float32)
+            amp = rng.uniform(20, 120) * rng.uniform(0.3, 1.0, c).astype(np.float32)
+            tex = base[None, None, :] + amp[None, None, :] * t[:, :, None]
+            m = cell == r
+            img[m] = tex[m]
+        img += rng.standard_normal((h, w, c)).astype(np.float32) * 4.0
+        out[i] = np.clip(img, 0, 255).astype(np.uint8)
+    return out

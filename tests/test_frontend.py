@@ -254,5 +254,12 @@ def test_candidate_to_pose_chain(native_lib, cuda_device):
     # same candidate seen 5 s apart: the consistency check refuses it (ProcessedLoopCandidate.cpp:49-56)
     _, edge2 = consistent_pose_compute(fe, pb, K, img_a[None], img_b[None], [r], [(105.0, 100.0)], seed=3)[0]
     assert edge2 is None
+    # every depth outside the 0.1 .. 25 m gate: the solvers refuse (confidence -1, identity pose on the device); the
+    # reference's uninitialised matrices fail its checks -- here the candidate must be rejected, not published as identity
+    far_a, far_b = img_a.copy(), img_b.copy()
+    far_a[..., 2] = 60.0
+    far_b[..., 2] = 60.0
+    cand3, edge3 = consistent_pose_compute(fe, pb, K, far_a[None], far_b[None], [r], [(500.0, 100.0)], seed=3)[0]
+    assert cand3 is None and edge3 is None
     fe.close()
     pb.close()
