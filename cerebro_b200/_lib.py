@@ -103,6 +103,16 @@ _SIGNATURES = {
     "cb_index_search": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp]),
     "cb_index_search_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp]),
     "cb_topk_merge_device": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "cb_comm_get_unique_id": (C.c_int, [_vp]),
+    "cb_comm_create": (C.c_int, [C.POINTER(_vp), _vp, C.c_int, C.c_int, C.c_int]),
+    "cb_comm_destroy": (C.c_int, [_vp]),
+    "cb_comm_rank": (C.c_int, [_vp]),
+    "cb_comm_world": (C.c_int, [_vp]),
+    "cb_comm_nccl_version": (C.c_int, []),
+    "cb_index_attach_comm": (C.c_int, [_vp, _vp]),
+    "cb_index_search_sharded_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp]),
+    "cb_index_search_sharded": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp]),
+    "cb_index_gathered_queries": (_vp, [_vp]),
     "cb_index_naive_candidate": (
         C.c_int,
         [_vp, _i64, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(_i64), C.POINTER(C.c_double), C.POINTER(_i64)],

@@ -13,7 +13,7 @@ OUT_DIR = os.path.join(HERE, "_native")
 LIB = os.path.join(OUT_DIR, "libcerebro_b200.so")
 HARNESS = os.path.join(OUT_DIR, "cerebro_harness")
 STEREO_EMUL = os.path.join(OUT_DIR, "libstereo_emul.so")
-SOURCES = ["capi.cu", "search.cu", "pnp.cu", "netvlad.cu", "frontend.cu"]
+SOURCES = ["capi.cu", "comm.cu", "search.cu", "pnp.cu", "netvlad.cu", "frontend.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if r.returncode:
                 raise RuntimeError("nvcc failed for %s" % src)
     if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)

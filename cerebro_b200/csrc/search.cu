@@ -20,10 +20,13 @@
 //                         ranks them with the requested tie rule and writes the top k.
 //   merge_lists_kernel  : merges already-final fp64 lists (multi-GPU all-gather result).
 #include "common.cuh"
+#include "comm.cuh"
 #include "ptx.cuh"
 
 #include <math_constants.h>
 #include <stdlib.h>
+
+#include <vector>
 
 namespace {
 
@@ -532,12 +535,14 @@ finalize_kernel(const unsigned long long* __restrict__ ckeys, int n_chunks, cons
   }
 }
 
-// lists [n_lists][nq][k_in] (fp64 score, label) -> [nq][k_out]
+// lists [n_lists][nq][k_in] (fp64 score, label) -> [nq][k_out].  `list_stride` = elements between consecutive lists
+// (0: nq * k_in, the contiguous layout); the CTA for output query q reads input query q0 + q.
 __global__ void __launch_bounds__(32)
 merge_lists_kernel(const double* __restrict__ s, const long long* __restrict__ l, int n_lists, int nq,
                    int k_in, int k_out, int tie_high, double* __restrict__ out_s,
-                   long long* __restrict__ out_l) {
+                   long long* __restrict__ out_l, long long list_stride = 0, int q0 = 0) {
   const int q = blockIdx.x, lane = threadIdx.x;
+  if (list_stride == 0) list_stride = (long long)nq * k_in;
   WarpList<double> wl;
   wl.init();
   const int total = n_lists * k_in;
@@ -548,7 +553,7 @@ merge_lists_kernel(const double* __restrict__ s, const long long* __restrict__ l
     long long id = -1;
     if (in) {
       const int li = i / k_in, kk = i % k_in;
-      const size_t o = ((size_t)li * nq + q) * k_in + kk;
+      const size_t o = (size_t)li * list_stride + (size_t)(q0 + q) * k_in + kk;
       v = s[o];
       id = l[o];
     }
@@ -1225,6 +1230,20 @@ struct cb_index {
   __half* hl = nullptr;   // [capacity/256][d/32][4][128][32]
   __half* qhl = nullptr;  // [d/32][2][NQ][32], allocated for NQ = 128
   CUtensorMap tmA2, tmB2, tmB2w;  // tmB2: 64-query tile, tmB2w: 128-query tile
+  // cross-stream ordering: the host API runs on `stream`, the _device API on the caller's stream, and both share the
+  // rows, the lazily built planes and the scratch.  Whenever the launching stream changes, the new stream first waits
+  // for an event recorded on the previous one.
+  cudaStream_t last_stream = nullptr;
+  bool last_stream_set = false;
+  cudaEvent_t ev_order = nullptr;
+  // sharded search (cb_index_search_sharded*): communicator + gather buffers
+  cb_comm* comm = nullptr;   // not owned
+  float* gq = nullptr;       // [world * nq_local][d] all-gathered queries
+  size_t gq_bytes = 0;
+  double* glist = nullptr;   // this shard's lists, packed [scores nq_all*k | labels nq_all*k]
+  size_t glist_bytes = 0;
+  double* gall = nullptr;    // [world] of the above
+  size_t gall_bytes = 0;
   // optional device-side timing of the sweep kernel (bench.py roofline)
   bool timing = false;
   cudaEvent_t ev[2 * 64] = {};
@@ -1232,6 +1251,17 @@ struct cb_index {
 };
 
 namespace {
+
+int order_after_previous(cb_index* ix, cudaStream_t st) {
+  if (ix->last_stream_set && ix->last_stream != st) {
+    if (!ix->ev_order) CB_CUDA(cudaEventCreateWithFlags(&ix->ev_order, cudaEventDisableTiming));
+    CB_CUDA(cudaEventRecord(ix->ev_order, ix->last_stream));
+    CB_CUDA(cudaStreamWaitEvent(st, ix->ev_order, 0));
+  }
+  ix->last_stream = st;
+  ix->last_stream_set = true;
+  return CB_OK;
+}
 
 int grow(void** p, size_t* cur, size_t need) {
   if (*cur >= need) return CB_OK;
@@ -1360,6 +1390,10 @@ bool ensure_planes(cb_index* ix, cudaStream_t st) {
 
 int search_device_impl(cb_index* ix, int nq, const float* xq_dev, int k, int64_t limit_rows,
                        int tie_mode, double* scores_dev, long long* labels_dev, cudaStream_t st) {
+  {
+    int rc0 = order_after_previous(ix, st);
+    if (rc0) return rc0;
+  }
   const int tie_high = tie_mode == CB_TIE_HIGH_LABEL;
   const int64_t n_rows = local_limit(ix, limit_rows);
   const int n_chunks = (int)((n_rows + kChunkRows - 1) / kChunkRows);
@@ -1557,8 +1591,12 @@ int cb_index_destroy(cb_index* ix) {
   cudaFree(ix->q_lo);
   cudaFree(ix->hl);
   cudaFree(ix->qhl);
+  cudaFree(ix->gq);
+  cudaFree(ix->glist);
+  cudaFree(ix->gall);
   for (cudaEvent_t ev : ix->ev)
     if (ev) cudaEventDestroy(ev);
+  if (ix->ev_order) cudaEventDestroy(ix->ev_order);
   cudaStreamDestroy(ix->stream);
   delete ix;
   return CB_OK;
@@ -1579,6 +1617,10 @@ const float* cb_index_device_rows(const cb_index* ix) { return ix ? ix->rows : n
 
 // copies the rows of [g0, g0+n) that belong to this shard from a (host or device) fp32 source
 static int add_impl(cb_index* ix, int64_t n, const float* x, cudaMemcpyKind kind, cudaStream_t st) {
+  {
+    int rc0 = order_after_previous(ix, st);
+    if (rc0) return rc0;
+  }
   const int64_t g0 = ix->ntotal;
   // first global label >= g0 owned by this shard
   int64_t first = g0 + ((ix->rank - g0 % ix->world) + ix->world) % ix->world;
@@ -1638,6 +1680,10 @@ int cb_index_add_local_device(cb_index* ix, int64_t n_local, const float* x_dev,
                     (long long)ix->nlocal, (long long)n_local);
   if (n_local == 0) return CB_OK;
   cb::DeviceGuard g(ix->device);
+  {
+    int rc0 = order_after_previous(ix, (cudaStream_t)stream);
+    if (rc0) return rc0;
+  }
   CB_CUDA(cudaMemcpyAsync(ix->rows + (size_t)ix->nlocal * ix->d, x_dev, (size_t)n_local * ix->d * sizeof(float),
                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   ix->nlocal += n_local;
@@ -1733,6 +1779,85 @@ int cb_topk_merge_device(int n_lists, int nq, int k_in, const double* scores_dev
   return CB_OK;
 }
 
+int cb_index_attach_comm(cb_index* ix, cb_comm* c) {
+  if (!ix) return cb::fail(CB_EINVAL, "index is NULL");
+  if (c && (c->world != ix->world || c->rank != ix->rank || c->device != ix->device))
+    return cb::fail(CB_EINVAL, "communicator is rank %d of %d on device %d, the index is shard %d of %d on device %d", c->rank, c->world,
+                    c->device, ix->rank, ix->world, ix->device);
+  ix->comm = c;
+  return CB_OK;
+}
+
+const float* cb_index_gathered_queries(const cb_index* ix) { return ix ? ix->gq : nullptr; }
+
+int cb_index_search_sharded_device(cb_index* ix, int nq_local, const float* xq_local_dev, int k, int64_t limit_rows, int tie_mode,
+                                   double* scores_dev, int64_t* labels_dev, void* stream) {
+  if (!ix || !xq_local_dev || !scores_dev || !labels_dev) return cb::fail(CB_EINVAL, "NULL argument to cb_index_search_sharded_device");
+  if (nq_local <= 0) return cb::fail(CB_EINVAL, "nq_local must be > 0");
+  if (k < 1 || k > kList) return cb::fail(CB_EINVAL, "k must be in [1,32], got %d", k);
+  cb::DeviceGuard g(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ix->world == 1)
+    return search_device_impl(ix, nq_local, xq_local_dev, k, limit_rows, tie_mode, scores_dev, (long long*)labels_dev, st);
+  if (!ix->comm) return cb::fail(CB_EINVAL, "sharded index without a communicator: call cb_index_attach_comm first");
+  const cb::NcclApi* api = cb::nccl_api();
+  if (!api) return CB_ENODEVICE;
+  const int world = ix->world, nq_all = world * nq_local;
+  const size_t list_elems = (size_t)nq_all * k;  // per shard: list_elems scores, then list_elems labels
+  int rc = grow((void**)&ix->gq, &ix->gq_bytes, (size_t)nq_all * ix->d * sizeof(float));
+  if (!rc) rc = grow((void**)&ix->glist, &ix->glist_bytes, 2 * list_elems * sizeof(double));
+  if (!rc) rc = grow((void**)&ix->gall, &ix->gall_bytes, (size_t)world * 2 * list_elems * sizeof(double));
+  if (rc) return rc;
+  // 1. everybody's new descriptors become everybody's queries
+  ncclResult_t r = api->AllGather(xq_local_dev, ix->gq, (size_t)nq_local * ix->d, ncclFloat32, ix->comm->comm, st);
+  if (r != ncclSuccess) return cb::fail(CB_ECUDA, "ncclAllGather (queries): %s", api->GetErrorString(r));
+  // 2. this shard's top-k of all of them (fp64 re-scored, global labels)
+  rc = search_device_impl(ix, nq_all, ix->gq, k, limit_rows, tie_mode, ix->glist, (long long*)(ix->glist + list_elems), st);
+  if (rc) return rc;
+  // 3. ONE all-gather of the packed (score, label) lists
+  r = api->AllGather(ix->glist, ix->gall, 2 * list_elems * sizeof(double), ncclInt8, ix->comm->comm, st);
+  if (r != ncclSuccess) return cb::fail(CB_ECUDA, "ncclAllGather (top-k lists): %s", api->GetErrorString(r));
+  // 4. the same deterministic merge on every rank, for its own queries
+  merge_lists_kernel<<<nq_local, 32, 0, st>>>(ix->gall, (const long long*)(ix->gall + list_elems), world, nq_all, k, k,
+                                              tie_mode == CB_TIE_HIGH_LABEL, scores_dev, (long long*)labels_dev,
+                                              (long long)(2 * list_elems), ix->rank * nq_local);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+int cb_index_search_sharded(cb_index* ix, int nq_local, const float* xq_local, int k, int64_t limit_rows, int tie_mode,
+                            float* distances, int64_t* labels, double* scores_f64) {
+  if (!ix || !xq_local || !labels) return cb::fail(CB_EINVAL, "NULL argument to cb_index_search_sharded");
+  if (nq_local <= 0) return cb::fail(CB_EINVAL, "nq_local must be > 0");
+  if (k < 1 || k > kList) return cb::fail(CB_EINVAL, "k must be in [1,32], got %d", k);
+  cb::DeviceGuard g(ix->device);
+  int rc = grow((void**)&ix->q_dev, &ix->q_bytes, (size_t)nq_local * ix->d * sizeof(float));
+  if (rc) return rc;
+  const size_t oe = (size_t)nq_local * k;
+  if (ix->out_elems < oe) {
+    if (ix->out_s) cudaFree(ix->out_s);
+    if (ix->out_l) cudaFree(ix->out_l);
+    ix->out_s = nullptr;
+    ix->out_l = nullptr;
+    ix->out_elems = 0;
+    CB_CUDA(cudaMalloc(&ix->out_s, oe * sizeof(double)));
+    CB_CUDA(cudaMalloc(&ix->out_l, oe * sizeof(long long)));
+    ix->out_elems = oe;
+  }
+  CB_CUDA(cudaMemcpyAsync(ix->q_dev, xq_local, (size_t)nq_local * ix->d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+  rc = cb_index_search_sharded_device(ix, nq_local, ix->q_dev, k, limit_rows, tie_mode, ix->out_s, (int64_t*)ix->out_l, ix->stream);
+  if (rc) return rc;
+  std::vector<double> hs(oe);
+  CB_CUDA(cudaMemcpyAsync(hs.data(), ix->out_s, oe * sizeof(double), cudaMemcpyDeviceToHost, ix->stream));
+  CB_CUDA(cudaMemcpyAsync(labels, ix->out_l, oe * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
+  CB_CUDA(cudaStreamSynchronize(ix->stream));
+  for (size_t i = 0; i < oe; ++i) {
+    if (distances) distances[i] = (float)hs[i];
+    if (scores_f64) scores_f64[i] = hs[i];
+  }
+  return CB_OK;
+}
+
 int cb_index_naive_candidate(cb_index* ix, int64_t l, int lag, int locality_thresh, float dot_thresh,
                              int* out_found, int64_t* out_prev, double* out_score, int64_t argmax3[3]) {
   if (!ix || !out_found) return cb::fail(CB_EINVAL, "NULL argument to cb_index_naive_candidate");
@@ -1779,6 +1904,10 @@ int cb_index_get_rows(cb_index* ix, int64_t first_local, int64_t n, float* out) 
   if (!ix || !out || first_local < 0 || n < 0 || first_local + n > ix->nlocal)
     return cb::fail(CB_EINVAL, "bad range for cb_index_get_rows");
   cb::DeviceGuard g(ix->device);
+  {
+    int rc0 = order_after_previous(ix, ix->stream);
+    if (rc0) return rc0;
+  }
   CB_CUDA(cudaMemcpyAsync(out, ix->rows + (size_t)first_local * ix->d, (size_t)n * ix->d * sizeof(float),
                           cudaMemcpyDeviceToHost, ix->stream));
   CB_CUDA(cudaStreamSynchronize(ix->stream));

@@ -164,14 +164,59 @@ def shard_rows(n_total: int, rank: int, world: int) -> np.ndarray:
     return np.arange(rank, n_total, world)
 
 
+COMM_ID_BYTES = 128
+
+
+class Comm:
+    """cb_comm: the NCCL communicator behind the C ABI.  ``Comm.from_torch_group()`` creates the id on rank 0 and hands it
+    round with torch.distributed (any backend) -- a C++ host would use its own transport for those 128 bytes."""
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int):
+        self._lib = _lib.load()
+        assert len(unique_id) == COMM_ID_BYTES
+        self._id = np.frombuffer(unique_id, dtype=np.uint8).copy()
+        h = C.c_void_p()
+        check(self._lib.cb_comm_create(C.byref(h), ptr(self._id), rank, world, device))
+        self._h = h
+        self.rank, self.world, self.device = rank, world, device
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = np.zeros(COMM_ID_BYTES, dtype=np.uint8)
+        check(_lib.load().cb_comm_get_unique_id(ptr(buf)))
+        return buf.tobytes()
+
+    @classmethod
+    def from_torch_group(cls, device: int, group=None):
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return cls(box[0], rank, world, device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cb_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ShardedIndex:
-    """Descriptor DB sharded over the ranks of a torch.distributed group (one process per GPU).
+    """Descriptor DB sharded over the GPUs of one box (one process per GPU).
 
-    Every rank calls ``add`` with the same global rows (or only its own via ``add_local``)
-    and ``search`` with the same queries; the only communication is one all-gather of the
-    per-shard top-k (world * nq * k * 16 bytes)."""
+    Every rank calls ``add`` with the same global rows (or only its own via ``add_local``).  ``search_sharded_device`` is the
+    product path: every rank passes its OWN queries and the C ABI does query all-gather -> local sweep -> ONE ncclAllGather
+    of the packed per-shard top-k -> merge (``cb_index_search_sharded_device``).  ``search_device`` (the same queries on
+    every rank, lists gathered with torch.distributed) is kept as the cross-check the tests compare it with."""
 
-    def __init__(self, d: int, capacity_per_shard: int, device: int, group=None):
+    def __init__(self, d: int, capacity_per_shard: int, device: int, group=None, comm: "Comm | None" = None):
         import torch.distributed as dist
 
         self.dist = dist
@@ -180,6 +225,13 @@ class ShardedIndex:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.local = IndexFlatIP(d, capacity_per_shard, device, self.rank, self.world)
         self.d = d
+        self.comm = None
+        if comm is not None:
+            self.attach_comm(comm)
+
+    def attach_comm(self, comm: "Comm"):
+        check(self.local._lib.cb_index_attach_comm(self.local._h, comm._h))
+        self.comm = comm
 
     @property
     def ntotal(self):
@@ -187,6 +239,40 @@ class ShardedIndex:
 
     def add(self, x):
         self.local.add(x)
+
+    def search_sharded_device(self, xq_local, k: int, limit_rows: int | None = None, tie: int = TIE_LOW_LABEL, out=None):
+        """CUDA tensor [nq_local, d] of THIS rank's queries in; merged global top-k of those queries out
+        (scores float64 [nq_local, k], labels int64 [nq_local, k]).  Collective: every rank must call it."""
+        import torch
+
+        assert xq_local.is_cuda and xq_local.dtype == torch.float32 and xq_local.is_contiguous()
+        nq = xq_local.numel() // self.d
+        if out is None:
+            s = torch.empty((nq, k), dtype=torch.float64, device=xq_local.device)
+            l = torch.empty((nq, k), dtype=torch.int64, device=xq_local.device)
+        else:
+            s, l = out
+        check(self.local._lib.cb_index_search_sharded_device(
+            self.local._h, nq, ptr(xq_local), k, -1 if limit_rows is None else int(limit_rows), tie, ptr(s), ptr(l),
+            _lib.current_stream_ptr()))
+        return s, l
+
+    def search_sharded(self, xq_local, k: int, limit_rows: int | None = None, tie: int = TIE_LOW_LABEL):
+        """Host arrays in / out through ``cb_index_search_sharded`` (blocking; the call a C++ host makes)."""
+        xq = np.ascontiguousarray(xq_local, dtype=np.float32).reshape(-1, self.d)
+        nq = xq.shape[0]
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        S = np.empty((nq, k), dtype=np.float64)
+        check(self.local._lib.cb_index_search_sharded(
+            self.local._h, nq, ptr(xq), k, -1 if limit_rows is None else int(limit_rows), tie, ptr(D), ptr(I), ptr(S)))
+        return D, I, S
+
+    def add_gathered_device(self, n_rows: int):
+        """Append the block the last ``search_sharded_device`` gathered (world * nq_local new descriptors in global,
+        rank-major order) to the sharded DB: every rank keeps its own rows, no second exchange."""
+        p = self.local._lib.cb_index_gathered_queries(self.local._h)
+        check(self.local._lib.cb_index_add_device(self.local._h, n_rows, p, _lib.current_stream_ptr()))
 
     def search_device(self, xq, k: int, limit_rows: int | None = None, tie: int = TIE_LOW_LABEL):
         import torch

@@ -486,8 +486,13 @@ class LoopPipeline:
         self.dim = self.desc.dim
         self.sharded = sharded
         if sharded:
+            from .index import Comm
+
             self.index = ShardedIndex(self.dim, db_rows_local, device)
             self.world = self.index.world
+            if self.world > 1:  # the collective search lives behind the C ABI (cb_index_search_sharded_device)
+                self.comm = Comm.from_torch_group(device)
+                self.index.attach_comm(self.comm)
         else:
             self.index = IndexFlatIP(self.dim, db_rows_local, device)
             self.world = 1
@@ -497,7 +502,8 @@ class LoopPipeline:
         self._side = None  # second CUDA stream for the verifier
 
     def step_device(self, images_dev, offsets_dev, X_dev, uv_dev, bufs):
-        """All inputs already in HBM.  Returns (labels [B*world,k], scores, pnp outputs).
+        """All inputs already in HBM.  Returns (labels [B,k] -- the merged global top-k of this rank's keyframes --,
+        scores, pnp outputs).
 
         The verifier does not depend on the descriptor/search chain of the same step (the reference runs them
         in different threads, cerebro_node.cpp:487-509), so it is issued on a second CUDA stream: its
@@ -511,10 +517,9 @@ class LoopPipeline:
             out = self.pnp.solve_device(offsets_dev, X_dev, uv_dev, self.params, out=bufs["pnp"])
         d = self.desc.compute_device(images_dev, out=bufs["desc"])
         if self.sharded and self.world > 1:
-            q = bufs["queries"]
-            self.index.dist.all_gather_into_tensor(q, d, group=self.index.group)
+            # one C-ABI call: query all-gather -> shard sweep -> ONE ncclAllGather of the packed top-k -> merge
+            s, l = self.index.search_sharded_device(d, self.k, out=bufs.get("search_out"))
         else:
-            q = d
-        s, l = self.index.search_device(q, self.k)
+            s, l = self.index.search_device(d, self.k)
         main.wait_stream(self._side)
         return l, s, out

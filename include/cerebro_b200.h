@@ -25,8 +25,12 @@
  *   - "_device" variants take raw device pointers (memory owned by the caller, e.g. a
  *     torch tensor's data_ptr) and a cudaStream_t passed as void* (NULL = the CUDA default
  *     stream, as everywhere in CUDA); they enqueue on exactly that stream and do not
- *     synchronise.  Use one stream per handle for its device calls (scratch is per handle).  All other variants take HOST pointers, copy in
- *     and out, and return when the result is in the caller's buffer.
+ *     synchronise.  Use one stream per handle for its device calls (scratch is per handle).  All other variants take
+ *     HOST pointers, copy in and out on the handle's own stream, and return when the result is in the caller's buffer.
+ *     An index handle orders the two against each other: whenever consecutive calls launch on different streams, the
+ *     later stream first waits (cudaStreamWaitEvent) for the work the earlier call enqueued, so a host search after an
+ *     add_device / search_device on the caller's stream sees the rows, planes and scratch that call produced.  The
+ *     caller's stream must still be alive at the next call on the handle.
  *   - there is no CPU fallback anywhere behind this ABI: without a CUDA device every
  *     create call fails with CB_ENODEVICE.
  */
@@ -114,6 +118,40 @@ CB_API int cb_index_search_device(cb_index* ix, int nq, const float* xq_dev, int
 CB_API int cb_topk_merge_device(int n_lists, int nq, int k_in, const double* scores_dev,
                          const int64_t* labels_dev, int k_out, int tie_mode, double* out_scores_dev,
                          int64_t* out_labels_dev, void* stream);
+
+/* ---- sharded database over the GPUs of one box (BASELINE configs 3 and 4).  The reference has no
+ * collective anywhere (its only transport is ROS); this is the scaling axis the B200 build adds: DB rows round-robin over
+ * `world` ranks (one per GPU), every rank scans its shard for all queries, ONE ncclAllGather of the per-shard top-k lists,
+ * and the same deterministic merge on every rank.  A rank is a process (torchrun) or a thread of one process (a ROS node
+ * driving 8 GPUs); NCCL is loaded at run time (dlopen), a single-GPU host never touches it. */
+typedef struct cb_comm cb_comm;
+#define CB_COMM_ID_BYTES 128 /* sizeof(ncclUniqueId) */
+/* rank 0 makes the id and hands it to the other ranks by whatever means the host has (a ROS parameter, a file,
+ * torch.distributed ...); then every rank calls cb_comm_create with the same id (collective: returns when all have). */
+CB_API int cb_comm_get_unique_id(uint8_t* id_out /* [CB_COMM_ID_BYTES] */);
+CB_API int cb_comm_create(cb_comm** out, const uint8_t* id, int rank, int world, int device);
+CB_API int cb_comm_destroy(cb_comm* c);
+CB_API int cb_comm_rank(const cb_comm* c);
+CB_API int cb_comm_world(const cb_comm* c);
+CB_API int cb_comm_nccl_version(void); /* e.g. 22809, -1 when NCCL cannot be loaded */
+
+/* Attach a communicator to a sharded index (rank / world must equal the index's). */
+CB_API int cb_index_attach_comm(cb_index* ix, cb_comm* c);
+
+/* Collective search: every rank passes ITS OWN nq_local queries (the descriptors of the keyframes it just computed; the
+ * same nq_local on every rank).  One call = ncclAllGather of the queries -> local sweep + top-k of all world * nq_local
+ * queries over this shard -> ONE ncclAllGather of the packed per-shard lists (fp64 score, int64 label) -> merge.
+ * Outputs the merged GLOBAL top-k of this rank's own queries: scores [nq_local][k] fp64, labels [nq_local][k] int64.
+ * Deterministic and independent of the sharding: the lists carry fp64 re-scored values (see cb_index_search).
+ * cb_index_gathered_queries returns the device block [world * nq_local][d] the call gathered (rank-major: global order of
+ * the new keyframes) -- passing it to cb_index_add_device appends the step's descriptors to the sharded DB without a
+ * second exchange. */
+CB_API int cb_index_search_sharded_device(cb_index* ix, int nq_local, const float* xq_local_dev, int k, int64_t limit_rows,
+                                   int tie_mode, double* scores_dev, int64_t* labels_dev, void* stream);
+/* host buffers in and out (blocking), the call a C++ / ROS host makes */
+CB_API int cb_index_search_sharded(cb_index* ix, int nq_local, const float* xq_local, int k, int64_t limit_rows, int tie_mode,
+                            float* distances, int64_t* labels, double* scores_f64);
+CB_API const float* cb_index_gathered_queries(const cb_index* ix);
 
 /* One iteration of Cerebro::descrip_N__dot__descrip_0_N (src/Cerebro.cpp:1019-1081) for
  * list length l on a NON-sharded index that already holds rows [0,l): scores of rows

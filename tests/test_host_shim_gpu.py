@@ -50,13 +50,11 @@ def test_cpp_shim_stream_matches_oracle(native_lib, cuda_device, tmp_path, model
     assert out["descriptor_size"] == dim and out["n_computed"] == n
     desc = NV.describe(imgs, raw, dtype="float32").astype(np.float64)
     expected = naive_stream(desc, list(range(3, n + 1, 3)))
-    # candidates within 2e-2 of the 0.85 acceptance threshold may legitimately differ (fp16 descriptors, L2 error ~1e-3);
-    # everything clear of it must be identical
-    clear = lambda lst: [(a, b, s) for a, b, s in lst if s > 0.87]
-    expected_c, found_c = clear(expected), clear([tuple(x) for x in out["found"]])
-    assert len(expected_c) >= 5
-    assert [(a, b) for a, b, _ in found_c] == [(a, b) for a, b, _ in expected_c]
-    assert np.allclose([s for *_, s in found_c], [s for *_, s in expected_c], atol=5e-3)
+    # identical candidate list, no carve-out around the 0.85 acceptance threshold (descriptor L2 error ~5e-4)
+    found = [tuple(x) for x in out["found"]]
+    assert len(expected) >= 5
+    assert [(a, b) for a, b, _ in found] == [(a, b) for a, b, _ in expected]
+    assert np.allclose([s for *_, s in found], [s for *_, s in expected], atol=1e-3)
     assert all(s > 0.85 for *_, s in out["found"])
     o = D.ransac_pnp(X, uv, D.sample_table(0, 0, 50, 180))
     assert abs(out["pnp"]["confidence"] - o["confidence"]) < 1e-6
