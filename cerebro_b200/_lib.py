@@ -35,6 +35,7 @@ class NetvladWeights(C.Structure):
         ("vlad_w", C.POINTER(C.c_float)),
         ("vlad_b", C.POINTER(C.c_float)),
         ("vlad_c", C.POINTER(C.c_float)),
+        ("vlad_ghost", C.c_int),
     ]
 
 
@@ -66,6 +67,7 @@ class NetvladV2Weights(C.Structure):  # cb_netvlad_v2_weights
         ("vlad_w", C.POINTER(C.c_float)),
         ("vlad_b", C.POINTER(C.c_float)),
         ("vlad_c", C.POINTER(C.c_float)),
+        ("vlad_ghost", C.c_int),
     ]
 
 
@@ -132,6 +134,7 @@ _SIGNATURES = {
     "cb_descriptor_destroy": (C.c_int, [_vp]),
     "cb_descriptor_dim": (C.c_int, [_vp]),
     "cb_descriptor_compute": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp]),
+    "cb_descriptor_compute_f64": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp]),
     "cb_descriptor_compute_device": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "cb_descriptor_get_activation": (_i64, [_vp, C.c_int, _vp, _i64]),
     "cb_ransac_params_default": (None, [C.POINTER(RansacParams)]),

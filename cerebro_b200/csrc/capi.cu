@@ -31,7 +31,7 @@ int select_device(int device, int* sm_count) {
 
 extern "C" {
 
-int cb_version(void) { return 1; }
+int cb_version(void) { return 2; }
 
 const char* cb_last_error(void) { return cb::tls_error_buffer(); }
 

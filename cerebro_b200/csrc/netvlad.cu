@@ -1561,9 +1561,11 @@ __global__ void __launch_bounds__(256) vlad_aggregate_kernel(const __half* __res
 
 // CTA per frame: sum the pixel-split partials, add the centre term, intra-normalise each cluster over D, flatten
 // K-major, L2-normalise (eps 1e-12 on the squared norm, like tf.nn.l2_normalize).  D <= 512.
+// GhostVLADLayer (predict_utils.py:110-141): only the first k_out clusters are kept (`v[:,0:num_clusters,:]`, :133) -- the ghost
+// clusters took part in the softmax, their rows never reach the norms or the output.
 __global__ void __launch_bounds__(512) vlad_norm_kernel(const float* __restrict__ Vp, const float* __restrict__ Ap,
                                                        const float* __restrict__ Cc /*[D][16]*/, int D,
-                                                       float* __restrict__ out) {
+                                                       float* __restrict__ out, int k_out) {
   __shared__ float s_ss[kK];
   const int f = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 16 warps, one per cluster
@@ -1593,10 +1595,11 @@ __global__ void __launch_bounds__(512) vlad_norm_kernel(const float* __restrict_
 #pragma unroll
   for (int k = 0; k < kK; ++k) {
     const float ik = rsqrtf(fmaxf(s_ss[k], 1e-12f));
-    tot += s_ss[k] * ik * ik;
+    if (k < k_out) tot += s_ss[k] * ik * ik;
   }
   const float inv_t = rsqrtf(fmaxf(tot, 1e-12f));
-  float* o = out + (size_t)f * kK * D + (size_t)warp * D;
+  if (warp >= k_out) return;
+  float* o = out + (size_t)f * k_out * D + (size_t)warp * D;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int d = lane + 32 * i;
@@ -1685,6 +1688,12 @@ struct cb_descriptor {
   float* out_dev = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // host-API uploads, overlapped with the forward pass chunk by chunk
+  // pinned staging ring for pageable callers (a cv::Mat's data, Cerebro.cpp:243-256): two buffers of `stage_frames` frames;
+  // the CPU copy of chunk i+1 into one overlaps the DMA + forward pass of chunk i from the other
+  uint8_t* stage_host[2] = {nullptr, nullptr};
+  cudaEvent_t stage_free[2] = {nullptr, nullptr};
+  int stage_frames = 8;
+  float* out_host = nullptr;  // pinned read-back buffer of cb_descriptor_compute_f64 (max_batch descriptors)
   std::vector<cudaEvent_t> ev_copy;
   bool force_simt = false;
   bool no_fuse = false;  // CB_NO_FUSE=1: separate depthwise + GEMM kernels
@@ -1908,7 +1917,7 @@ int run_vlad_head(cb_descriptor* d, int n, int cur, float* out_dev, cudaStream_t
   CB_CUDA(cudaFuncSetAttribute(vlad_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAggSmem));
   vlad_aggregate_kernel<<<dim3(kAggSplit, n), 256, kAggSmem, st>>>(d->act[cur], d->assign, P, d->D, d->Vraw, Ap);
   CB_LAUNCH_CHECK();
-  vlad_norm_kernel<<<n, 512, 0, st>>>(d->Vraw, Ap, d->vlad_c, d->D, out_dev);
+  vlad_norm_kernel<<<n, 512, 0, st>>>(d->Vraw, Ap, d->vlad_c, d->D, out_dev, d->K);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
@@ -2030,9 +2039,19 @@ int alloc_common(cb_descriptor* d, size_t max_elems, int n_bufs) {
 
 // stem weights (fp32 for the CUDA-core kernel, hi/lo fp16 with the 2/255 scale folded in for the tcgen05 one) and the
 // NetVLAD head (fp32 + hi/lo fp16 K-major soft-assignment weights, one feature-map tensor map per activation buffer)
-int setup_stem_and_head(cb_descriptor* d, const float* conv1_w, const float* conv1_b, const float* vlad_w, const float* vlad_b,
-                        const float* vlad_c) {
+int setup_stem_and_head(cb_descriptor* d, const float* conv1_w, const float* conv1_b, const float* vlad_w_in, const float* vlad_b_in,
+                        const float* vlad_c_in, int k_total) {
   const int chnls = d->chnls, max_batch = d->max_batch;
+  // the head kernels are built for 16 soft-assignment columns: fewer clusters (or clusters + ghosts) are padded with dead
+  // ones -- zero weights and centres, bias -1e30, so their softmax weight is exactly 0
+  std::vector<float> wpad((size_t)d->D * kK, 0.f), bpad(kK, -1e30f), cpad((size_t)d->D * kK, 0.f);
+  for (int dd = 0; dd < d->D; ++dd)
+    for (int k = 0; k < k_total; ++k) {
+      wpad[(size_t)dd * kK + k] = vlad_w_in[(size_t)dd * k_total + k];
+      cpad[(size_t)dd * kK + k] = vlad_c_in[(size_t)dd * k_total + k];
+    }
+  for (int k = 0; k < k_total; ++k) bpad[k] = vlad_b_in[k];
+  const float *vlad_w = wpad.data(), *vlad_b = bpad.data(), *vlad_c = cpad.data();
   int rc = upload_f32(&d->conv1_w, conv1_w, (size_t)9 * chnls * 32);
   if (!rc) {
     std::vector<__half> hi(32 * 32, __float2half_rn(0.f)), lo(32 * 32, __float2half_rn(0.f));
@@ -2096,7 +2115,9 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
   if (chnls != w->in_channels || (chnls != 1 && chnls != 3))
     return cb::fail(CB_EINVAL, "image channels %d do not match the model's %d (must be 1 or 3)", chnls, w->in_channels);
   if (rows < 32 || cols < 32 || max_batch < 1) return cb::fail(CB_EINVAL, "bad image size / batch");
-  if (w->vlad_k != kK) return cb::fail(CB_EINVAL, "only K=16 NetVLAD heads are built (got %d)", w->vlad_k);
+  if (w->vlad_k < 1 || w->vlad_k > kK || w->vlad_ghost < 0 || w->vlad_ghost >= w->vlad_k)
+    return cb::fail(CB_EINVAL, "NetVLAD heads are built for up to 16 soft-assignment clusters, ghosts included (got K=%d, ghosts=%d)",
+                    w->vlad_k, w->vlad_ghost);
   int sm = 0;
   int rc = cb::select_device(device, &sm);
   if (rc) return rc;
@@ -2161,13 +2182,13 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
   d->Hf = h;
   d->Wf = wd;
   d->D = c;
-  d->K = w->vlad_k;
+  d->K = w->vlad_k - w->vlad_ghost;  // clusters that reach the output
   if (w->vlad_d != c || c % 64 || c > 512) {
     cb_descriptor_destroy(d);
     return cb::fail(CB_EINVAL, "NetVLAD input dim %d does not match backbone output %d (or not a multiple of 64)", w->vlad_d, c);
   }
   rc = alloc_common(d, max_elems, 2);
-  if (!rc) rc = setup_stem_and_head(d, w->conv1_w, w->conv1_b, w->vlad_w, w->vlad_b, w->vlad_c);
+  if (!rc) rc = setup_stem_and_head(d, w->conv1_w, w->conv1_b, w->vlad_w, w->vlad_b, w->vlad_c, w->vlad_k);
   cudaError_t e = cudaSuccess;
   for (size_t i = 0; i < d->blocks.size() && !rc; ++i) {
     Block& b = d->blocks[i];
@@ -2290,7 +2311,9 @@ int cb_descriptor_create_v2(cb_descriptor** out, const cb_netvlad_v2_weights* w,
   if (chnls != w->in_channels || (chnls != 1 && chnls != 3))
     return cb::fail(CB_EINVAL, "image channels %d do not match the model's %d (must be 1 or 3)", chnls, w->in_channels);
   if (rows < 32 || cols < 32 || max_batch < 1) return cb::fail(CB_EINVAL, "bad image size / batch");
-  if (w->vlad_k != kK) return cb::fail(CB_EINVAL, "only K=16 NetVLAD heads are built (got %d)", w->vlad_k);
+  if (w->vlad_k < 1 || w->vlad_k > kK || w->vlad_ghost < 0 || w->vlad_ghost >= w->vlad_k)
+    return cb::fail(CB_EINVAL, "NetVLAD heads are built for up to 16 soft-assignment clusters, ghosts included (got K=%d, ghosts=%d)",
+                    w->vlad_k, w->vlad_ghost);
   int sm = 0;
   int rc = cb::select_device(device, &sm);
   if (rc) return rc;
@@ -2356,13 +2379,13 @@ int cb_descriptor_create_v2(cb_descriptor** out, const cb_netvlad_v2_weights* w,
   d->Hf = h;
   d->Wf = wd;
   d->D = c;
-  d->K = w->vlad_k;
+  d->K = w->vlad_k - w->vlad_ghost;  // clusters that reach the output
   if (w->vlad_d != c_nat || c_nat % 64 || c > 512) {
     cb_descriptor_destroy(d);
     return cb::fail(CB_EINVAL, "NetVLAD input dim %d does not match backbone output %d (or not a multiple of 64)", w->vlad_d, c_nat);
   }
   rc = alloc_common(d, max_elems, 3);
-  if (!rc) rc = setup_stem_and_head(d, w->conv1_w, w->conv1_b, w->vlad_w, w->vlad_b, w->vlad_c);
+  if (!rc) rc = setup_stem_and_head(d, w->conv1_w, w->conv1_b, w->vlad_w, w->vlad_b, w->vlad_c, w->vlad_k);
   c_nat = 32;
   for (int i = 0; i < w->n_blocks && !rc; ++i) {
     const cb_ir_block& src = w->blocks[i];
@@ -2407,6 +2430,11 @@ int cb_descriptor_destroy(cb_descriptor* d) {
                   d->act[2], d->assign,  d->Vraw,    d->img_dev, d->out_dev};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (d->stage_host[i]) cudaFreeHost(d->stage_host[i]);
+    if (d->stage_free[i]) cudaEventDestroy(d->stage_free[i]);
+  }
+  if (d->out_host) cudaFreeHost(d->out_host);
   if (d->stream) cudaStreamDestroy(d->stream);
   if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
   for (cudaEvent_t ev : d->ev_copy) cudaEventDestroy(ev);
@@ -2423,18 +2451,36 @@ int cb_descriptor_compute_device(cb_descriptor* d, int n, const uint8_t* images_
   return forward(d, n, images_dev, out_dev, (cudaStream_t)stream);
 }
 
-int cb_descriptor_compute(cb_descriptor* d, int n, const uint8_t* images, int64_t row_stride_bytes, float* out) {
-  if (!d || !images || !out) return cb::fail(CB_EINVAL, "NULL argument to cb_descriptor_compute");
-  if (n < 1 || n > d->max_batch) return cb::fail(CB_EINVAL, "batch %d outside [1,%d]", n, d->max_batch);
-  cb::DeviceGuard g(d->device);
+namespace {
+
+bool host_pointer_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// uploads + forward passes of `n` frames; descriptors land in d->out_dev (no read-back, no synchronisation)
+int compute_to_device(cb_descriptor* d, int n, const uint8_t* images, int64_t row_stride_bytes) {
   const size_t rowb = (size_t)d->cols * d->chnls;
   if (row_stride_bytes == 0) row_stride_bytes = (int64_t)rowb;
   if ((size_t)row_stride_bytes < rowb) return cb::fail(CB_EINVAL, "row stride smaller than a row");
   // server.py:614-619 asserts the image shape; here the shape is fixed at create time
-  // Frames go up in chunks on a copy stream while the previous chunk is being processed: with pinned host images the
-  // 0.9 MB/frame upload (the largest cost of the host path) overlaps the forward pass.
-  const int chunk = d->upload_chunk;
   const size_t frame_bytes = rowb * d->rows;
+  const bool pinned = host_pointer_is_pinned(images);
+  // Pinned caller memory: frames go up in chunks straight from the caller's buffer on a copy stream while the previous
+  // chunk is being processed (the 0.9 MB/frame upload is the largest cost of the host path).  Pageable memory (what a ROS
+  // callback holds): the same pipeline through the library's own pinned ring, so the DMA never waits for the driver's
+  // internal staging and the CPU copy of the next chunk overlaps the device work of the current one.
+  const int chunk = pinned ? d->upload_chunk : d->stage_frames;
+  if (!pinned && !d->stage_host[0]) {
+    for (int i = 0; i < 2; ++i) {
+      CB_CUDA(cudaHostAlloc((void**)&d->stage_host[i], (size_t)d->stage_frames * frame_bytes, cudaHostAllocDefault));
+      CB_CUDA(cudaEventCreateWithFlags(&d->stage_free[i], cudaEventDisableTiming));
+    }
+  }
   int ci = 0;
   for (int c0 = 0; c0 < n; c0 += chunk, ++ci) {
     const int nc = n - c0 < chunk ? n - c0 : chunk;
@@ -2443,15 +2489,56 @@ int cb_descriptor_compute(cb_descriptor* d, int n, const uint8_t* images, int64_
       CB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
       d->ev_copy.push_back(ev);
     }
-    CB_CUDA(cudaMemcpy2DAsync(d->img_dev + (size_t)c0 * frame_bytes, rowb, images + (size_t)c0 * d->rows * (size_t)row_stride_bytes,
-                              (size_t)row_stride_bytes, rowb, (size_t)nc * d->rows, cudaMemcpyHostToDevice, d->copy_stream));
+    const uint8_t* src = images + (size_t)c0 * d->rows * (size_t)row_stride_bytes;
+    uint8_t* dst = d->img_dev + (size_t)c0 * frame_bytes;
+    if (pinned) {
+      CB_CUDA(cudaMemcpy2DAsync(dst, rowb, src, (size_t)row_stride_bytes, rowb, (size_t)nc * d->rows, cudaMemcpyHostToDevice, d->copy_stream));
+    } else {
+      const int sb = ci & 1;
+      if (ci >= 2) CB_CUDA(cudaEventSynchronize(d->stage_free[sb]));  // the DMA that last read this buffer has finished
+      uint8_t* stg = d->stage_host[sb];
+      if ((size_t)row_stride_bytes == rowb) {
+        memcpy(stg, src, (size_t)nc * frame_bytes);
+      } else {
+        for (size_t r = 0; r < (size_t)nc * d->rows; ++r) memcpy(stg + r * rowb, src + r * (size_t)row_stride_bytes, rowb);
+      }
+      CB_CUDA(cudaMemcpyAsync(dst, stg, (size_t)nc * frame_bytes, cudaMemcpyHostToDevice, d->copy_stream));
+      CB_CUDA(cudaEventRecord(d->stage_free[sb], d->copy_stream));
+    }
     CB_CUDA(cudaEventRecord(d->ev_copy[ci], d->copy_stream));
     CB_CUDA(cudaStreamWaitEvent(d->stream, d->ev_copy[ci], 0));
-    int rc = forward(d, nc, d->img_dev + (size_t)c0 * frame_bytes, d->out_dev + (size_t)c0 * d->K * d->D, d->stream);
+    int rc = forward(d, nc, dst, d->out_dev + (size_t)c0 * d->K * d->D, d->stream);
     if (rc) return rc;
   }
+  return CB_OK;
+}
+
+}  // namespace
+
+int cb_descriptor_compute(cb_descriptor* d, int n, const uint8_t* images, int64_t row_stride_bytes, float* out) {
+  if (!d || !images || !out) return cb::fail(CB_EINVAL, "NULL argument to cb_descriptor_compute");
+  if (n < 1 || n > d->max_batch) return cb::fail(CB_EINVAL, "batch %d outside [1,%d]", n, d->max_batch);
+  cb::DeviceGuard g(d->device);
+  int rc = compute_to_device(d, n, images, row_stride_bytes);
+  if (rc) return rc;
   CB_CUDA(cudaMemcpyAsync(out, d->out_dev, (size_t)n * d->K * d->D * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
   CB_CUDA(cudaStreamSynchronize(d->stream));
+  return CB_OK;
+}
+
+int cb_descriptor_compute_f64(cb_descriptor* d, int n, const uint8_t* images, int64_t row_stride_bytes, double* out) {
+  if (!d || !images || !out) return cb::fail(CB_EINVAL, "NULL argument to cb_descriptor_compute_f64");
+  if (n < 1 || n > d->max_batch) return cb::fail(CB_EINVAL, "batch %d outside [1,%d]", n, d->max_batch);
+  cb::DeviceGuard g(d->device);
+  const size_t ne = (size_t)n * d->K * d->D;
+  if (!d->out_host) CB_CUDA(cudaHostAlloc((void**)&d->out_host, (size_t)d->max_batch * d->K * d->D * sizeof(float), cudaHostAllocDefault));
+  int rc = compute_to_device(d, n, images, row_stride_bytes);
+  if (rc) return rc;
+  // fp32 crosses the bus (half the bytes of the service's float64[]), the widening of server.py:648 / Cerebro.cpp:268-271
+  // happens while writing the caller's buffer
+  CB_CUDA(cudaMemcpyAsync(d->out_host, d->out_dev, ne * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+  CB_CUDA(cudaStreamSynchronize(d->stream));
+  for (size_t i = 0; i < ne; ++i) out[i] = (double)d->out_host[i];
   return CB_OK;
 }
 

@@ -66,6 +66,7 @@ class NetvladDescriptor:
             w2.vlad_w = _fptr(f32(net["vlad_w"]))
             w2.vlad_b = _fptr(f32(net["vlad_b"]))
             w2.vlad_c = _fptr(f32(net["vlad_c"]))
+            w2.vlad_ghost = int(net.get("vlad_ghost", 0))
             check(self._lib.cb_descriptor_create_v2(C.byref(self._h), C.byref(w2), rows, cols, chnls, max_batch, device))
             self.dim = int(self._lib.cb_descriptor_dim(self._h))
             return
@@ -99,6 +100,7 @@ class NetvladDescriptor:
         w.vlad_w = _fptr(f32(net["vlad_w"]))
         w.vlad_b = _fptr(f32(net["vlad_b"]))
         w.vlad_c = _fptr(f32(net["vlad_c"]))
+        w.vlad_ghost = int(net.get("vlad_ghost", 0))  # GhostVLADLayer: trailing clusters dropped before the norms
         check(self._lib.cb_descriptor_create(C.byref(self._h), C.byref(w), rows, cols, chnls, max_batch, device))
         self.dim = int(self._lib.cb_descriptor_dim(self._h))
 
@@ -126,6 +128,17 @@ class NetvladDescriptor:
             out = np.empty((n, self.dim), dtype=np.float32)
         assert out.dtype == np.float32 and out.shape == (n, self.dim) and out.flags["C_CONTIGUOUS"]
         check(self._lib.cb_descriptor_compute(self._h, n, ptr(images_u8), 0, ptr(out)))
+        return out
+
+    def compute_f64(self, images_u8: np.ndarray, row_stride_bytes: int = 0) -> np.ndarray:
+        """``cb_descriptor_compute_f64``: the service reply's ``float64[] desc`` written directly (srv:4)."""
+        if images_u8.ndim == 3:
+            images_u8 = images_u8[..., None]
+        assert images_u8.dtype == np.uint8
+        n = images_u8.shape[0]
+        images_u8 = np.ascontiguousarray(images_u8)
+        out = np.empty((n, self.dim), dtype=np.float64)
+        check(self._lib.cb_descriptor_compute_f64(self._h, n, ptr(images_u8), row_stride_bytes, ptr(out)))
         return out
 
     def compute_device(self, images_u8, out=None):
@@ -186,9 +199,9 @@ class HDF5ModelImageDescriptor:
         ), "\n[whole_image_descriptor_compute_server] Input shape of the image \
                 does not match with the allocated GPU memory. Expecting an input image of \
                 size %dx%dx%d, but received : %s" % (self.im_rows, self.im_cols, self.im_chnls, str(cv_image.shape))  # :614-619
-        u = self.model.compute(cv_image.astype(np.uint8)[None])
+        u = self.model.compute_f64(cv_image.astype(np.uint8)[None])  # float64[] desc (srv:4) straight from the C ABI
         self.request_count += 1
         result = WholeImageDescriptorComputeResponse()
-        result.desc = u[0, :].astype(np.float64)  # float64[] desc (srv:4)
+        result.desc = u[0, :]
         result.model_type = self.model_type
         return result

@@ -164,7 +164,6 @@ class Cerebro {
     if (!m_dataManager_available) return -1;
     auto* data_map = dataManager->getDataMapRef();
     int done = 0;
-    std::vector<float> out(descriptor_size);
     for (auto& kv : *data_map) {
       DataNode* node = kv.second;
       if (!node->isKeyFrame() || node->isWholeImageDescriptorAvailable()) continue;  // :189
@@ -197,12 +196,12 @@ class Cerebro {
       } else if (node->left_image.size() != px * (size_t)chnls_) {
         continue;
       }
-      const int rc = cb_descriptor_compute(desc_, 1, img, 0, out.data());  // replaces client.call(srv), :263
+      std::vector<double> vec(descriptor_size);
+      const int rc = cb_descriptor_compute_f64(desc_, 1, img, 0, vec.data());  // replaces client.call(srv), :263; the reply IS float64[] (:268-271)
       if (rc != CB_OK) {
         std::fprintf(stderr, "[descriptor_computer_thread] %s\n", cb_last_error());  // ROS_ERROR and continue, :288-290
         continue;
       }
-      std::vector<double> vec(out.begin(), out.end());  // float64[] desc -> VectorXd, :268-271
       node->setWholeImageDescriptor(vec);               // :274
       {
         std::lock_guard<std::mutex> lk(m_wholeImageComputedList);

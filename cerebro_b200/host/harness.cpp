@@ -142,6 +142,7 @@ int main(int argc, char** argv) {
     w2.vlad_k = vsh2[1];
     w2.vlad_b = w.get("vlad_b")->data();
     w2.vlad_c = w.get("vlad_c")->data();
+    w2.vlad_ghost = 0;
     if (cb_descriptor_create_v2(&desc, &w2, rows, cols, chnls, 1, 0) != CB_OK) {
       std::fprintf(stderr, "cb_descriptor_create_v2: %s\n", cb_last_error());
       return 1;
@@ -177,6 +178,7 @@ int main(int argc, char** argv) {
   nw.vlad_k = vsh[1];
   nw.vlad_b = w.get("vlad_b")->data();
   nw.vlad_c = w.get("vlad_c")->data();
+  nw.vlad_ghost = 0;  // the shipped models use NetVLADLayer
 
   if (!w.v2 && cb_descriptor_create(&desc, &nw, rows, cols, chnls, 1, 0) != CB_OK) {
     std::fprintf(stderr, "cb_descriptor_create: %s\n", cb_last_error());

@@ -420,6 +420,7 @@ def save_cbw(path: str, net: dict, meta: dict | None = None) -> None:
         "strides": [b["stride"] for b in (net["ir_blocks"] if v2 else net["blocks"])],
         "residual": [b["residual"] for b in net["ir_blocks"]] if v2 else [],
         "arrays": [[n, list(a.shape)] for n, a in items],
+        "vlad_ghost": int(net.get("vlad_ghost", 0)),  # GhostVLADLayer: trailing clusters dropped before the norms
         "meta": meta or {},
     }
     hj = json.dumps(hdr).encode("utf8")
@@ -451,6 +452,7 @@ def load_cbw(path: str) -> dict:
         for k in ("vlad_w", "vlad_b", "vlad_c"):
             net[k] = arrs[k]
         net["meta"] = hdr.get("meta", {})
+        net["vlad_ghost"] = int(hdr.get("vlad_ghost", 0))
         return net
     net = {"conv1_w": arrs["conv1_w"], "conv1_b": arrs["conv1_b"], "blocks": []}
     for i, s in enumerate(hdr["strides"]):
@@ -459,6 +461,7 @@ def load_cbw(path: str) -> dict:
     for k in ("vlad_w", "vlad_b", "vlad_c"):
         net[k] = arrs[k]
     net["meta"] = hdr.get("meta", {})
+    net["vlad_ghost"] = int(hdr.get("vlad_ghost", 0))
     return net
 
 

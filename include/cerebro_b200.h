@@ -56,7 +56,7 @@ extern "C" {
 #define CB_ENOMEM (-4)    /* capacity exceeded / allocation failed */
 #define CB_EREFUSED (-5)  /* input refused by the algorithm (reference returns -1) */
 
-CB_API int cb_version(void);             /* ABI version, currently 1 */
+CB_API int cb_version(void);             /* ABI version, currently 2 (1 -> 2: vlad_ghost, cb_comm_*, cb_index_search_sharded*) */
 CB_API const char* cb_last_error(void);  /* thread-local, never NULL */
 CB_API int cb_device_count(void);        /* number of visible CUDA devices (0 if none) */
 
@@ -187,11 +187,14 @@ typedef struct cb_netvlad_weights {
   const float* const* pw_b; /* n_blocks x [Cout]     */
   const int* dw_stride;   /* n_blocks, 1 or 2 */
   const int* channels_out; /* n_blocks, Cout of the block */
-  int vlad_k;             /* clusters */
+  int vlad_k;             /* clusters the soft-assignment runs over (NetVLADLayer: K; GhostVLADLayer: K + ghosts); <= 16 */
   int vlad_d;             /* feature dim entering NetVLAD */
   const float* vlad_w;    /* [D][K] */
   const float* vlad_b;    /* [K] */
   const float* vlad_c;    /* [D][K] */
+  int vlad_ghost;         /* GhostVLADLayer (scripts/predict_utils.py:110-141): the LAST vlad_ghost clusters take part in the
+                             softmax but are dropped before the two norms (:133); descriptor dim = (vlad_k - vlad_ghost) * D.
+                             0 = NetVLADLayer */
 } cb_netvlad_weights;
 
 /* HDF5ModelImageDescriptor.__init__(kerasmodel_file, im_rows, im_cols, im_chnls)
@@ -227,6 +230,7 @@ typedef struct cb_netvlad_v2_weights {
   const float* vlad_w; /* [D][K] */
   const float* vlad_b; /* [K] */
   const float* vlad_c; /* [D][K] */
+  int vlad_ghost;      /* as in cb_netvlad_weights */
 } cb_netvlad_v2_weights;
 
 /* Same handle type and the same compute / dim / destroy calls as cb_descriptor_create. */
@@ -240,6 +244,13 @@ CB_API int cb_descriptor_dim(const cb_descriptor* d); /* K * D, what the probe c
  * index k*D+d.  The ROS shim widens to float64[] (srv:4). */
 CB_API int cb_descriptor_compute(cb_descriptor* d, int n, const uint8_t* images, int64_t row_stride_bytes,
                           float* out);
+/* The same, writing the service reply's `float64[] desc` (srv/WholeImageDescriptorCompute.srv:4, server.py:648; the client
+ * copies it into a VectorXd, Cerebro.cpp:268-271) directly: fp32 crosses the bus, the widening happens into `out`.
+ * Both calls accept pageable `images` (a cv::Mat's data: Cerebro.cpp:243-256) as well as pinned memory: pageable frames go
+ * through a pinned staging ring inside the library (CPU copy of the next chunk overlaps the DMA + forward pass of the
+ * current one), pinned frames are uploaded in place. */
+CB_API int cb_descriptor_compute_f64(cb_descriptor* d, int n, const uint8_t* images, int64_t row_stride_bytes,
+                              double* out);
 CB_API int cb_descriptor_compute_device(cb_descriptor* d, int n, const uint8_t* images_dev, float* out_dev,
                                  void* stream);
 /* debugging / parity: copy the activation after layer `layer` (0 = conv1, then dw1, pw1, dw2, ...)

@@ -137,8 +137,10 @@ def is_mobilenetv2(w: dict) -> bool:
     return "Conv1/kernel" in w and "expanded_conv_depthwise/depthwise_kernel" in w
 
 
-def netvlad(x: torch.Tensor, w: dict) -> torch.Tensor:
-    """predict_utils.py:36-64.  x: NCHW feature map -> [N, K*D], index k*D+d."""
+def netvlad(x: torch.Tensor, w: dict, num_ghost_clusters: int = 0) -> torch.Tensor:
+    """NetVLADLayer.call, predict_utils.py:36-64.  x: NCHW feature map -> [N, K*D], index k*D+d.
+    ``num_ghost_clusters`` > 0 restates GhostVLADLayer.call (predict_utils.py:110-141): the weights carry K + ghosts
+    clusters, all take part in the softmax, and ``v = v[:, 0:num_clusters, :]`` (:133) drops the ghosts before the norms."""
     dt = x.dtype
     name = [k.split("/")[0] for k in w if k.endswith("/cluster_centers")][0]
     kern = torch.as_tensor(w[name + "/kernel"], dtype=dt)[0, 0]  # (D,K)
@@ -151,13 +153,15 @@ def netvlad(x: torch.Tensor, w: dict) -> torch.Tensor:
     # :47-52  v[d,k] = sum_hw a[hw,k] * (x[hw,d] + C[d,k])    (PLUS, as written at :47)
     v = torch.einsum("npk,npd->ndk", a, xf) + cent.unsqueeze(0) * a.sum(dim=1).unsqueeze(1)
     v = v.permute(0, 2, 1)  # :54  -> N x K x D
+    if num_ghost_clusters:
+        v = v[:, : v.shape[1] - num_ghost_clusters, :]  # :133
     v = v * torch.rsqrt(torch.clamp((v * v).sum(-1, keepdim=True), min=L2_EPS))  # :59
     v = v.reshape(N, -1)  # :60 batch_flatten (K-major)
     v = v * torch.rsqrt(torch.clamp((v * v).sum(-1, keepdim=True), min=L2_EPS))  # :61
     return v
 
 
-def describe(images_u8: np.ndarray, w: dict, dtype: str = "float32", threads: int | None = None) -> np.ndarray:
+def describe(images_u8: np.ndarray, w: dict, dtype: str = "float32", threads: int | None = None, num_ghost_clusters: int = 0) -> np.ndarray:
     """uint8 [N,H,W,C] (or [N,H,W]) -> descriptors [N, K*D] as float32/float64 numpy."""
     if images_u8.ndim == 3:
         images_u8 = images_u8[..., None]  # server.py:603-605
@@ -167,5 +171,5 @@ def describe(images_u8: np.ndarray, w: dict, dtype: str = "float32", threads: in
     with torch.no_grad():
         x = preprocess(images_u8, dt)
         f = backbone_v2(x, w) if is_mobilenetv2(w) else backbone(x, w)
-        d = netvlad(f, w)
+        d = netvlad(f, w, num_ghost_clusters)
     return d.numpy()

@@ -25,7 +25,7 @@ def test_ctypes_table_matches_header(native_lib):
 
 
 def test_version_and_error_string(native_lib):
-    assert native_lib.cb_version() == 1
+    assert native_lib.cb_version() == 2
     assert isinstance(native_lib.cb_last_error(), bytes)
 
 

@@ -209,3 +209,32 @@ def test_reference_server_call_shape(native_lib, cuda_device, tmp_path):
     req.ima = np.zeros((100, 128), dtype=np.uint8)
     with pytest.raises(AssertionError):
         srv.handle_req(req)
+
+
+@pytest.mark.parametrize("k_total,ghost", [(12, 3), (16, 4), (9, 0)])
+def test_ghostvlad_and_small_k_heads(native_lib, cuda_device, k_total, ghost):
+    """GhostVLADLayer (predict_utils.py:110-141): K + ghost clusters in the softmax, ghosts dropped before the norms; and plain
+    NetVLAD heads with fewer than 16 clusters.  No shipped model has such a head: the gray conv6 backbone gets a random one,
+    identical in the oracle and on the device."""
+    from cerebro_b200.descriptor import NetvladDescriptor
+    from oracle import netvlad as NV
+
+    raw = dict(golden_io.raw_weights("gray_conv6"))
+    name = [k.split("/")[0] for k in raw if k.endswith("/cluster_centers")][0]
+    D = raw[name + "/kernel"].shape[2]
+    rng = np.random.default_rng(k_total * 31 + ghost)
+    raw[name + "/kernel"] = (rng.standard_normal((1, 1, D, k_total)) * 0.05).astype(np.float32)
+    raw[name + "/bias"] = (rng.standard_normal((1, 1, k_total)) * 0.1).astype(np.float32)
+    raw[name + "/cluster_centers"] = (rng.standard_normal((1, 1, 1, D, k_total)) * 0.5).astype(np.float32)
+    net = _net("gray_conv6")
+    net["vlad_w"], net["vlad_b"], net["vlad_c"] = raw[name + "/kernel"][0, 0], raw[name + "/bias"].reshape(-1), raw[name + "/cluster_centers"][0, 0, 0]
+    net["vlad_ghost"] = ghost
+    imgs = synth.textured_scenes(2, 240, 320, 1, seed=k_total)
+    nd = NetvladDescriptor(net, 240, 320, 1, max_batch=2)
+    assert nd.dim == (k_total - ghost) * D
+    d = nd.compute(imgs)
+    nd.close()
+    ref = NV.describe(imgs, raw, dtype="float64", num_ghost_clusters=ghost)
+    assert d.shape == ref.shape
+    assert np.linalg.norm(d - ref, axis=1).max() < L2_TOL
+    assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)

@@ -294,3 +294,27 @@ def test_hypothesis_manager_ttl_and_chaining():
     h.time_to_live = 100
     h.increment_ttl()  # > 100 after the first increment -> a second one (HypothesisManager.h:115-117)
     assert h.time_to_live == 102
+
+
+def test_ghostvlad_oracle_drops_ghost_clusters():
+    """GhostVLADLayer.call (predict_utils.py:110-141): K + G clusters share the softmax, only the first K reach the output;
+    each kept cluster block has norm 1/sqrt(K) and the whole descriptor norm 1."""
+    import torch
+
+    from oracle import netvlad as NV
+
+    rng = np.random.default_rng(0)
+    D, K, G = 64, 6, 3
+    w = {"gv/kernel": rng.standard_normal((1, 1, D, K + G)).astype(np.float32) * 0.1,
+         "gv/bias": rng.standard_normal((1, 1, K + G)).astype(np.float32) * 0.1,
+         "gv/cluster_centers": rng.standard_normal((1, 1, 1, D, K + G)).astype(np.float32)}
+    x = torch.as_tensor(rng.uniform(0, 6, (2, D, 5, 7)))
+    full = NV.netvlad(x, w).numpy()
+    ghost = NV.netvlad(x, w, num_ghost_clusters=G).numpy()
+    assert full.shape == (2, (K + G) * D) and ghost.shape == (2, K * D)
+    assert np.allclose(np.linalg.norm(ghost, axis=1), 1.0)
+    blocks = ghost.reshape(2, K, D)
+    assert np.allclose(np.linalg.norm(blocks, axis=2), 1.0 / np.sqrt(K))
+    # same directions as the un-ghosted layer's first K blocks (the softmax is shared), different global scale
+    fb = full.reshape(2, K + G, D)[:, :K]
+    assert np.allclose(blocks * np.sqrt(K), fb * np.sqrt(K + G), atol=1e-12)

@@ -108,6 +108,33 @@ def test_descriptor_row_stride(native_lib, cuda_device):
     nd.close()
 
 
+def test_pageable_pinned_and_f64_entry_points_agree(native_lib, cuda_device):
+    """cb_descriptor_compute from pageable memory (the library's pinned staging ring, more frames than one ring buffer and a
+    padded row stride) == from pinned memory (uploaded in place) == cb_descriptor_compute_f64 narrowed back (the service's
+    float64[] reply, srv/WholeImageDescriptorCompute.srv:4)."""
+    import torch
+
+    from cerebro_b200 import _lib
+    from cerebro_b200.descriptor import NetvladDescriptor
+    from cerebro_b200.keras_weights import fold_mobilenet_netvlad
+
+    n = 21  # > 2 x 8 staged frames: every ring buffer is reused
+    nd = NetvladDescriptor(fold_mobilenet_netvlad(golden_io.raw_weights("gray_conv6")), 96, 128, 1, max_batch=n)
+    imgs = synth.textured_scenes(n, 96, 128, 1, seed=8)
+    pageable = nd.compute(imgs)
+    pinned_in = torch.from_numpy(imgs).pin_memory()
+    pinned = nd.compute(pinned_in.numpy())
+    assert np.array_equal(pageable, pinned)
+    f64 = nd.compute_f64(imgs)
+    assert f64.dtype == np.float64 and np.array_equal(f64.astype(np.float32), pageable) and np.array_equal(f64, pageable.astype(np.float64))
+    padded = np.zeros((n, 96, 160), dtype=np.uint8)
+    padded[:, :, :128] = imgs[..., 0]
+    out = np.empty((n, nd.dim), dtype=np.float64)
+    _lib.check(_lib.load().cb_descriptor_compute_f64(nd._h, n, _lib.ptr(padded), 160, _lib.ptr(out)))
+    assert np.array_equal(out, f64)
+    nd.close()
+
+
 def test_clique_and_multihypothesis_rules_match_oracle(native_lib, cuda_device):
     """faiss_clique_loopcandidate_generator / faiss_multihypothesis_tracking (Cerebro.cpp:506-885) on the device index,
     one batched top-5 search per wake-up, against the oracle's one-query-at-a-time replay."""
