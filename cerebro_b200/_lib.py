@@ -129,6 +129,13 @@ _SIGNATURES = {
     "cb_frontend_last_stereo_ms": (C.c_float, [_vp]),
     "cb_frontend_disparity_to_3d": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
     "cb_frontend_collect": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cb_features_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cb_features_destroy": (C.c_int, [_vp]),
+    "cb_features_set_remap": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "cb_features_remap": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
+    "cb_features_orb": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cb_features_last_orb_ms": (C.c_float, [_vp]),
+    "cb_features_debug_read": (_i64, [_vp, C.c_int, _vp, _i64]),
     "cb_descriptor_create": (C.c_int, [C.POINTER(_vp), C.POINTER(NetvladWeights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "cb_descriptor_create_v2": (C.c_int, [C.POINTER(_vp), C.POINTER(NetvladV2Weights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "cb_descriptor_destroy": (C.c_int, [_vp]),

@@ -13,7 +13,8 @@ OUT_DIR = os.path.join(HERE, "_native")
 LIB = os.path.join(OUT_DIR, "libcerebro_b200.so")
 HARNESS = os.path.join(OUT_DIR, "cerebro_harness")
 STEREO_EMUL = os.path.join(OUT_DIR, "libstereo_emul.so")
-SOURCES = ["capi.cu", "comm.cu", "search.cu", "pnp.cu", "netvlad.cu", "frontend.cu"]
+ORB_EMUL = os.path.join(OUT_DIR, "liborb_emul.so")
+SOURCES = ["capi.cu", "comm.cu", "search.cu", "pnp.cu", "netvlad.cu", "frontend.cu", "features.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -77,6 +78,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("stereo emulation build failed")
+    # same for the ORB / remap kernels (separate roundings everywhere: -ffp-contract=off)
+    osrc = [os.path.join(host, "orb_emul.cpp"), os.path.join(CSRC, "orb_core.h"), os.path.join(CSRC, "orb_pipeline.h"), os.path.join(CSRC, "orb_pattern.h")]
+    if force or _stale(ORB_EMUL, osrc):
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", osrc[0], "-o", ORB_EMUL]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("ORB emulation build failed")
     return LIB
 
 

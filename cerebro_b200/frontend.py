@@ -169,22 +169,27 @@ class StaticPointFeatureMatching:
             cls._fe = FrontEnd(max_pairs=1, max_features=max(n_feat, 5000))
         return cls._fe
 
+    _feat = None
+
+    @classmethod
+    def _features(cls, rows, cols):
+        from .features import Features
+
+        if cls._feat is None or (cls._feat.rows, cls._feat.cols) != (rows, cols):
+            cls._feat = Features(rows, cols, max_images=2, max_keypoints=8192)
+        return cls._feat
+
     @classmethod
     def gms_point_feature_matches(cls, imleft_undistorted: np.ndarray, imright_undistorted: np.ndarray, n_orb_feat: int = 5000):
         """PointFeatureMatching.cpp:5-75: returns (u, ud), 3xN homogeneous pixel coordinates of the GMS matches (empty
-        arrays when there is none).  ORB = cv2.ORB_create(n_orb_feat) with FAST threshold 0 (:17-18), on the host."""
-        import cv2  # the reference's own dependency; only this convenience wrapper needs it
-
-        orb = cv2.ORB_create(n_orb_feat)
-        orb.setFastThreshold(0)
-        k1, d1 = orb.detectAndCompute(imleft_undistorted, None)
-        k2, d2 = orb.detectAndCompute(imright_undistorted, None)
-        if d1 is None or d2 is None or len(k1) == 0 or len(k2) == 0:
+        arrays when there is none).  ORB = ``cv::ORB::create(n_orb_feat)`` with FAST threshold 0 (:17-18) -- on the device
+        (``cb_features_orb``), like the matcher and the GMS filter behind it."""
+        a, b = np.asarray(imleft_undistorted), np.asarray(imright_undistorted)
+        assert a.shape == b.shape and a.ndim == 2 and a.dtype == np.uint8
+        r = cls._features(*a.shape).orb(np.stack([a, b]), n_orb_feat)
+        if len(r[0]["pt"]) == 0 or len(r[1]["pt"]) == 0:
             return np.zeros((3, 0)), np.zeros((3, 0))
-        fe = cls._frontend(max(len(k1), len(k2)))
-        kp1 = np.array([k.pt for k in k1], dtype=np.float32)
-        kp2 = np.array([k.pt for k in k2], dtype=np.float32)
-        h1, w1 = imleft_undistorted.shape[:2]
-        h2, w2 = imright_undistorted.shape[:2]
-        fe.match_gms([kp1], [d1], [kp2], [d2], (w1, h1), (w2, h2))
+        fe = cls._frontend(max(len(r[0]["pt"]), len(r[1]["pt"])))
+        h, w = a.shape
+        fe.match_gms([r[0]["pt"]], [r[0]["desc"]], [r[1]["pt"]], [r[1]["desc"]], (w, h), (w, h))
         return fe.matched_points(0)

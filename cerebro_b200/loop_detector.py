@@ -145,6 +145,44 @@ def consistent_pose_compute(fe, pnp, K, img3d_a, img3d_b, match_results, stamps,
     return out
 
 
+def process_loop_candidates_from_raw_stereo(feat, fe, pnp, K, Q, left_a, right_a, left_b, right_b, stamps, node_indices=None,
+                                            warp_slots=None, n_orb_feat=5000, seed=0):
+    """``Cerebro::process_loop_candidate_imagepair_consistent_pose_compute`` (src/Cerebro.cpp:1414-1771) for a batch of loop
+    candidates FROM THE RAW STEREO PAIRS, every stage on the device:
+
+      raw images --cv::remap x2--> stereo-rectified (StereoGeometry, CameraGeometry.cpp:42, 381-382; ``feat.remap``)
+      --StereoBM(64, 21)--> disparity --disparity_to_3DPoints--> the two 3-D images (:81, 410-418, 459-520; ``fe.stereo_bm``)
+      left images --cv::ORB(n_orb_feat, FAST threshold 0)--> keypoints + descriptors (PointFeatureMatching.cpp:16-22; ``feat.orb``)
+      --BFMatcher(HAMMING) + GMS--> matches (:40-52; ``fe.match_gms``) --> Options A / B / C + consistency check
+      (``consistent_pose_compute``).
+
+    left_a / right_a / left_b / right_b: [n, rows, cols] uint8.  warp_slots = ((undistort_left, rectify_left),
+    (undistort_right, rectify_right)) slot numbers of ``feat.set_remap``, or None when the images are already rectified.
+    K: 3x3 intrinsics of the rectified left camera, Q: 4x4 reprojection matrix (both from cv::stereoRectify, host set-up).
+    Returns the list ``consistent_pose_compute`` returns plus the per-candidate match results."""
+    la, ra, lb, rb = (np.ascontiguousarray(x, dtype=np.uint8) for x in (left_a, right_a, left_b, right_b))
+    n = la.shape[0]
+    if warp_slots is not None:
+        (ul, rl), (ur, rr) = warp_slots
+        lefts = np.concatenate([feat.remap(la[i : i + feat.max_images], ul, rl) for i in range(0, n, feat.max_images)] +
+                               [feat.remap(lb[i : i + feat.max_images], ul, rl) for i in range(0, n, feat.max_images)])
+        rights = np.concatenate([feat.remap(ra[i : i + feat.max_images], ur, rr) for i in range(0, n, feat.max_images)] +
+                                [feat.remap(rb[i : i + feat.max_images], ur, rr) for i in range(0, n, feat.max_images)])
+    else:
+        lefts, rights = np.concatenate([la, lb]), np.concatenate([ra, rb])
+    disp = fe.stereo_bm(lefts, rights)          # [2n, rows, cols] int16
+    img3d = fe.disparity_to_3d(disp, Q)         # [2n, rows, cols, 3] float32
+    orb = []
+    for i in range(0, 2 * n, feat.max_images):
+        orb += feat.orb(lefts[i : i + feat.max_images], n_orb_feat)
+    rows, cols = la.shape[1:3]
+    kp1, d1 = [orb[p]["pt"] for p in range(n)], [orb[p]["desc"] for p in range(n)]
+    kp2, d2 = [orb[n + p]["pt"] for p in range(n)], [orb[n + p]["desc"] for p in range(n)]
+    matches = fe.match_gms(kp1, d1, kp2, d2, (cols, rows), (cols, rows))
+    out = consistent_pose_compute(fe, pnp, K, img3d[:n], img3d[n:], matches, stamps, node_indices, seed=seed)
+    return out, matches
+
+
 # cv::cvtColor(CV_BGR2GRAY) on 8-bit images is fixed point: OpenCV 4 uses 15 bits, (3735 B + 19235 G + 9798 R + 2^14) >> 15
 # (bit-exact against the installed cv2, tests/test_host_logic.py); OpenCV 3 -- the reference's era -- used 14 bits,
 # (1868 B + 9617 G + 4899 R + 2^13) >> 14, which differs by one grey level on ~0.2 % of the pixels.

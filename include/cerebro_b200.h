@@ -368,6 +368,40 @@ CB_API float cb_frontend_last_stereo_ms(const cb_frontend* f); /* device time of
 CB_API int cb_frontend_disparity_to_3d(cb_frontend* f, int n, const int16_t* disparity, int rows, int cols, float Q03,
                                 float Q13, float Q23, float Q32, float Q33, float* out3d);
 
+/* ------------------------------------------------------------------------------------
+ * features: the image side of a loop candidate -- undistortion / stereo-rectification warps and ORB extraction
+ * (StereoGeometry::do_image_undistortion / do_stereo_rectification_of_undistorted_images, src/utils/CameraGeometry.cpp:42,
+ * 381-382; StaticPointFeatureMatching::gms_point_feature_matches, src/utils/PointFeatureMatching.cpp:16-22)
+ * ---------------------------------------------------------------------------------- */
+typedef struct cb_features cb_features;
+
+/* One handle per camera geometry: images are rows x cols, 8-bit, one channel; up to max_images per call and max_keypoints
+ * keypoints per image (cv::ORB keeps ties at the response threshold, so allow a margin over n_features). */
+CB_API int cb_features_create(cb_features** out, int rows, int cols, int max_images, int max_keypoints, int device);
+CB_API int cb_features_destroy(cb_features* f);
+
+/* The CV_32FC1 map pair of one warp (camodocal's initUndistortRectifyMap, CameraGeometry.cpp:20-34, or
+ * cv::initUndistortRectifyMap, :348-349 -- computed once on the host at start-up), kept on the device in `slot` 0..3. */
+CB_API int cb_features_set_remap(cb_features* f, int slot, const float* map_x, const float* map_y);
+/* cv::remap(src, dst, map_x, map_y, CV_INTER_LINEAR) (border constant 0) for n images [n][rows][cols]; with slot_b >= 0 the
+ * result is warped again through slot_b (raw -> undistorted -> rectified, 8-bit rounding in between exactly like the reference's two
+ * calls).  Bit-exact against cv::remap (tests/test_orb.py). */
+CB_API int cb_features_remap(cb_features* f, int n, const uint8_t* src, int slot_a, int slot_b, uint8_t* dst);
+
+/* cv::ORB::create(n_features) -> setFastThreshold(0) -> detectAndCompute(image, noArray(), keypoints, descriptors) for n images
+ * [n][rows][cols].  Per image i: n_keypoints[i] keypoints in cv::ORB's output order at [i][0 .. n_keypoints[i]):
+ *   kp_xy [n][max_keypoints][2] KeyPoint.pt, kp_size, kp_angle (degrees), kp_response (Harris), kp_octave, descriptors
+ *   [n][max_keypoints][32].  kp_size / kp_angle / kp_response / kp_octave may be NULL.
+ * Keypoints (order, coordinates, size, angle, response, octave) are bit-exact against the installed OpenCV; descriptors agree
+ * except for isolated bits (~1 in 10^6) where OpenCV's own 7x7 Gaussian -- an IPP float filter whose rounding depends on the
+ * host CPU's code path -- lands on the other side of a .5 tie. */
+CB_API int cb_features_orb(cb_features* f, int n, const uint8_t* images, int n_features, int32_t* n_keypoints, float* kp_xy,
+                    float* kp_size, float* kp_angle, float* kp_response, int32_t* kp_octave, uint8_t* descriptors);
+CB_API float cb_features_last_orb_ms(const cb_features* f); /* stream time of the last cb_features_orb, host selections included */
+/* parity tests: pyramid (what = 0), FAST score map (1) or blurred pyramid (2) of image 0 of the last cb_features_orb call, the 8
+ * levels back to back; returns the number of bytes written or a negative error */
+CB_API int64_t cb_features_debug_read(cb_features* f, int what, uint8_t* out, int64_t max_bytes);
+
 #ifdef __cplusplus
 }
 #endif
