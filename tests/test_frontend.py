@@ -263,3 +263,70 @@ def test_candidate_to_pose_chain(native_lib, cuda_device):
     assert cand3 is None and edge3 is None
     fe.close()
     pb.close()
+
+
+@pytest.mark.gpu
+def test_raw_stereo_pairs_to_loop_edge_all_on_device(native_lib, cuda_device):
+    """Scope row a10 end to end (Cerebro.cpp:1414-1771): two keyframes' raw stereo pairs -> remap -> StereoBM -> 3-D image, ORB
+    -> matcher -> GMS -> the three sets -> Options A / B / C -> consistency check -> LoopEdge, every stage behind the C ABI.
+    A slanted textured plane seen by a rectified pair (f 400 px, baseline 0.12 m, depth 3 - 4.8 m); keyframe b is the same
+    rig moved 0.06 m to the right.  The same chain with OpenCV's ORB and StereoBM spliced in must give the same edge."""
+    from cerebro_b200.features import Features
+    from cerebro_b200.frontend import FrontEnd
+    from cerebro_b200.loop_detector import consistent_pose_compute, process_loop_candidates_from_raw_stereo
+    from cerebro_b200.pnp import PnpBatch
+    from tests.synth_stereo import _blur
+
+    h, w, f, B = 480, 640, 400.0, 0.12
+    rng = np.random.default_rng(7)
+    pad = 80
+    tex = _blur(rng.random((h, w + 2 * pad)), 1.0)
+    tex = (tex - tex.min()) / (tex.max() - tex.min()) * 255.0
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    d = 10.0 + 6.0 * xs / w  # disparity of the plane, defined on the target pixel grid
+
+    def view(shift):  # image whose pixel x shows texture position x + shift(x)
+        src = xs + pad + shift
+        x0 = np.floor(src).astype(int)
+        a = src - x0
+        rows = np.arange(h)[:, None]
+        img = (1 - a) * tex[rows, np.clip(x0, 0, tex.shape[1] - 1)] + a * tex[rows, np.clip(x0 + 1, 0, tex.shape[1] - 1)]
+        return np.clip(np.rint(img + rng.normal(0, 1.0, img.shape)), 0, 255).astype(np.uint8)
+
+    left_a, right_a = view(0 * d), view(d)            # right(x) = left(x + d)
+    left_b, right_b = view(0.5 * d), view(1.5 * d)    # the rig moved half a baseline to the right
+    K = np.array([[f, 0, w / 2], [0, f, h / 2], [0, 0, 1.0]])
+    Q = np.array([[1, 0, 0, -w / 2], [0, 1, 0, -h / 2], [0, 0, 0, f], [0, 0, 1.0 / B, 0]])  # cv::stereoRectify's Q, Tx = -B
+    # identity warps in the two remap slots exercise the rectification stage (bit-exact pass-through)
+    ident_x, ident_y = np.tile(np.arange(w, dtype=np.float32), (h, 1)), np.tile(np.arange(h, dtype=np.float32)[:, None], (1, w))
+    feat = Features(h, w, max_images=2, max_keypoints=8192)
+    feat.set_remap(0, ident_x, ident_y)
+    feat.set_remap(1, ident_x, ident_y)
+    fe = FrontEnd(max_pairs=1, max_features=8192)
+    pb = PnpBatch(max_candidates=2, max_points_total=20000, max_hypotheses=50)
+    out, matches = process_loop_candidates_from_raw_stereo(feat, fe, pb, K, Q, left_a[None], right_a[None], left_b[None], right_b[None],
+                                                           [(500.0, 100.0)], [(40, 7)], warp_slots=((0, 1), (0, 1)), seed=3)
+    cand, edge = out[0]
+    assert matches[0]["n_inliers"] > 800, matches[0]["n_inliers"]
+    assert cand is not None and edge is not None
+    T = edge.pose_1T0
+    assert np.abs(T[:3, :3] - np.eye(3)).max() < 0.02 and np.abs(T[:3, 3] - np.array([-0.06, 0, 0])).max() < 0.03, T
+    assert edge.timestamp0 == 500.0 and edge.timestamp1 == 100.0 and edge.description.startswith("40<=>7")
+    try:
+        import cv2
+    except ImportError:
+        return
+    # the same chain with OpenCV's own ORB and StereoBM outputs spliced in
+    orb = cv2.ORB_create(5000)
+    orb.setFastThreshold(0)
+    k1, d1 = orb.detectAndCompute(left_a, None)
+    k2, d2 = orb.detectAndCompute(left_b, None)
+    bm = cv2.StereoBM_create(64, 21)
+    img3d = fe.disparity_to_3d(np.stack([bm.compute(left_a, right_a), bm.compute(left_b, right_b)]), Q)
+    m2 = fe.match_gms([np.array([k.pt for k in k1], np.float32)], [d1], [np.array([k.pt for k in k2], np.float32)], [d2], (w, h), (w, h))
+    cand2, edge2 = consistent_pose_compute(fe, pb, K, img3d[:1], img3d[1:], m2, [(500.0, 100.0)], [(40, 7)], seed=3)[0]
+    assert m2[0]["n_inliers"] == matches[0]["n_inliers"]
+    assert edge2 is not None and np.array_equal(edge2.pose_1T0, edge.pose_1T0) and edge2.weight == edge.weight
+    feat.close()
+    fe.close()
+    pb.close()
