@@ -621,9 +621,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dwpw_kernel(const __half* __
 //                 drains columns [256 g, 256 g + 256) of every tile.  [Round 1 had one group: ncu showed the 16 producer
 //                 warps stalled ~50-70 % on a_empty behind it -- the kernel was epilogue-bound.]
 // ---------------------------------------------------------------------------------------------
-constexpr int kEpiWarps = 8;                                         // two groups of four (one per TMEM lane quarter)
-constexpr int kHaloProd0 = 32 * (3 + kEpiWarps);                     // first producer thread (352)
-constexpr int kHaloThreads = kHaloProd0 + kProdThreads;              // 864
+// epilogue warps: two groups of four (one per TMEM lane quarter) where the epilogue is the longer pole (COUT = 2 CIN), one
+// group where producers and epilogue balance (COUT = CIN: 736 threads leave 80 registers per thread instead of 72)
+constexpr int halo_threads(int epi_warps) { return 32 * (kProdWarps + epi_warps + 3); }
 constexpr int kTH = 16, kTW = 8;
 
 // MODE bits of the halo kernel (the "precise" descriptor path):
@@ -642,7 +642,7 @@ constexpr int kInQ = 1, kSplit = 2, kOutQ = 4, kSplitA = 8;
 constexpr float kQ15Scale = 32767.0f / 6.0f;          // x -> u
 constexpr double kQ15DecodeW = 16384.0 * 6.0 / 32767.0;  // (f - 2) -> x
 
-template <int CIN, int COUT, int S, bool SPLIT = false, bool SPLIT_B = SPLIT>
+template <int CIN, int COUT, int S, bool SPLIT = false, bool SPLIT_B = SPLIT, int EW = 8>
 struct HaloCfg {
   static constexpr int KB = 32;  // channels per K block (= per halo box): 64-byte pixels, 64-byte swizzled A/B rows
   static constexpr int NKB = CIN / KB;
@@ -662,7 +662,7 @@ struct HaloCfg {
   static constexpr int kTeamWarps = kTasks / 32;
   static constexpr int kASmin = (SPLIT && S == 2) ? 2 : 3;          // the big stride-2 halos need the room
   static constexpr int kAS = kTeams > kASmin ? kTeams : kASmin;
-  static constexpr int kStageBytes = kEpiWarps * 32 * 64;          // epilogue staging: 32 pixels x 32 channels per warp
+  static constexpr int kStageBytes = EW * 32 * 64;                 // epilogue staging: 32 pixels x 32 channels per warp
   static constexpr int kBudget = 232448 - 1024 - 512 - kStageBytes;
   static constexpr int kFit = (kBudget - kBS * kBBytes - kAS * kABytes) / kHaloBytes;
   // halo stages beyond the number of teams are the prefetch depth: a team's next box is already in flight while it
@@ -716,8 +716,8 @@ __device__ __forceinline__ void relu6_split_h2(unsigned long long v, uint32_t& h
   nlo_out = *reinterpret_cast<const uint32_t*>(&nl);
 }
 
-template <int CIN, int COUT, int S, int MODE>
-__global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid_constant__ CUtensorMap tmH,
+template <int CIN, int COUT, int S, int MODE, int EW>
+__global__ void __launch_bounds__(halo_threads(EW), 1) dwpw_halo_kernel(const __grid_constant__ CUtensorMap tmH,
                                                                    const float* __restrict__ dw_w /*[3][3][CIN]*/,
                                                                    const float* __restrict__ dw_b,
                                                                    const __grid_constant__ CUtensorMap tmB,
@@ -726,7 +726,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
                                                                    int tiles_per_frame, int n_tiles) {
   constexpr bool INQ = (MODE & kInQ) != 0, SPLIT_B = (MODE & kSplit) != 0, SPLIT = SPLIT_B || (MODE & kSplitA) != 0,
                  OUTQ = (MODE & kOutQ) != 0;
-  using SM = HaloCfg<CIN, COUT, S, SPLIT, SPLIT_B>;
+  using SM = HaloCfg<CIN, COUT, S, SPLIT, SPLIT_B, EW>;
+  constexpr int kEpiWarps = EW;
   constexpr int KB = SM::KB, NKB = SM::NKB, SWZ = SM::SWZ;
   constexpr int kAS = SM::kAS, kHS = SM::kHS, kAcc = SM::kAcc;
   constexpr int N_MMA = COUT > 256 ? 256 : COUT;
@@ -769,7 +770,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], kAcc == 2 ? 4 : kEpiWarps);
+      mbar_init(&tmem_empty_bar[s], (kAcc == 2 || EW == 4) ? 4 : kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -850,11 +851,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) dwpw_halo_kernel(const __grid
     const uint32_t stage = smem_u32(smem_o + (warp - kWarpEpi0) * 2048);
     const uint32_t srow = stage + lane * 64;
     const int sw = (lane >> 1) & 3;      // Swizzle<2,4,3>: 16-byte chunk ^= row bits [1,3)
-    constexpr int C_BEGIN_STEP = kAcc == 2 ? 0 : 256;  // one accumulator stage: group g owns columns [256 g, 256 g + 256)
-    constexpr int C_COUNT = kAcc == 2 ? COUT : 256;
-    uint32_t ti = kAcc == 2 ? (uint32_t)grp : 0u;
-    const int tile_step = kAcc == 2 ? 2 : 1;
-    for (int tile = blockIdx.x + (kAcc == 2 ? grp : 0) * (int)gridDim.x; tile < n_tiles; tile += tile_step * (int)gridDim.x, ti += tile_step) {
+    constexpr bool kByTile = kAcc == 2 && EW == 8;      // two groups, two accumulator stages: group g drains stage g
+    constexpr bool kByCols = kAcc == 1 && EW == 8;      // two groups, one stage: group g owns columns [256 g, 256 g + 256)
+    constexpr int C_BEGIN_STEP = kByCols ? 256 : 0;
+    constexpr int C_COUNT = kByCols ? 256 : COUT;
+    uint32_t ti = kByTile ? (uint32_t)grp : 0u;
+    const int tile_step = kByTile ? 2 : 1;
+    for (int tile = blockIdx.x + (kByTile ? grp : 0) * (int)gridDim.x; tile < n_tiles; tile += tile_step * (int)gridDim.x, ti += tile_step) {
       const int acc = ti % kAcc;
       const int f = tile / tiles_per_frame, rem = tile - f * tiles_per_frame;
       const int tyi = rem / tiles_x, txi = rem - tyi * tiles_x;
@@ -1100,6 +1103,28 @@ __global__ void __launch_bounds__(kConvThreads) conv1_tc_kernel(const uint8_t* _
   const uint32_t idesc = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   // rows start 4-byte aligned: the 3-channel producers can use aligned 32-bit loads
   const bool wide_loads = CIN == 3 && ((W * 3) & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0;
+  // the three image rows (9 bytes each) under output pixel m; issued one tile ahead so that the global-load latency hides
+  // behind the previous tile's MMA + epilogue (the kernel was latency-bound: 0.27 of HBM with ~50 % of the warps resident)
+  uint32_t rv[3][3];
+  bool have_rv = false;
+  auto load_rows = [&](long long m, uint32_t (&o)[3][3]) {
+    const int x = (int)(m % Wo);
+    const long long t2 = m / Wo;
+    const int y = (int)(t2 % Ho);
+    const long long frame_bytes = (long long)H * W * 3;
+    const uint8_t* base = img + (size_t)(t2 / Ho) * frame_bytes;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * y + ky;
+      if (iy < H) {
+        const long long roff = (long long)iy * W * 3;
+        load_row9(base + roff, x, W, frame_bytes - roff, o[ky][0], o[ky][1], o[ky][2]);
+      } else {  // zero padding row
+        o[ky][0] = o[ky][1] = 0x80808080u;
+        o[ky][2] = 0x80u;
+      }
+    }
+  };
 
   for (int it = 0; it < kConvTiles; ++it) {
     const long long m0 = ((long long)blockIdx.x * kConvTiles + it) * 128;
@@ -1128,23 +1153,7 @@ __global__ void __launch_bounds__(kConvThreads) conv1_tc_kernel(const uint8_t* _
       for (int i = 0; i < 32; ++i) hv[i] = __ushort_as_half((unsigned short)0);
       if (CIN == 3 && wide_loads) {
         if (ok) {  // 9 aligned 32-bit loads + byte permutes instead of 27 byte loads + conversions
-          const int x = (int)(m % Wo);
-          const long long t2 = m / Wo;
-          const int y = (int)(t2 % Ho);
-          const long long frame_bytes = (long long)H * W * 3;
-          const uint8_t* base = img + (size_t)(t2 / Ho) * frame_bytes;
-          uint32_t rv[3][3];
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            const int iy = 2 * y + ky;
-            if (iy < H) {
-              const long long roff = (long long)iy * W * 3;
-              load_row9(base + roff, x, W, frame_bytes - roff, rv[ky][0], rv[ky][1], rv[ky][2]);
-            } else {  // zero padding row
-              rv[ky][0] = rv[ky][1] = 0x80808080u;
-              rv[ky][2] = 0x80u;
-            }
-          }
+          if (!have_rv) load_rows(m, rv);  // else: prefetched while the previous tile's MMA and epilogue ran
           // 27 bytes (+ one padding byte) as 7 words, tap order (ky, kx, ci)
           uint32_t wd[7];
           wd[0] = rv[0][0];
@@ -1186,6 +1195,11 @@ __global__ void __launch_bounds__(kConvThreads) conv1_tc_kernel(const uint8_t* _
       tc_fence_before();  // orders the previous tile's tcgen05.ld before the next MMA overwrites TMEM
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full);
+      have_rv = false;
+      if (CIN == 3 && wide_loads && it + 1 < kConvTiles && m + 128 < M_total) {
+        load_rows(m + 128, rv);
+        have_rv = true;
+      }
       // ---- epilogue of this tile
       mbar_wait(&tmem_full, it & 1);
       tc_fence_after();
@@ -1626,6 +1640,7 @@ struct Block {
   CUtensorMap tmBh;    // weight map with the halo kernel's K block
   // "precise" halo path (MODE bits of dwpw_halo_kernel)
   int mode = 0;              // kInQ | kSplit | kOutQ, fixed at create time
+  int epi_warps = 4;         // epilogue warps of the COUT == CIN blocks (CB_DESC_EPI); the COUT = 2 CIN blocks always use 8
   bool runs_halo = false;    // this block is executed by dwpw_halo_kernel (decides the storage format of its input)
   float* dw_wq = nullptr;    // depthwise weights / bias with the q15 decode folded in
   float* dw_bq = nullptr;
@@ -1753,20 +1768,30 @@ int run_fused(const Block& b, int n, int sm, const __half* in, __half* out, cuda
   return launch_fused<512, 512, 1>(b, n, sm, in, out, st);
 }
 
-template <int CIN, int COUT, int S, int MODE>
-int launch_halo_mode(const Block& b, int n, int sm_count, int in_buf, cudaStream_t st) {
-  using SM = HaloCfg<CIN, COUT, S, (MODE & (kSplit | kSplitA)) != 0, (MODE & kSplit) != 0>;
-  auto kern = dwpw_halo_kernel<CIN, COUT, S, MODE>;
+template <int CIN, int COUT, int S, int MODE, int EW>
+int launch_halo_ew(const Block& b, int n, int sm_count, int in_buf, cudaStream_t st) {
+  using SM = HaloCfg<CIN, COUT, S, (MODE & (kSplit | kSplitA)) != 0, (MODE & kSplit) != 0, EW>;
+  auto kern = dwpw_halo_kernel<CIN, COUT, S, MODE, EW>;
   CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
   const int tiles_x = (b.Wo + kTW - 1) / kTW, tiles_y = (b.Ho + kTH - 1) / kTH;
   const int per_frame = tiles_x * tiles_y;
   const int n_tiles = n * per_frame;
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;  // persistent: one CTA per SM
-  kern<<<grid, kHaloThreads, SM::kTotal, st>>>(b.tmH[in_buf], (MODE & kInQ) ? b.dw_wq : b.dw_w, (MODE & kInQ) ? b.dw_bq : b.dw_b,
+  kern<<<grid, halo_threads(EW), SM::kTotal, st>>>(b.tmH[in_buf], (MODE & kInQ) ? b.dw_wq : b.dw_w, (MODE & kInQ) ? b.dw_bq : b.dw_b,
                                                (MODE & kSplit) ? b.tmBs : b.tmBh, (MODE & kOutQ) ? b.pw_bq : b.pw_b,
                                                b.tmO[in_buf ^ 1], tiles_x, per_frame, n_tiles);
   CB_LAUNCH_CHECK();
   return CB_OK;
+}
+
+template <int CIN, int COUT, int S, int MODE>
+int launch_halo_mode(const Block& b, int n, int sm_count, int in_buf, cudaStream_t st) {
+  if constexpr (COUT == CIN) {  // balanced blocks: the epilogue width is a run-time choice (CB_DESC_EPI), default one group
+    if (b.epi_warps == 8) return launch_halo_ew<CIN, COUT, S, MODE, 8>(b, n, sm_count, in_buf, st);
+    return launch_halo_ew<CIN, COUT, S, MODE, 4>(b, n, sm_count, in_buf, st);
+  } else {
+    return launch_halo_ew<CIN, COUT, S, MODE, 8>(b, n, sm_count, in_buf, st);
+  }
 }
 
 template <int CIN, int COUT, int S>
@@ -2288,6 +2313,11 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
       }
       layer += b.has_pw ? 2 : 1;
     }
+    // measured per shape (tools/bench_desc.py --layers, 64 frames of 480 x 640): 128->128 207 us with two epilogue groups vs 228
+    // with one, 512->512 102 vs 116, but 256->256 137 with ONE group vs 176 with two
+    for (Block& b : d->blocks) b.epi_warps = (b.C == 256 && b.Cout == 256) ? 4 : 8;
+    if (const char* ee = getenv("CB_DESC_EPI"))
+      for (Block& b : d->blocks) b.epi_warps = atoi(ee) == 8 ? 8 : 4;
     d->stem_q = !d->blocks.empty() && (d->blocks[0].mode & kInQ);
     if (d->stem_q) {
       std::vector<float> bq(32);
