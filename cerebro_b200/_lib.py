@@ -158,6 +158,7 @@ _SIGNATURES = {
         [_vp, C.c_int, _vp, _vp, _vp, C.POINTER(RansacParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     ),
     "cb_pnp_dls_minimal": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "cb_pnp_debug_read": (C.c_int64, [_vp, C.c_int, C.c_int, _vp, C.c_int64]),
 }
 
 _lib = None

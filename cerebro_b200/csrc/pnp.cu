@@ -431,6 +431,302 @@ __global__ void __launch_bounds__(kElimThreads) dls_eliminate_kernel(const doubl
 }
 
 // ---------------------------------------------------------------------------------------------
+// stage 2, second version (the default; CB_PNP_ELIM_V1=1 keeps the kernel above): ONE WARP per hypothesis and the
+// Gauss-Jordan solves run on REGISTERS.
+// The first version was issue-bound on shared-memory traffic and redundancy (ncu, profiles/r2b: 126 k warp instructions
+// per hypothesis -- 3 LDS/STS per FMA, the pivot search repeated by all four warps, a CTA barrier per pivot).  Here a lane
+// owns one matrix ROW in registers (blocks of 3..27 rows; the 36-row block gives lanes 0..3 a second row), so a pivot
+// step is: arg-max over the lanes with two REDUX + one ballot (lowest row wins ties, as before), the pivot lane
+// publishes its row through a 448-byte shared buffer (STS.128 / broadcast LDS.128), and every lane updates its own row
+// with (columns - k) independent DFMAs from registers.  Same pivots, same operations in the same order per element: the
+// action matrix is bit-identical to the first version's (tests/test_pnp_gpu.py compares them).
+// Shared memory per warp: N[60][27] | AUG (rows are still assembled lane = column, then read back lane = row) | the
+// pivot-row double buffer (later Y of the degree-7 block) | coef[60]  = 26 224 bytes -> 8 warps per SM.
+// ---------------------------------------------------------------------------------------------
+constexpr int kE2Warps = 4;
+constexpr int kE2Stride7 = 41;                       // AUG row stride of the 36 x 39 block (odd)
+constexpr int kE2AugDoubles = 1486;                  // >= 27 * kAug = 1485 and 36 * 41 = 1476, even
+constexpr int kE2RowBuf = 56;                        // one published pivot row (<= 54 columns), 16-byte aligned
+constexpr int kE2PerWarp = kNRows * kN + kE2AugDoubles + 2 * kE2RowBuf + 60;  // doubles
+constexpr int kE2SmemBytes = kE2Warps * kE2PerWarp * 8;
+static_assert(kE2PerWarp % 2 == 0 && (kNRows * kN) % 2 == 0, "16-byte alignment of the per-warp regions");
+
+// Gauss-Jordan on the first NR columns of an NR x NC system, lane = row (lanes >= NR hold zeros).  On return the lane
+// with myk == k holds unknown k, still scaled by its pivot mypiv.
+template <int NR, int NC>
+__device__ __forceinline__ void gauss_jordan_lanes(double (&a)[NC], double* rowbuf, int lane, int& myk, double& mypiv) {
+  // (no __restrict__ on the shared-memory pointers of this kernel: they carry data BETWEEN lanes, and a restrict-qualified
+  //  pointer lets the compiler keep a value it loaded before a __syncwarp() -- the pivot row of two steps earlier)
+  unsigned used = 0u;
+  myk = -1;
+  mypiv = 1.0;
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    const double x = a[k];
+    const bool cand = lane < NR && !((used >> lane) & 1u) && (x == x);
+    const int hi = cand ? (__double2hiint(x) & 0x7fffffff) : -1;
+    const int mhi = __reduce_max_sync(FULL, hi);
+    int p;
+    if (mhi < 0) {  // only NaNs left in the column: first unused row (the solve is lost anyway)
+      p = __ffs(~used & ((NR < 32) ? ((1u << NR) - 1u) : 0xffffffffu)) - 1;
+    } else {
+      const bool top = hi == mhi;
+      const unsigned lo = top ? (unsigned)__double2loint(x) : 0u;
+      const unsigned mlo = __reduce_max_sync(FULL, lo);
+      p = __ffs(__ballot_sync(FULL, top && lo == mlo)) - 1;
+    }
+    used |= 1u << p;
+    double* pr = rowbuf + (k & 1) * kE2RowBuf;
+    if (lane == p) {
+      myk = k;
+      mypiv = x;
+#pragma unroll
+      for (int c = k & ~1; c < NC; c += 2) {
+        if (c + 1 < NC)
+          *reinterpret_cast<double2*>(pr + c) = make_double2(a[c], a[c + 1]);
+        else
+          pr[c] = a[c];
+      }
+    }
+    __syncwarp();
+    const double inv = 1.0 / pr[k];
+    const double f = (lane == p || lane >= NR) ? 0.0 : x * inv;
+#pragma unroll
+    for (int c = (k + 1) & ~1; c < NC; c += 2) {
+      if (c + 1 < NC) {
+        const double2 pv = *reinterpret_cast<const double2*>(pr + c);
+        if (c > k) a[c] = fma(-f, pv.x, a[c]);
+        a[c + 1] = fma(-f, pv.y, a[c + 1]);
+      } else {
+        a[c] = fma(-f, pr[c], a[c]);
+      }
+    }
+  }
+}
+
+constexpr int kOffC[6] = {0, 3, 12, 30, 57, 93};  // dls::kBlockOff as compile-time constants
+
+template <int BLK>
+__device__ __forceinline__ void elim2_block(double* N, double* AUG, double* rowbuf, const double* coef, int lane) {
+  constexpr int o0 = kOffC[BLK], n = kOffC[BLK + 1] - kOffC[BLK], NC = n + kN;
+  for (int r = 0; r < n; ++r) {  // assemble [D | R] row by row, lane = column
+    const int row = o0 + r;
+    const int pi = dls::kRowPoly[row];
+    double* arow = AUG + r * kAug;
+    arow[lane] = 0.0;
+    if (lane + 32 < kAug) arow[lane + 32] = 0.0;
+    double c = 0.0;
+    int cd = 0;
+    if (lane < 20) {
+      c = coef[pi * 20 + lane];
+      cd = dls::kRowTerms[row][lane];
+    }
+    const double acc = row_lower_part(N, c, cd, o0, lane);
+    __syncwarp();
+    if (lane < 20) {
+      if (cd < kN) arow[n + cd] = -c;
+      else if (cd - kN >= o0) arow[cd - kN - o0] = c;
+    }
+    __syncwarp();
+    if (lane < kN) arow[n + lane] += acc;
+  }
+  __syncwarp();
+  double a[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) a[c] = lane < n ? AUG[lane * kAug + c] : 0.0;
+  int myk;
+  double mypiv;
+  gauss_jordan_lanes<n, NC>(a, rowbuf, lane, myk, mypiv);
+  if (lane < n) {  // normal forms: N[o0 + k][b] = R[row of unknown k][b] / pivot_k
+    const double inv = 1.0 / mypiv;
+    double* Nr = N + (o0 + myk) * kN;
+#pragma unroll
+    for (int b = 0; b < kN; ++b) Nr[b] = a[n + b] * inv;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * kE2Warps, 2) dls_eliminate2_kernel(const double* __restrict__ coef_in,
+                                                                         const int* __restrict__ status, int count,
+                                                                         double* __restrict__ S_out) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * kE2Warps + warp;
+  if (t >= count || status[t] != 0) return;  // warp-uniform, and the kernel has no CTA-wide barrier
+  double* N = sm + (size_t)warp * kE2PerWarp;  // [60][27]
+  double* AUG = N + kNRows * kN;
+  double* rowbuf = AUG + kE2AugDoubles;
+  double* coef = rowbuf + 2 * kE2RowBuf;
+  coef[lane] = coef_in[(size_t)t * 60 + lane];
+  if (lane + 32 < 60) coef[lane + 32] = coef_in[(size_t)t * 60 + lane + 32];
+  __syncwarp();
+
+  elim2_block<0>(N, AUG, rowbuf, coef, lane);
+  elim2_block<1>(N, AUG, rowbuf, coef, lane);
+  elim2_block<2>(N, AUG, rowbuf, coef, lane);
+  elim2_block<3>(N, AUG, rowbuf, coef, lane);
+
+  // ---------------- degree 7: three rows of D^-1 R via D^T Y = E_J (36 x 39; lanes 0..3 own rows 32..35 as well) ----
+  {
+    constexpr int o0 = kOffC[4], n = 36, NC = 39, ST = kE2Stride7;
+    for (int i = lane; i < n * ST; i += 32) AUG[i] = 0.0;
+    __syncwarp();
+    for (int r = 0; r < n; ++r) {  // row r of D -> column r of AUG
+      const int row = o0 + r;
+      const int pi = dls::kRowPoly[row];
+      if (lane < 20) {
+        const int cd = dls::kRowTerms[row][lane];
+        if (cd >= kN && cd - kN >= o0) AUG[(cd - kN - o0) * ST + r] = coef[pi * 20 + lane];
+      }
+    }
+    if (lane < 3) AUG[dls::kBorder7[lane] * ST + 36 + lane] = 1.0;
+    __syncwarp();
+    double aA[NC], aB[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      aA[c] = AUG[lane * ST + c];
+      aB[c] = lane < 4 ? AUG[(32 + lane) * ST + c] : 0.0;
+    }
+    unsigned usedA = 0u, usedB = 0u;
+    int mykA = -1, mykB = -1;
+    double mypivA = 1.0, mypivB = 1.0;
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+      const double xa = aA[k], xb = aB[k];
+      const bool candA = !((usedA >> lane) & 1u) && (xa == xa);
+      const bool candB = lane < 4 && !((usedB >> lane) & 1u) && (xb == xb);
+      const int hiA = candA ? (__double2hiint(xa) & 0x7fffffff) : -1;
+      const int hiB = candB ? (__double2hiint(xb) & 0x7fffffff) : -1;
+      const int mhi = __reduce_max_sync(FULL, hiA > hiB ? hiA : hiB);
+      int p;  // row 0..35
+      if (mhi < 0) {
+        p = (~usedA) ? __ffs(~usedA) - 1 : 32 + __ffs(~usedB & 0xfu) - 1;
+      } else {
+        const bool topA = hiA == mhi, topB = hiB == mhi;
+        const unsigned loA = topA ? (unsigned)__double2loint(xa) : 0u;
+        const unsigned loB = topB ? (unsigned)__double2loint(xb) : 0u;
+        const unsigned mlo = __reduce_max_sync(FULL, loA > loB ? loA : loB);
+        const unsigned bA = __ballot_sync(FULL, topA && loA == mlo);
+        const unsigned bB = __ballot_sync(FULL, topB && loB == mlo);
+        p = bA ? __ffs(bA) - 1 : 32 + __ffs(bB) - 1;  // lowest row index wins ties
+      }
+      if (p < 32) usedA |= 1u << p;
+      else usedB |= 1u << (p - 32);
+      double* pr = rowbuf + (k & 1) * kE2RowBuf;
+      if (lane == p) {
+        mykA = k;
+        mypivA = xa;
+#pragma unroll
+        for (int c = k & ~1; c < NC; c += 2) {
+          if (c + 1 < NC) *reinterpret_cast<double2*>(pr + c) = make_double2(aA[c], aA[c + 1]);
+          else pr[c] = aA[c];
+        }
+      }
+      if (lane + 32 == p) {
+        mykB = k;
+        mypivB = xb;
+#pragma unroll
+        for (int c = k & ~1; c < NC; c += 2) {
+          if (c + 1 < NC) *reinterpret_cast<double2*>(pr + c) = make_double2(aB[c], aB[c + 1]);
+          else pr[c] = aB[c];
+        }
+      }
+      __syncwarp();
+      const double inv = 1.0 / pr[k];
+      const double fA = (lane == p) ? 0.0 : xa * inv;
+      const double fB = (lane >= 4 || lane + 32 == p) ? 0.0 : xb * inv;
+#pragma unroll
+      for (int c = (k + 1) & ~1; c < NC; c += 2) {
+        if (c + 1 < NC) {
+          const double2 pv = *reinterpret_cast<const double2*>(pr + c);
+          if (c > k) {
+            aA[c] = fma(-fA, pv.x, aA[c]);
+            aB[c] = fma(-fB, pv.x, aB[c]);
+          }
+          aA[c + 1] = fma(-fA, pv.y, aA[c + 1]);
+          aB[c + 1] = fma(-fB, pv.y, aB[c + 1]);
+        } else {
+          aA[c] = fma(-fA, pr[c], aA[c]);
+          aB[c] = fma(-fB, pr[c], aB[c]);
+        }
+      }
+    }
+    // Y[r][j] = (row of unknown r)[36 + j] / pivot_r  -> shared (aliases the pivot-row buffers: wait for their readers)
+    __syncwarp();
+    double* Y = rowbuf;  // [36][3]
+    {
+      const double inv = 1.0 / mypivA;
+      Y[mykA * 3 + 0] = aA[36] * inv;
+      Y[mykA * 3 + 1] = aA[37] * inv;
+      Y[mykA * 3 + 2] = aA[38] * inv;
+    }
+    if (lane < 4) {
+      const double inv = 1.0 / mypivB;
+      Y[mykB * 3 + 0] = aB[36] * inv;
+      Y[mykB * 3 + 1] = aB[37] * inv;
+      Y[mykB * 3 + 2] = aB[38] * inv;
+    }
+    __syncwarp();
+    // contract: N7[j][b] = sum_r Y[r][j] * R[r][b]; four partial sums over r mod 4, added in the first version's order
+    double acc[4][3];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) acc[w][0] = acc[w][1] = acc[w][2] = 0.0;
+    for (int r4 = 0; r4 < n; r4 += 4) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int r = r4 + w;
+        const int row = o0 + r;
+        const int pi = dls::kRowPoly[row];
+        double c = 0.0;
+        int cd = 0;
+        if (lane < 20) {
+          c = coef[pi * 20 + lane];
+          cd = dls::kRowTerms[row][lane];
+        }
+        double rr = row_lower_part(N, c, cd, o0, lane);
+        unsigned m = __ballot_sync(FULL, lane < 20 && cd < kN);
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const double cc = __shfl_sync(FULL, c, b);
+          const int code = __shfl_sync(FULL, cd, b);
+          if (lane == code) rr -= cc;
+        }
+        acc[w][0] = fma(Y[r * 3 + 0], rr, acc[w][0]);
+        acc[w][1] = fma(Y[r * 3 + 1], rr, acc[w][1]);
+        acc[w][2] = fma(Y[r * 3 + 2], rr, acc[w][2]);
+      }
+    }
+    if (lane < kN) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) v += acc[w][j];
+        N[(57 + j) * kN + lane] = v;
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---------------- action matrix of f0 ----------------
+  double* So = S_out + (size_t)t * kN * kN;
+  for (int b = 0; b < kN; ++b) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int cd = dls::kF0Terms[b][k];
+      if (cd < kN) {
+        if (lane == cd) v += dls::kF0[k];
+      } else if (lane < kN) {
+        v += dls::kF0[k] * N[(cd - kN) * kN + lane];
+      }
+    }
+    if (lane < kN) So[b * kN + lane] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // stage 3: eigenvalues + roots + cheirality (warp per hypothesis)
 // ---------------------------------------------------------------------------------------------
 constexpr int kRootsWarps = 4;
@@ -1170,6 +1466,7 @@ struct cb_pnp {
   int device = 0, sm_count = 0;
   int max_cand = 0, max_points = 0, max_hyp = 0;
   int chunk = 16384;
+  bool elim_v1 = false;  // CB_PNP_ELIM_V1=1: the CTA-per-hypothesis shared-memory elimination (cross-check of the default)
   cudaStream_t stream = nullptr;
   // inputs (host API staging)
   int* offsets = nullptr;
@@ -1196,12 +1493,23 @@ struct cb_pnp {
 
 namespace {
 
+int launch_eliminate(cb_pnp* p, int count, cudaStream_t st) {
+  if (p->elim_v1) {
+    CB_CUDA(cudaFuncSetAttribute(dls_eliminate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kElimSmemBytes));
+    dls_eliminate_kernel<<<count, kElimThreads, kElimSmemBytes, st>>>(p->coef, p->status, count, p->S);
+  } else {
+    CB_CUDA(cudaFuncSetAttribute(dls_eliminate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kE2SmemBytes));
+    dls_eliminate2_kernel<<<(count + kE2Warps - 1) / kE2Warps, 32 * kE2Warps, kE2SmemBytes, st>>>(p->coef, p->status, count,
+                                                                                                 p->S);
+  }
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
 int run_chunks(cb_pnp* p, int n_cand, const int* offsets_dev, const double* X, const double* uv, int H,
                const cb_ransac_params& prm, const int* samples_dev, cudaStream_t st) {
   const long long total = (long long)n_cand * H;
-  const size_t elim_smem = kElimSmemBytes;
   const size_t roots_smem = (size_t)kRootsWarps * kRootsSmemPerWarp * sizeof(double);
-  CB_CUDA(cudaFuncSetAttribute(dls_eliminate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)elim_smem));
   CB_CUDA(cudaFuncSetAttribute(dls_roots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)roots_smem));
   for (long long g0 = 0; g0 < total; g0 += p->chunk) {
     const int count = (int)((total - g0) < p->chunk ? (total - g0) : p->chunk);
@@ -1220,8 +1528,7 @@ int run_chunks(cb_pnp* p, int n_cand, const int* offsets_dev, const double* X, c
     sa.status = p->status;
     dls_setup_kernel<<<(count + 127) / 128, 128, 0, st>>>(sa);
     CB_LAUNCH_CHECK();
-    dls_eliminate_kernel<<<count, kElimThreads, elim_smem, st>>>(p->coef, p->status, count, p->S);
-    CB_LAUNCH_CHECK();
+    if (int rc = launch_eliminate(p, count, st)) return rc;
     RootsArgs ra;
     ra.S = p->S;
     ra.T = p->T;
@@ -1261,6 +1568,7 @@ int cb_pnp_create(cb_pnp** out, int max_candidates, int max_points_total, int ma
   p->max_cand = max_candidates;
   p->max_points = max_points_total;
   p->max_hyp = max_hypotheses;
+  if (const char* env = getenv("CB_PNP_ELIM_V1")) p->elim_v1 = env[0] == '1';
   const size_t all = (size_t)max_candidates * max_hypotheses;
   if ((size_t)p->chunk > all) p->chunk = (int)all;
   const size_t ch = (size_t)p->chunk;
@@ -1509,9 +1817,7 @@ int cb_pnp_dls_minimal(cb_pnp* p, int n_sets, int m, const double* X, const doub
   delete[] h_off;
   delete[] h_samples;
   if (total < 20) return cb::fail(CB_EINVAL, "need at least 2 sets");
-  const size_t elim_smem = kElimSmemBytes;
   const size_t roots_smem = (size_t)kRootsWarps * kRootsSmemPerWarp * sizeof(double);
-  CB_CUDA(cudaFuncSetAttribute(dls_eliminate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)elim_smem));
   CB_CUDA(cudaFuncSetAttribute(dls_roots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)roots_smem));
   SetupArgs sa;
   sa.offsets = p->offsets;
@@ -1528,8 +1834,7 @@ int cb_pnp_dls_minimal(cb_pnp* p, int n_sets, int m, const double* X, const doub
   sa.status = p->status;
   dls_setup_kernel<<<(n_sets + 127) / 128, 128, 0, st>>>(sa);
   CB_LAUNCH_CHECK();
-  dls_eliminate_kernel<<<n_sets, kElimThreads, elim_smem, st>>>(p->coef, p->status, n_sets, p->S);
-  CB_LAUNCH_CHECK();
+  if (int rc = launch_eliminate(p, n_sets, st)) return rc;
   RootsArgs ra;
   ra.S = p->S;
   ra.T = p->T;
@@ -1557,6 +1862,17 @@ int cb_pnp_dls_minimal(cb_pnp* p, int n_sets, int m, const double* X, const doub
     }
   delete[] hm;
   return CB_OK;
+}
+
+int64_t cb_pnp_debug_read(cb_pnp* p, int what, int n_sets, double* out, int64_t max_doubles) {
+  if (!p || !out || n_sets < 1 || n_sets > p->chunk || what < 0 || what > 1) return cb::fail(CB_EINVAL, "bad arguments");
+  cb::DeviceGuard g(p->device);
+  const int64_t per = what == 0 ? kN * kN : 60;
+  const int64_t n = per * n_sets;
+  if (n > max_doubles) return cb::fail(CB_EINVAL, "buffer too small: %lld doubles needed", (long long)n);
+  CB_CUDA(cudaStreamSynchronize(p->stream));
+  CB_CUDA(cudaMemcpy(out, what == 0 ? p->S : p->coef, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  return n;
 }
 
 }  // extern "C"

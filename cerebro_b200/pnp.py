@@ -129,6 +129,15 @@ class PnpBatch:
         check(self._lib.cb_pnp_dls_minimal(self._h, s, m, ptr(X_sets), ptr(uv_sets), ptr(ns), ptr(R), ptr(t)))
         return ns, R, t
 
+    def debug_read(self, what: int, n_sets: int) -> np.ndarray:
+        """Intermediates of the last dls_minimal call: what = 0 the 27 x 27 action matrices, 1 the 60 gradient coefficients."""
+        per = 729 if what == 0 else 60
+        out = np.empty((n_sets, per), dtype=np.float64)
+        n = self._lib.cb_pnp_debug_read(self._h, what, n_sets, ptr(out), out.size)
+        if n < 0:
+            check(int(n))
+        return out.reshape(n_sets, 27, 27) if what == 0 else out
+
 
 class StaticTheiaPoseCompute:
     """Same call shape as the reference class (src/DlsPnpWithRansac.h:169-179)."""

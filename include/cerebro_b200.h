@@ -314,6 +314,9 @@ CB_API int cb_pnp_icp_batch_device(cb_pnp* p, int n_cand, const int32_t* offsets
  * row-major, t [n_sets][27][3].  For parity tests of the solver. */
 CB_API int cb_pnp_dls_minimal(cb_pnp* p, int n_sets, int m, const double* X, const double* uv,
                        int32_t* n_solutions, double* R, double* t);
+/* parity tests: intermediates of the last cb_pnp_dls_minimal call, per set -- what = 0: the 27 x 27 action matrix
+ * (729 doubles), 1: the 60 gradient coefficients.  Returns the number of doubles copied, negative on error. */
+CB_API int64_t cb_pnp_debug_read(cb_pnp* p, int what, int n_sets, double* out, int64_t max_doubles);
 
 /* ------------------------------------------------------------------------------------
  * frontend: ORB descriptors + keypoints + depth images of a loop candidate's two frames ->

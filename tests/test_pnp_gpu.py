@@ -137,3 +137,29 @@ def test_config5_scale_properties(native_lib, cuda_device):
     e = _pose_err(r["T"][5], o["T"])
     assert e[0] < ROT_TOL and e[1] < TRANS_TOL
     pb.close()
+
+
+def test_elimination_versions_bit_identical(native_lib, cuda_device, monkeypatch):
+    """The register-resident warp-per-hypothesis elimination (default) picks the same pivots and applies the same operations
+    in the same order as the CTA-per-hypothesis shared-memory kernel (CB_PNP_ELIM_V1=1): every solution must match bit
+    for bit, on clean, noisy and outlier-contaminated minimal sets."""
+    from cerebro_b200.pnp import PnpBatch
+    from oracle import dls_pnp as D
+
+    rng = np.random.default_rng(7)
+    sets = [D.synth_candidate(rng, n=15, noise=[0.0, 1e-3, 2e-2][i % 3], outlier_frac=0.3 if i % 5 == 4 else 0.0)[:2] for i in range(300)]
+    X = np.stack([s[0] for s in sets])
+    uv = np.stack([s[1] for s in sets])
+    out, acts = [], []
+    for v1 in ("1", "0"):
+        monkeypatch.setenv("CB_PNP_ELIM_V1", v1)
+        pb = PnpBatch(max_candidates=1, max_points_total=300 * 15, max_hypotheses=512)
+        out.append(pb.dls_minimal(X, uv))
+        acts.append(pb.debug_read(0, 300))
+        pb.close()
+    (ns1, R1, t1), (ns2, R2, t2) = out
+    assert np.array_equal(acts[0], acts[1], equal_nan=True)  # the 27 x 27 action matrices themselves
+    assert np.array_equal(ns1, ns2)
+    assert ns1.sum() > 250
+    for i in range(300):
+        assert np.array_equal(R1[i, : ns1[i]], R2[i, : ns2[i]]) and np.array_equal(t1[i, : ns1[i]], t2[i, : ns2[i]]), i
