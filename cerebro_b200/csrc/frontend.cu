@@ -558,6 +558,60 @@ __global__ void sbm_vsad_kernel(const uint16_t* __restrict__ hsad, const int* __
   }
 }
 
+// Vertical pass, second version (the default for numDisparities == 64, the reference's value; CB_SBM_V1=1 keeps the kernel
+// above): ONE WARP per (output column, row stripe), a lane owns candidates 2*lane and 2*lane+1 -- one aligned 32-bit load
+// fetches both u16 sums, a warp reads the 128 contiguous bytes of a pixel -- and the per-pixel decision is warp-parallel:
+// first minimum = one REDUX.MIN over (sad << 8 | d), uniqueness test = one vote, the two parabola neighbours by shuffle.
+// Same integers as sbm_decide (tests compare the two kernels and the oracle).  [The first version's decision was a serial
+// scan by thread 0 of a 64-thread block between two block barriers: 6.4 ms for 8 pairs of 480 x 640.]
+constexpr int kSbm2Warps = 8;     // adjacent output columns per block
+constexpr int kSbm2Stripe = 120;  // rows per warp
+
+__global__ void __launch_bounds__(32 * kSbm2Warps) sbm_vsad2_kernel(const uint16_t* __restrict__ hsad, const int* __restrict__ htext,
+                                                                    SbmGeom g, int16_t* __restrict__ disp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.z, x = blockIdx.x * kSbm2Warps + warp;
+  if (x >= g.width1) return;
+  const int y0 = blockIdx.y * kSbm2Stripe, y1 = min(y0 + kSbm2Stripe, g.h);
+  const size_t hs = (size_t)pair * g.h * g.width1;
+  const uint32_t* H = reinterpret_cast<const uint32_t*>(hsad + hs * 64);  // [row][column][32 pairs of candidates]
+  const int* T = htext + hs;
+  int16_t* out = disp + (size_t)pair * g.h * g.w;
+  const int d0 = 2 * lane, d1 = 2 * lane + 1;
+  int r0 = 0, r1 = 0;
+  for (int j = -g.wsz2; j <= g.wsz2; ++j) {
+    const uint32_t v = __ldg(H + ((size_t)sbm_clampi(y0 + j, 0, g.h - 1) * g.width1 + x) * 32 + lane);
+    r0 += (int)(v & 0xffffu);
+    r1 += (int)(v >> 16);
+  }
+  int tsum = sbm_vtext_init(T, g, x, y0);  // every lane keeps it (broadcast loads)
+  for (int y = y0; y < y1; ++y) {
+    // next row's two loads first: they do not depend on the decision
+    const uint32_t va = __ldg(H + ((size_t)sbm_clampi(y + 1 + g.wsz2, 0, g.h - 1) * g.width1 + x) * 32 + lane);
+    const uint32_t vb = __ldg(H + ((size_t)sbm_clampi(y - g.wsz2, 0, g.h - 1) * g.width1 + x) * 32 + lane);
+    const unsigned k0 = ((unsigned)r0 << 8) | (unsigned)d0, k1 = ((unsigned)r1 << 8) | (unsigned)d1;
+    const unsigned kmin = __reduce_min_sync(0xffffffffu, k0 < k1 ? k0 : k1);
+    const int minsad = (int)(kmin >> 8), mind = (int)(kmin & 255u);
+    int v = g.filtered;
+    if (tsum >= g.texture_threshold) {  // warp-uniform
+      const int thresh = minsad + (minsad * g.uniqueness_ratio / 100);
+      const bool bad = ((d0 < mind - 1 || d0 > mind + 1) && r0 <= thresh) || ((d1 < mind - 1 || d1 > mind + 1) && r1 <= thresh);
+      if (!(g.uniqueness_ratio > 0 && __any_sync(0xffffffffu, bad))) {
+        const int ip = mind + 1 == 64 ? 62 : mind + 1, in = mind - 1 < 0 ? 1 : mind - 1;  // the two guard elements
+        const int pa = __shfl_sync(0xffffffffu, r0, ip >> 1), pb = __shfl_sync(0xffffffffu, r1, ip >> 1);
+        const int na = __shfl_sync(0xffffffffu, r0, in >> 1), nb = __shfl_sync(0xffffffffu, r1, in >> 1);
+        const int p = (ip & 1) ? pb : pa, n = (in & 1) ? nb : na;
+        const int dd = p + n - 2 * minsad + (p > n ? p - n : n - p);
+        v = (((64 - mind - 1 + g.mindisp) * 256 + (dd != 0 ? (p - n) * 256 / dd : 0) + 15) >> 4);
+      }
+    }
+    if (lane == 0) out[(size_t)y * g.w + g.lofs + x] = (int16_t)(sbm_in_roi(g, y, g.lofs + x) ? v : g.filtered);
+    r0 += (int)(va & 0xffffu) - (int)(vb & 0xffffu);
+    r1 += (int)(va >> 16) - (int)(vb >> 16);
+    tsum = sbm_vtext_step(T, g, x, y, tsum);
+  }
+}
+
 __global__ void sbm_to3d_kernel(const int16_t* __restrict__ disp, int n, int h, int w, float Q03, float Q13, float Q23, float Q32,
                                 float Q33, float* __restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -593,6 +647,7 @@ struct cb_frontend {
   unsigned long long* best = nullptr;
   // tensor-core matcher: descriptors expanded to one byte per bit + their popcounts (CB_MATCH_SIMT=1 keeps the popc kernel)
   bool match_simt = false;
+  bool sbm_v1 = false;  // CB_SBM_V1=1: block-per-column vertical pass with the serial decision (cross-check of the default)
   uint8_t* e1 = nullptr;
   uint8_t* e2 = nullptr;
   int* pop1 = nullptr;
@@ -645,6 +700,7 @@ int cb_frontend_create(cb_frontend** out, int max_pairs, int max_features, int d
   f->sm_count = sm_count;
   const char* env = getenv("CB_MATCH_SIMT");
   f->match_simt = env && env[0] == '1';
+  if (const char* e2 = getenv("CB_SBM_V1")) f->sbm_v1 = e2[0] == '1';
   f->max_pairs = max_pairs;
   f->max_features = max_features;
   const size_t tot = (size_t)max_pairs * max_features;
@@ -829,8 +885,12 @@ int cb_frontend_stereo_bm(cb_frontend* f, int n, const uint8_t* left, const uint
     sbm_hsad_kernel<<<dim3((unsigned)((g.width1 + kSbmSeg - 1) / kSbmSeg), (unsigned)rows, (unsigned)nc), ndisp, 0, st>>>(
         f->sb_pre, f->sb_pre + per * nc, g, f->sb_hsad, f->sb_htext);
     CB_LAUNCH_CHECK();
-    sbm_vsad_kernel<<<dim3((unsigned)g.width1, (unsigned)((rows + kSbmStripe - 1) / kSbmStripe), (unsigned)nc), ndisp,
-                      (size_t)(ndisp + 2) * sizeof(int), st>>>(f->sb_hsad, f->sb_htext, g, f->sb_disp);
+    if (ndisp == 64 && !f->sbm_v1)
+      sbm_vsad2_kernel<<<dim3((unsigned)((g.width1 + kSbm2Warps - 1) / kSbm2Warps), (unsigned)((rows + kSbm2Stripe - 1) / kSbm2Stripe),
+                              (unsigned)nc), 32 * kSbm2Warps, 0, st>>>(f->sb_hsad, f->sb_htext, g, f->sb_disp);
+    else
+      sbm_vsad_kernel<<<dim3((unsigned)g.width1, (unsigned)((rows + kSbmStripe - 1) / kSbmStripe), (unsigned)nc), ndisp,
+                        (size_t)(ndisp + 2) * sizeof(int), st>>>(f->sb_hsad, f->sb_htext, g, f->sb_disp);
     CB_LAUNCH_CHECK();
     CB_CUDA(cudaEventRecord(f->ev[1], st));
     CB_CUDA(cudaMemcpyAsync(disparity + (size_t)c0 * per, f->sb_disp, per * sizeof(int16_t) * nc, cudaMemcpyDeviceToHost, st));

@@ -99,3 +99,30 @@ def test_device_stereo_matches_oracle(native_lib, cuda_device):
     with pytest.raises(Exception):
         fe.stereo_bm(left, right, ndisp=20, wsz=5)
     fe.close()
+
+
+@pytest.mark.gpu
+def test_device_stereo_full_size_and_both_vertical_passes(native_lib, cuda_device, monkeypatch):
+    """480 x 640 (the bench / EuRoC-sized frames): the warp-per-column vertical pass (default), the block-per-column one
+    (CB_SBM_V1=1) and the installed OpenCV -- or, without cv2, the oracle on a crop-free 480 x 640 pair -- give the same
+    int16 image; textureless band, disparity jumps and the ROI border included."""
+    from cerebro_b200.frontend import FrontEnd
+
+    pairs = [stereo_scene(480, 640, kind, seed=40 + kind) for kind in range(3)]
+    L, R = np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+    out = []
+    for v1 in ("0", "1"):
+        monkeypatch.setenv("CB_SBM_V1", v1)
+        fe = FrontEnd(max_pairs=1, max_features=512)
+        out.append(fe.stereo_bm(L, R, ndisp=64, wsz=21))
+        fe.close()
+    assert np.array_equal(out[0], out[1])
+    assert (out[0] >= 0).mean() > 0.3 and (out[0] == -16).mean() > 0.05
+    try:
+        import cv2
+
+        bm = cv2.StereoBM_create(64, 21)
+        ref = np.stack([bm.compute(L[k], R[k]) for k in range(3)])
+    except ImportError:
+        ref = np.stack([stereo.stereo_bm(L[k], R[k], ndisp=64, wsz=21) for k in range(3)])
+    assert np.array_equal(out[0], ref)
