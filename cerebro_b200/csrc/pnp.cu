@@ -506,34 +506,75 @@ __device__ __forceinline__ void gauss_jordan_lanes(double (&a)[NC], double* rowb
 
 constexpr int kOffC[6] = {0, 3, 12, 30, 57, 93};  // dls::kBlockOff as compile-time constants
 
+// Row descriptions for lane = row access: per template row 24 bytes = its 20 term codes, the polynomial index, 3 pad.
+// (The __constant__ tables of dls_tables.h serialise when every lane asks for a different row; this copy lives in global
+// memory / L1 and is filled once per handle by dls_pack_rows_kernel.)
+__device__ unsigned int g_dls_rows[dls::kNonRed * 6];
+
+__global__ void dls_pack_rows_kernel() {
+  const int r = threadIdx.x;
+  if (r >= dls::kNonRed) return;
+  unsigned char b[24];
+  for (int t = 0; t < 20; ++t) b[t] = dls::kRowTerms[r][t];
+  b[20] = dls::kRowPoly[r];
+  b[21] = b[22] = b[23] = 0;
+  for (int i = 0; i < 6; ++i)
+    g_dls_rows[r * 6 + i] = (unsigned)b[4 * i] | ((unsigned)b[4 * i + 1] << 8) | ((unsigned)b[4 * i + 2] << 16) | ((unsigned)b[4 * i + 3] << 24);
+}
+
+// One template row per LANE: the lane walks the 20 terms of row `row`; terms on a same-degree non-reduced monomial or on
+// a reduced monomial are scattered into the lane's own shared-memory row `arow` ([D (n) | R (27)], zeroed here), the
+// lower-degree terms are folded into 27 register accumulators: racc[b] -= c * N[cd - 27][b], in ascending term order (the
+// order of the first version's ballot loop, so the sums round identically).  TRANSPOSED = the degree-7 block, which only
+// needs the right-hand side (its D goes to shared memory transposed, by the caller).
+template <int O0, int NCOLS_D, bool RHS_ONLY>
+__device__ __forceinline__ void lane_row_assemble(bool active, int row, const double* coef, const double* N, double* arow,
+                                                  double (&racc)[kN]) {
+  const unsigned int* rw = g_dls_rows + (active ? row : 0) * 6;
+  unsigned int w[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) w[i] = __ldg(rw + i);
+  const int pi = (int)(w[5] & 0xffu);
+#pragma unroll
+  for (int b = 0; b < kN; ++b) racc[b] = 0.0;
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < NCOLS_D + kN; ++c) arow[c] = 0.0;
+  }
+#pragma unroll
+  for (int t = 0; t < 20; ++t) {
+    const int cd = (int)((w[t >> 2] >> (8 * (t & 3))) & 0xffu);
+    const double c = coef[pi * 20 + t];
+    const bool lower = active && cd >= kN && (cd - kN) < O0;
+    if (active) {
+      if (cd < kN) arow[NCOLS_D + cd] = -c;
+      else if (!RHS_ONLY && cd - kN >= O0) arow[cd - kN - O0] = c;
+    }
+    if (O0 > 0 && __any_sync(FULL, lower)) {  // warp-uniform
+      const double* Nb = N + (lower ? (cd - kN) * kN : 0);
+#pragma unroll
+      for (int b = 0; b < kN; ++b)
+        if (lower) racc[b] = fma(-c, Nb[b], racc[b]);
+    }
+  }
+}
+
 template <int BLK>
 __device__ __forceinline__ void elim2_block(double* N, double* AUG, double* rowbuf, const double* coef, int lane) {
   constexpr int o0 = kOffC[BLK], n = kOffC[BLK + 1] - kOffC[BLK], NC = n + kN;
-  for (int r = 0; r < n; ++r) {  // assemble [D | R] row by row, lane = column
-    const int row = o0 + r;
-    const int pi = dls::kRowPoly[row];
-    double* arow = AUG + r * kAug;
-    arow[lane] = 0.0;
-    if (lane + 32 < kAug) arow[lane + 32] = 0.0;
-    double c = 0.0;
-    int cd = 0;
-    if (lane < 20) {
-      c = coef[pi * 20 + lane];
-      cd = dls::kRowTerms[row][lane];
-    }
-    const double acc = row_lower_part(N, c, cd, o0, lane);
-    __syncwarp();
-    if (lane < 20) {
-      if (cd < kN) arow[n + cd] = -c;
-      else if (cd - kN >= o0) arow[cd - kN - o0] = c;
-    }
-    __syncwarp();
-    if (lane < kN) arow[n + lane] += acc;
-  }
-  __syncwarp();
+  // every lane assembles ITS row [D | R]: scatter through its own shared-memory row (a term's column is a run-time index),
+  // lower-degree terms through registers; nothing crosses lanes, so no barrier
+  const bool active = lane < n;
+  double* arow = AUG + lane * kAug;
   double a[NC];
+  {
+    double racc[kN];
+    lane_row_assemble<o0, n, false>(active, o0 + lane, coef, N, arow, racc);
 #pragma unroll
-  for (int c = 0; c < NC; ++c) a[c] = lane < n ? AUG[lane * kAug + c] : 0.0;
+    for (int c = 0; c < NC; ++c) a[c] = active ? arow[c] : 0.0;
+#pragma unroll
+    for (int b = 0; b < kN; ++b) a[n + b] += racc[b];  // (direct term) + (lower-degree part), as the first version adds them
+  }
   int myk;
   double mypiv;
   gauss_jordan_lanes<n, NC>(a, rowbuf, lane, myk, mypiv);
@@ -667,7 +708,48 @@ __global__ void __launch_bounds__(32 * kE2Warps, 2) dls_eliminate2_kernel(const 
       Y[mykB * 3 + 2] = aB[38] * inv;
     }
     __syncwarp();
-    // contract: N7[j][b] = sum_r Y[r][j] * R[r][b]; four partial sums over r mod 4, added in the first version's order
+    // right-hand side rows of the 36 degree-7 template rows, one per lane (two passes: rows 0..31, then 32..35), into
+    // shared memory (AUG is free again); then lane = column b contracts N7[j][b] = sum_r Y[r][j] * R[r][b], four partial
+    // sums over r mod 4 added in the first version's order
+    double* Rsm = AUG;  // [36][27]
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int r = pass * 32 + lane;
+      const bool active = r < n;
+      double racc[kN];
+      double* rrow = Rsm + (active ? r : 0) * kN;
+      {
+        const unsigned int* rw = g_dls_rows + (o0 + (active ? r : 0)) * 6;
+        unsigned int w[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) w[i] = __ldg(rw + i);
+        const int pi = (int)(w[5] & 0xffu);
+#pragma unroll
+        for (int b = 0; b < kN; ++b) racc[b] = 0.0;
+        double cs[20];
+        int cds[20];
+#pragma unroll
+        for (int t = 0; t < 20; ++t) {
+          cds[t] = (int)((w[t >> 2] >> (8 * (t & 3))) & 0xffu);
+          cs[t] = coef[pi * 20 + t];
+          const bool lower = active && cds[t] >= kN && (cds[t] - kN) < o0;
+          if (__any_sync(FULL, lower)) {
+            const double* Nb = N + (lower ? (cds[t] - kN) * kN : 0);
+#pragma unroll
+            for (int b = 0; b < kN; ++b)
+              if (lower) racc[b] = fma(-cs[t], Nb[b], racc[b]);
+          }
+        }
+        if (active) {
+#pragma unroll
+          for (int b = 0; b < kN; ++b) rrow[b] = racc[b];
+#pragma unroll
+          for (int t = 0; t < 20; ++t)
+            if (cds[t] < kN) rrow[cds[t]] -= cs[t];  // a reduced monomial appears once per row
+        }
+      }
+    }
+    __syncwarp();
     double acc[4][3];
 #pragma unroll
     for (int w = 0; w < 4; ++w) acc[w][0] = acc[w][1] = acc[w][2] = 0.0;
@@ -675,23 +757,7 @@ __global__ void __launch_bounds__(32 * kE2Warps, 2) dls_eliminate2_kernel(const 
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         const int r = r4 + w;
-        const int row = o0 + r;
-        const int pi = dls::kRowPoly[row];
-        double c = 0.0;
-        int cd = 0;
-        if (lane < 20) {
-          c = coef[pi * 20 + lane];
-          cd = dls::kRowTerms[row][lane];
-        }
-        double rr = row_lower_part(N, c, cd, o0, lane);
-        unsigned m = __ballot_sync(FULL, lane < 20 && cd < kN);
-        while (m) {
-          const int b = __ffs(m) - 1;
-          m &= m - 1;
-          const double cc = __shfl_sync(FULL, c, b);
-          const int code = __shfl_sync(FULL, cd, b);
-          if (lane == code) rr -= cc;
-        }
+        const double rr = lane < kN ? Rsm[r * kN + lane] : 0.0;
         acc[w][0] = fma(Y[r * 3 + 0], rr, acc[w][0]);
         acc[w][1] = fma(Y[r * 3 + 1], rr, acc[w][1]);
         acc[w][2] = fma(Y[r * 3 + 2], rr, acc[w][2]);
@@ -1569,6 +1635,12 @@ int cb_pnp_create(cb_pnp** out, int max_candidates, int max_points_total, int ma
   p->max_points = max_points_total;
   p->max_hyp = max_hypotheses;
   if (const char* env = getenv("CB_PNP_ELIM_V1")) p->elim_v1 = env[0] == '1';
+  dls_pack_rows_kernel<<<1, 96>>>();  // per-lane copy of the template rows (idempotent; device calls may arrive on any stream)
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    const cudaError_t e0 = cudaGetLastError();
+    delete p;
+    return cb::fail(CB_ECUDA, "dls_pack_rows_kernel failed: %s", cudaGetErrorString(e0));
+  }
   const size_t all = (size_t)max_candidates * max_hypotheses;
   if ((size_t)p->chunk > all) p->chunk = (int)all;
   const size_t ch = (size_t)p->chunk;
