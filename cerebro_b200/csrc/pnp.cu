@@ -451,18 +451,27 @@ constexpr int kE2PerWarp = kNRows * kN + kE2AugDoubles + 2 * kE2RowBuf + 60;  //
 constexpr int kE2SmemBytes = kE2Warps * kE2PerWarp * 8;
 static_assert(kE2PerWarp % 2 == 0 && (kNRows * kN) % 2 == 0, "16-byte alignment of the per-warp regions");
 
-// Gauss-Jordan on the first NR columns of an NR x NC system, lane = row (lanes >= NR hold zeros).  On return the lane
-// with myk == k holds unknown k, still scaled by its pivot mypiv.
+// IEEE reciprocal, deliberately NOT inlined: the inline expansion is ~45 instructions per use, and straight-line code size
+// -- not arithmetic -- was the limit of this kernel's first register-resident version (45 k SASS instructions executed once
+// per hypothesis: ncu showed 32 % of the warp stalls on instruction fetch)
+__device__ __noinline__ double dls_recip(double x) { return 1.0 / x; }
+
+// Gauss-Jordan on the first NR columns of an NR x NC system, lane = row (lanes >= NR hold zeros).  The pivot loop is a
+// real loop: after step k column k is dead, so every step shifts the row one column to the left while it eliminates
+// (a[c] = a[c+1] - f * pivot_row[c+1]) and the pivot column is always a[0] -- register indices stay compile-time constants
+// without unrolling the NR steps.  On return the right-hand sides sit in a[0 .. NC-NR) and the lane with myk == k holds
+// unknown k, still scaled by its pivot mypiv.  Same pivots and the same operations per live element as the first version.
+// (No __restrict__ on the shared-memory pointers of this kernel: they carry data BETWEEN lanes, and a restrict-qualified
+// pointer lets the compiler keep a value it loaded before a __syncwarp() -- the pivot row of two steps earlier.)
 template <int NR, int NC>
 __device__ __forceinline__ void gauss_jordan_lanes(double (&a)[NC], double* rowbuf, int lane, int& myk, double& mypiv) {
-  // (no __restrict__ on the shared-memory pointers of this kernel: they carry data BETWEEN lanes, and a restrict-qualified
-  //  pointer lets the compiler keep a value it loaded before a __syncwarp() -- the pivot row of two steps earlier)
+  static_assert(NC % 2 == 0 || NC + 1 <= kE2RowBuf, "row buffer too small");
   unsigned used = 0u;
   myk = -1;
   mypiv = 1.0;
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < NR; ++k) {
-    const double x = a[k];
+    const double x = a[0];
     const bool cand = lane < NR && !((used >> lane) & 1u) && (x == x);
     const int hi = cand ? (__double2hiint(x) & 0x7fffffff) : -1;
     const int mhi = __reduce_max_sync(FULL, hi);
@@ -481,7 +490,7 @@ __device__ __forceinline__ void gauss_jordan_lanes(double (&a)[NC], double* rowb
       myk = k;
       mypiv = x;
 #pragma unroll
-      for (int c = k & ~1; c < NC; c += 2) {
+      for (int c = 0; c < NC; c += 2) {
         if (c + 1 < NC)
           *reinterpret_cast<double2*>(pr + c) = make_double2(a[c], a[c + 1]);
         else
@@ -489,18 +498,19 @@ __device__ __forceinline__ void gauss_jordan_lanes(double (&a)[NC], double* rowb
       }
     }
     __syncwarp();
-    const double inv = 1.0 / pr[k];
+    const double inv = dls_recip(pr[0]);
     const double f = (lane == p || lane >= NR) ? 0.0 : x * inv;
 #pragma unroll
-    for (int c = (k + 1) & ~1; c < NC; c += 2) {
+    for (int c = 0; c < NC; c += 2) {  // aligned pairs of the pivot row; column c+1 lands in column c
       if (c + 1 < NC) {
         const double2 pv = *reinterpret_cast<const double2*>(pr + c);
-        if (c > k) a[c] = fma(-f, pv.x, a[c]);
-        a[c + 1] = fma(-f, pv.y, a[c + 1]);
+        if (c >= 2) a[c - 1] = fma(-f, pv.x, a[c]);
+        a[c] = fma(-f, pv.y, a[c + 1]);
       } else {
-        a[c] = fma(-f, pr[c], a[c]);
+        a[c - 1] = fma(-f, pr[c], a[c]);
       }
     }
+    a[NC - 1] = 0.0;
   }
 }
 
@@ -525,30 +535,26 @@ __global__ void dls_pack_rows_kernel() {
 // One template row per LANE: the lane walks the 20 terms of row `row`; terms on a same-degree non-reduced monomial or on
 // a reduced monomial are scattered into the lane's own shared-memory row `arow` ([D (n) | R (27)], zeroed here), the
 // lower-degree terms are folded into 27 register accumulators: racc[b] -= c * N[cd - 27][b], in ascending term order (the
-// order of the first version's ballot loop, so the sums round identically).  TRANSPOSED = the degree-7 block, which only
-// needs the right-hand side (its D goes to shared memory transposed, by the caller).
-template <int O0, int NCOLS_D, bool RHS_ONLY>
+// order of the first version's ballot loop, so the sums round identically).
+template <int O0, int NCOLS_D>
 __device__ __forceinline__ void lane_row_assemble(bool active, int row, const double* coef, const double* N, double* arow,
                                                   double (&racc)[kN]) {
-  const unsigned int* rw = g_dls_rows + (active ? row : 0) * 6;
-  unsigned int w[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) w[i] = __ldg(rw + i);
-  const int pi = (int)(w[5] & 0xffu);
+  const unsigned char* rb = reinterpret_cast<const unsigned char*>(g_dls_rows) + (active ? row : 0) * 24;
+  const int pi = (int)__ldg(rb + 20);
 #pragma unroll
   for (int b = 0; b < kN; ++b) racc[b] = 0.0;
   if (active) {
 #pragma unroll
     for (int c = 0; c < NCOLS_D + kN; ++c) arow[c] = 0.0;
   }
-#pragma unroll
+#pragma unroll 1
   for (int t = 0; t < 20; ++t) {
-    const int cd = (int)((w[t >> 2] >> (8 * (t & 3))) & 0xffu);
+    const int cd = (int)__ldg(rb + t);
     const double c = coef[pi * 20 + t];
     const bool lower = active && cd >= kN && (cd - kN) < O0;
     if (active) {
       if (cd < kN) arow[NCOLS_D + cd] = -c;
-      else if (!RHS_ONLY && cd - kN >= O0) arow[cd - kN - O0] = c;
+      else if (cd - kN >= O0) arow[cd - kN - O0] = c;
     }
     if (O0 > 0 && __any_sync(FULL, lower)) {  // warp-uniform
       const double* Nb = N + (lower ? (cd - kN) * kN : 0);
@@ -569,7 +575,7 @@ __device__ __forceinline__ void elim2_block(double* N, double* AUG, double* rowb
   double a[NC];
   {
     double racc[kN];
-    lane_row_assemble<o0, n, false>(active, o0 + lane, coef, N, arow, racc);
+    lane_row_assemble<o0, n>(active, o0 + lane, coef, N, arow, racc);
 #pragma unroll
     for (int c = 0; c < NC; ++c) a[c] = active ? arow[c] : 0.0;
 #pragma unroll
@@ -582,7 +588,7 @@ __device__ __forceinline__ void elim2_block(double* N, double* AUG, double* rowb
     const double inv = 1.0 / mypiv;
     double* Nr = N + (o0 + myk) * kN;
 #pragma unroll
-    for (int b = 0; b < kN; ++b) Nr[b] = a[n + b] * inv;
+    for (int b = 0; b < kN; ++b) Nr[b] = a[b] * inv;  // the solve shifted the right-hand sides down to a[0 .. 26]
   }
   __syncwarp();
 }
@@ -631,9 +637,9 @@ __global__ void __launch_bounds__(32 * kE2Warps, 2) dls_eliminate2_kernel(const 
     unsigned usedA = 0u, usedB = 0u;
     int mykA = -1, mykB = -1;
     double mypivA = 1.0, mypivB = 1.0;
-#pragma unroll
-    for (int k = 0; k < n; ++k) {
-      const double xa = aA[k], xb = aB[k];
+#pragma unroll 1
+    for (int k = 0; k < n; ++k) {  // same shifting loop as gauss_jordan_lanes, two register rows per lane
+      const double xa = aA[0], xb = aB[0];
       const bool candA = !((usedA >> lane) & 1u) && (xa == xa);
       const bool candB = lane < 4 && !((usedB >> lane) & 1u) && (xb == xb);
       const int hiA = candA ? (__double2hiint(xa) & 0x7fffffff) : -1;
@@ -658,7 +664,7 @@ __global__ void __launch_bounds__(32 * kE2Warps, 2) dls_eliminate2_kernel(const 
         mykA = k;
         mypivA = xa;
 #pragma unroll
-        for (int c = k & ~1; c < NC; c += 2) {
+        for (int c = 0; c < NC; c += 2) {
           if (c + 1 < NC) *reinterpret_cast<double2*>(pr + c) = make_double2(aA[c], aA[c + 1]);
           else pr[c] = aA[c];
         }
@@ -667,45 +673,47 @@ __global__ void __launch_bounds__(32 * kE2Warps, 2) dls_eliminate2_kernel(const 
         mykB = k;
         mypivB = xb;
 #pragma unroll
-        for (int c = k & ~1; c < NC; c += 2) {
+        for (int c = 0; c < NC; c += 2) {
           if (c + 1 < NC) *reinterpret_cast<double2*>(pr + c) = make_double2(aB[c], aB[c + 1]);
           else pr[c] = aB[c];
         }
       }
       __syncwarp();
-      const double inv = 1.0 / pr[k];
+      const double inv = dls_recip(pr[0]);
       const double fA = (lane == p) ? 0.0 : xa * inv;
       const double fB = (lane >= 4 || lane + 32 == p) ? 0.0 : xb * inv;
 #pragma unroll
-      for (int c = (k + 1) & ~1; c < NC; c += 2) {
+      for (int c = 0; c < NC; c += 2) {
         if (c + 1 < NC) {
           const double2 pv = *reinterpret_cast<const double2*>(pr + c);
-          if (c > k) {
-            aA[c] = fma(-fA, pv.x, aA[c]);
-            aB[c] = fma(-fB, pv.x, aB[c]);
+          if (c >= 2) {
+            aA[c - 1] = fma(-fA, pv.x, aA[c]);
+            aB[c - 1] = fma(-fB, pv.x, aB[c]);
           }
-          aA[c + 1] = fma(-fA, pv.y, aA[c + 1]);
-          aB[c + 1] = fma(-fB, pv.y, aB[c + 1]);
+          aA[c] = fma(-fA, pv.y, aA[c + 1]);
+          aB[c] = fma(-fB, pv.y, aB[c + 1]);
         } else {
-          aA[c] = fma(-fA, pr[c], aA[c]);
-          aB[c] = fma(-fB, pr[c], aB[c]);
+          aA[c - 1] = fma(-fA, pr[c], aA[c]);
+          aB[c - 1] = fma(-fB, pr[c], aB[c]);
         }
       }
+      aA[NC - 1] = 0.0;
+      aB[NC - 1] = 0.0;
     }
     // Y[r][j] = (row of unknown r)[36 + j] / pivot_r  -> shared (aliases the pivot-row buffers: wait for their readers)
     __syncwarp();
     double* Y = rowbuf;  // [36][3]
     {
       const double inv = 1.0 / mypivA;
-      Y[mykA * 3 + 0] = aA[36] * inv;
-      Y[mykA * 3 + 1] = aA[37] * inv;
-      Y[mykA * 3 + 2] = aA[38] * inv;
+      Y[mykA * 3 + 0] = aA[0] * inv;  // the solve shifted the three right-hand sides down to columns 0..2
+      Y[mykA * 3 + 1] = aA[1] * inv;
+      Y[mykA * 3 + 2] = aA[2] * inv;
     }
     if (lane < 4) {
       const double inv = 1.0 / mypivB;
-      Y[mykB * 3 + 0] = aB[36] * inv;
-      Y[mykB * 3 + 1] = aB[37] * inv;
-      Y[mykB * 3 + 2] = aB[38] * inv;
+      Y[mykB * 3 + 0] = aB[0] * inv;
+      Y[mykB * 3 + 1] = aB[1] * inv;
+      Y[mykB * 3 + 2] = aB[2] * inv;
     }
     __syncwarp();
     // right-hand side rows of the 36 degree-7 template rows, one per lane (two passes: rows 0..31, then 32..35), into
@@ -719,33 +727,30 @@ __global__ void __launch_bounds__(32 * kE2Warps, 2) dls_eliminate2_kernel(const 
       double racc[kN];
       double* rrow = Rsm + (active ? r : 0) * kN;
       {
-        const unsigned int* rw = g_dls_rows + (o0 + (active ? r : 0)) * 6;
-        unsigned int w[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) w[i] = __ldg(rw + i);
-        const int pi = (int)(w[5] & 0xffu);
+        const unsigned char* rb = reinterpret_cast<const unsigned char*>(g_dls_rows) + (o0 + (active ? r : 0)) * 24;
+        const int pi = (int)__ldg(rb + 20);
 #pragma unroll
         for (int b = 0; b < kN; ++b) racc[b] = 0.0;
-        double cs[20];
-        int cds[20];
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < 20; ++t) {
-          cds[t] = (int)((w[t >> 2] >> (8 * (t & 3))) & 0xffu);
-          cs[t] = coef[pi * 20 + t];
-          const bool lower = active && cds[t] >= kN && (cds[t] - kN) < o0;
+          const int cd = (int)__ldg(rb + t);
+          const double c = coef[pi * 20 + t];
+          const bool lower = active && cd >= kN && (cd - kN) < o0;
           if (__any_sync(FULL, lower)) {
-            const double* Nb = N + (lower ? (cds[t] - kN) * kN : 0);
+            const double* Nb = N + (lower ? (cd - kN) * kN : 0);
 #pragma unroll
             for (int b = 0; b < kN; ++b)
-              if (lower) racc[b] = fma(-cs[t], Nb[b], racc[b]);
+              if (lower) racc[b] = fma(-c, Nb[b], racc[b]);
           }
         }
         if (active) {
 #pragma unroll
           for (int b = 0; b < kN; ++b) rrow[b] = racc[b];
-#pragma unroll
-          for (int t = 0; t < 20; ++t)
-            if (cds[t] < kN) rrow[cds[t]] -= cs[t];  // a reduced monomial appears once per row
+#pragma unroll 1
+          for (int t = 0; t < 20; ++t) {
+            const int cd = (int)__ldg(rb + t);
+            if (cd < kN) rrow[cd] -= coef[pi * 20 + t];  // a reduced monomial appears once per row
+          }
         }
       }
     }
