@@ -639,7 +639,8 @@ constexpr int kTH = 16, kTW = 8;
 //   kSplitA only the A operand is split (blocks with 512 output channels: a second copy of their 32 KB weight stages
 //          does not fit beside the halo ring): A_hi B + A_lo B
 constexpr int kInQ = 1, kSplit = 2, kOutQ = 4, kSplitA = 8;
-constexpr float kQ15Scale = 32767.0f / 6.0f;          // x -> u
+constexpr int kSatPackMaxCin = 64;  // fused blocks up to this many input channels use q15_pack_sat (their bias is uploaded / 6)
+// q15: u = round(x * 32767 / 6)
 constexpr double kQ15DecodeW = 16384.0 * 6.0 / 32767.0;  // (f - 2) -> x
 
 template <int CIN, int COUT, int S, bool SPLIT = false, bool SPLIT_B = SPLIT, int EW = 8>
@@ -677,8 +678,9 @@ struct HaloCfg {
   static constexpr int kTotal = kAS * kABytes + kBS * kBBytes + kStageBytes + kHS * kHaloBytes + 1024 + 512;
 };
 
-// two fp32 accumulators (acc * scale + bias * scale already applied) -> two q15 values: clamp to [0, 32767], round to
-// nearest-even through the 2^23 magic add, keep the low 16 bits of each
+// two fp32 accumulators (acc * 32767 / 6 + bias * 32767 / 6 already applied by one FFMA2) -> two q15 values: clamp to
+// [0, 32767] on the ALU pipe, round to nearest-even through the 2^23 magic add, keep the low 16 bits of each.  Used where
+// the depthwise producers already fill the FMA pipe (CIN >= 128 and the stem).
 __device__ __forceinline__ uint32_t q15_pack(unsigned long long y) {
   float lo, hi;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(y));
@@ -688,6 +690,19 @@ __device__ __forceinline__ uint32_t q15_pack(unsigned long long y) {
   uint32_t a, b;
   asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(m));
   return __byte_perm(a, b, 0x5410);
+}
+constexpr float kQ15Scale = 32767.0f / 6.0f;  // x -> u
+
+// Two fp32 accumulators -> two q15 values in five instructions: FFMA.SAT maps ReLU6 onto [0, 1] (acc / 6 + bias / 6, the
+// saturation IS the clamp), a second FFMA scales by 32767 and adds 2^23 so that the round-to-nearest-even integer lands in
+// the low mantissa bits, one PRMT packs the two low halves.  Used by the blocks whose epilogue is the longer pole (CIN <= 64:
+// 32 -> 64 went 263 -> 239 us per 64 frames); it moves the clamp from the ALU pipe to the FMA pipe, which the depthwise
+// taps of the wider blocks already fill (128 -> 128 got 25 us SLOWER with it), so those keep q15_pack.  `bias` is pre-scaled
+// by 32767 / 6; the 1 / 32767 that maps it onto [0, 1] is folded into the first FFMA's constant.
+__device__ __forceinline__ uint32_t q15_pack_sat(float a0, float a1, float b0_6, float b1_6) {
+  const float t0 = __saturatef(fmaf(a0, 1.0f / 6.0f, b0_6)), t1 = __saturatef(fmaf(a1, 1.0f / 6.0f, b1_6));  // b*_6 = bias / 6
+  const float m0 = fmaf(t0, 32767.f, 8388608.f), m1 = fmaf(t1, 32767.f, 8388608.f);
+  return __byte_perm(__float_as_uint(m0), __float_as_uint(m1), 0x5410);
 }
 
 // eight q15 values (one 16-byte chunk) -> four packed float pairs f = 2 + u * 2^-14
@@ -868,26 +883,45 @@ __global__ void __launch_bounds__(halo_threads(EW), 1) dwpw_halo_kernel(const __
       for (int c = c_begin; c < c_begin + C_COUNT; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + acc * COUT + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-        if (lane == 0) bulk_wait_read0();  // the previous store has finished reading the staging rows
-        __syncwarp();
+        // Blocks whose epilogue is the longer pole (CIN <= 64: few K blocks per tile) convert all 32 channels of the lane's
+        // pixel BEFORE waiting for the staging rows of the previous store; the others stream (fewer live registers).
+        constexpr bool kLateWait = CIN <= kSatPackMaxCin;
+        uint4 o[kLateWait ? 4 : 1];
+        if (!kLateWait) {
+          if (lane == 0) bulk_wait_read0();  // the previous store has finished reading the staging rows
+          __syncwarp();
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           const ulonglong2 b0 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c + j));
           const ulonglong2 b1 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c + j + 4));
-          uint4 o;
-          if (OUTQ) {  // `bias` is pre-multiplied by 32767 / 6
+          uint4& oo = o[kLateWait ? (j >> 3) : 0];
+          if (OUTQ && CIN <= kSatPackMaxCin) {  // `bias` is pre-divided by 6
+            const float* bf0 = reinterpret_cast<const float*>(&b0);
+            const float* bf1 = reinterpret_cast<const float*>(&b1);
+            oo.x = q15_pack_sat(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]), bf0[0], bf0[1]);
+            oo.y = q15_pack_sat(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]), bf0[2], bf0[3]);
+            oo.z = q15_pack_sat(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]), bf1[0], bf1[1]);
+            oo.w = q15_pack_sat(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]), bf1[2], bf1[3]);
+          } else if (OUTQ) {  // `bias` is pre-multiplied by 32767 / 6
             const unsigned long long sc = pack_f32x2(kQ15Scale, kQ15Scale);
-            o.x = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1])), sc, b0.x));
-            o.y = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), sc, b0.y));
-            o.z = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])), sc, b1.x));
-            o.w = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])), sc, b1.y));
+            oo.x = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1])), sc, b0.x));
+            oo.y = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), sc, b0.y));
+            oo.z = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])), sc, b1.x));
+            oo.w = q15_pack(ffma2(pack_f32x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])), sc, b1.y));
           } else {
-            o.x = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1])), b0.x));
-            o.y = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), b0.y));
-            o.z = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])), b1.x));
-            o.w = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])), b1.y));
+            oo.x = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1])), b0.x));
+            oo.y = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), b0.y));
+            oo.z = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])), b1.x));
+            oo.w = relu6_pack_h2(fadd2(pack_f32x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])), b1.y));
           }
-          sts128(srow + (((j >> 3) ^ sw) << 4), o);
+          if (!kLateWait) sts128(srow + (((j >> 3) ^ sw) << 4), oo);
+        }
+        if (kLateWait) {
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sts128(srow + ((j ^ sw) << 4), o[kLateWait ? j : 0]);
         }
         fence_proxy_async();
         __syncwarp();
@@ -1644,7 +1678,7 @@ struct Block {
   bool runs_halo = false;    // this block is executed by dwpw_halo_kernel (decides the storage format of its input)
   float* dw_wq = nullptr;    // depthwise weights / bias with the q15 decode folded in
   float* dw_bq = nullptr;
-  float* pw_bq = nullptr;    // pointwise bias * 32767 / 6 (q15 epilogue)
+  float* pw_bq = nullptr;    // pointwise bias * 32767 / 6 (q15 epilogue), or bias / 6 where the epilogue uses q15_pack_sat
   __half* pw_whl = nullptr;  // [2][Cout][C]: fp16 hi rows, then lo rows
   CUtensorMap tmBs;          // map over pw_whl
 };
@@ -2266,7 +2300,7 @@ int cb_descriptor_create(cb_descriptor** out, const cb_netvlad_weights* w, int r
             }
             bq[ch] = (float)((double)w->dw_b[i][ch] - 2.0 * sum);
           }
-          for (int nn = 0; nn < b.Cout; ++nn) pbq[nn] = (float)((double)w->pw_b[i][nn] * (32767.0 / 6.0));
+          for (int nn = 0; nn < b.Cout; ++nn) pbq[nn] = (float)((double)w->pw_b[i][nn] * (b.C <= kSatPackMaxCin ? 1.0 / 6.0 : 32767.0 / 6.0));
           rc = upload_f32(&b.dw_wq, wq.data(), wq.size());
           if (!rc) rc = upload_f32(&b.dw_bq, bq.data(), bq.size());
           if (!rc) rc = upload_f32(&b.pw_bq, pbq.data(), pbq.size());
