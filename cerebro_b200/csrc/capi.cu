@@ -1,7 +1,45 @@
 // Library-wide pieces of the C ABI: version, error string, device selection.
 #include "common.cuh"
 
+#include <stdlib.h>
+#include <unistd.h>
+
 namespace cb {
+
+namespace {
+bool decide_blocking_sync() {
+  if (const char* e = getenv("CB_SYNC")) {
+    if (!strcmp(e, "block")) return true;
+    if (!strcmp(e, "spin")) return false;
+  }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess) {
+    cudaGetLastError();
+    n_dev = 1;
+  }
+  const long cores = sysconf(_SC_NPROCESSORS_ONLN);
+  return cores > 0 && cores < 4L * (n_dev > 0 ? n_dev : 1);
+}
+}  // namespace
+
+cudaError_t sync_stream(cudaStream_t st) {
+  static const bool blocking = decide_blocking_sync();
+  if (!blocking) return cudaStreamSynchronize(st);
+  // one interrupt-driven event per (thread, device); the waiting thread sleeps instead of spinning on a core it shares
+  constexpr int kMaxDev = 64;
+  static thread_local cudaEvent_t ev[kMaxDev] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDev) return cudaStreamSynchronize(st);
+  if (!ev[dev]) {
+    e = cudaEventCreateWithFlags(&ev[dev], cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  e = cudaEventRecord(ev[dev], st);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ev[dev]);
+}
 
 char* tls_error_buffer() {
   static thread_local char buf[512] = "";

@@ -222,7 +222,7 @@ extern "C" {
 int cb_features_destroy(cb_features* f) {
   if (!f) return CB_OK;
   cb::DeviceGuard g(f->device);
-  if (f->stream) cudaStreamSynchronize(f->stream);
+  if (f->stream) cb::sync_stream(f->stream);
   void* dev[] = {f->img,     f->pyr,    f->score,  f->blur,     f->dst,       f->hor,  f->row_count, f->row_off, f->level_count,
                  f->cand_xy, f->sel_xy, f->cand_sc, f->sel_level, f->resp,     f->n_sel, f->o_xy,      f->o_size,  f->o_angle,
                  f->o_octave, f->o_desc, f->map_x[0], f->map_x[1], f->map_x[2], f->map_x[3], f->map_y[0], f->map_y[1], f->map_y[2], f->map_y[3]};
@@ -335,7 +335,7 @@ int cb_features_set_remap(cb_features* f, int slot, const float* map_x, const fl
   if (!f->map_y[slot]) CB_CUDA(cudaMalloc((void**)&f->map_y[slot], bytes));
   CB_CUDA(cudaMemcpyAsync(f->map_x[slot], map_x, bytes, cudaMemcpyHostToDevice, f->stream));
   CB_CUDA(cudaMemcpyAsync(f->map_y[slot], map_y, bytes, cudaMemcpyHostToDevice, f->stream));
-  CB_CUDA(cudaStreamSynchronize(f->stream));
+  CB_CUDA(cb::sync_stream(f->stream));
   return CB_OK;
 }
 
@@ -359,7 +359,7 @@ int cb_features_remap(cb_features* f, int n, const uint8_t* src, int slot_a, int
     res = f->img;
   }
   CB_CUDA(cudaMemcpyAsync(dst, res, n * px, cudaMemcpyDeviceToHost, f->stream));
-  CB_CUDA(cudaStreamSynchronize(f->stream));
+  CB_CUDA(cb::sync_stream(f->stream));
   return CB_OK;
 }
 
@@ -397,7 +397,7 @@ int cb_features_orb(cb_features* f, int n, const uint8_t* images, int n_features
   blur_row_kernel<<<gpx, 256, 0, st>>>(f->pyr, pd, f->hor);
   CB_LAUNCH_CHECK();
   CB_CUDA(cudaMemcpyAsync(f->h_level_count, f->level_count, (size_t)n * kLevels * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-  CB_CUDA(cudaStreamSynchronize(st));
+  CB_CUDA(cb::sync_stream(st));
   for (int i = 0; i < n; ++i)
     for (int l = 0; l < kLevels; ++l) {
       const unsigned c = f->h_level_count[i * kLevels + l];
@@ -408,7 +408,7 @@ int cb_features_orb(cb_features* f, int n, const uint8_t* images, int n_features
     }
   blur_col_kernel<<<gpx, 256, 0, st>>>(f->hor, pd, f->blur);
   CB_LAUNCH_CHECK();
-  CB_CUDA(cudaStreamSynchronize(st));
+  CB_CUDA(cb::sync_stream(st));
   // ---- KeyPointsFilter::retainBest(2 x budget) on the FAST scores, per level (orb.cpp computeKeyPoints)
   std::vector<std::vector<int>> stage1_count((size_t)n, std::vector<int>(kLevels, 0));
   std::vector<orb::Rec> rec;
@@ -440,7 +440,7 @@ int cb_features_orb(cb_features* f, int n, const uint8_t* images, int n_features
     for (int i = 0; i < n; ++i)
       CB_CUDA(cudaMemcpyAsync(f->h_resp + (size_t)i * cap, f->resp + (size_t)i * cap, (size_t)f->h_n[i] * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
-  CB_CUDA(cudaStreamSynchronize(st));
+  CB_CUDA(cb::sync_stream(st));
   // ---- retainBest(budget) on the Harris responses, per level; the survivors, in this order, are the keypoints
   int max_fin = 0;
   for (int i = 0; i < n; ++i) {
@@ -483,7 +483,7 @@ int cb_features_orb(cb_features* f, int n, const uint8_t* images, int n_features
     }
   }
   CB_CUDA(cudaEventRecord(f->ev[1], st));
-  CB_CUDA(cudaStreamSynchronize(st));
+  CB_CUDA(cb::sync_stream(st));
   cudaEventElapsedTime(&f->last_orb_ms, f->ev[0], f->ev[1]);
   return CB_OK;
 }

@@ -757,7 +757,7 @@ int cb_frontend_create(cb_frontend** out, int max_pairs, int max_features, int d
 int cb_frontend_destroy(cb_frontend* f) {
   if (!f) return CB_OK;
   cb::DeviceGuard g(f->device);
-  if (f->stream) cudaStreamSynchronize(f->stream);
+  if (f->stream) cb::sync_stream(f->stream);
   void* ps[] = {f->d1, f->d2, f->kp1, f->kp2, f->off1, f->off2, f->best, f->train_idx, f->dist, f->mask, f->n_inl,
                 f->X,  f->uv, f->uvd, f->Y,   f->Kinv, f->count, f->img_a, f->img_b, f->e1, f->e2, f->pop1, f->pop2, f->tickets, f->sb_img, f->sb_pre, f->sb_hsad, f->sb_htext,
                 f->sb_disp, f->sb_3d};
@@ -836,7 +836,7 @@ int cb_frontend_match_gms(cb_frontend* f, int n_pairs, const int32_t* off1, cons
     CB_CUDA(cudaMemcpyAsync(inlier_mask, f->mask, (size_t)tot1, cudaMemcpyDeviceToHost, st));
   }
   CB_CUDA(cudaMemcpyAsync(n_inliers, f->n_inl, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
-  CB_CUDA(cudaStreamSynchronize(st));
+  CB_CUDA(cb::sync_stream(st));
   if (tot1) cudaEventElapsedTime(&f->last_match_ms, f->ev[0], f->ev[1]);
   f->n_pairs = n_pairs;
   f->total1 = tot1;
@@ -894,7 +894,7 @@ int cb_frontend_stereo_bm(cb_frontend* f, int n, const uint8_t* left, const uint
     CB_LAUNCH_CHECK();
     CB_CUDA(cudaEventRecord(f->ev[1], st));
     CB_CUDA(cudaMemcpyAsync(disparity + (size_t)c0 * per, f->sb_disp, per * sizeof(int16_t) * nc, cudaMemcpyDeviceToHost, st));
-    CB_CUDA(cudaStreamSynchronize(st));
+    CB_CUDA(cb::sync_stream(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, f->ev[0], f->ev[1]);
     total_ms += ms;
@@ -919,7 +919,7 @@ int cb_frontend_disparity_to_3d(cb_frontend* f, int n, const int16_t* disparity,
   sbm_to3d_kernel<<<(unsigned)((per * n + 255) / 256), 256, 0, st>>>(f->sb_disp, n, rows, cols, Q03, Q13, Q23, Q32, Q33, f->sb_3d);
   CB_LAUNCH_CHECK();
   CB_CUDA(cudaMemcpyAsync(out3d, f->sb_3d, per * 3 * sizeof(float) * n, cudaMemcpyDeviceToHost, st));
-  CB_CUDA(cudaStreamSynchronize(st));
+  CB_CUDA(cb::sync_stream(st));
   return CB_OK;
 }
 
@@ -956,7 +956,7 @@ int cb_frontend_collect(cb_frontend* f, int mode, const float* img3d_a, const fl
       CB_CUDA(cudaMemcpyAsync(Y, f->Y, n * 24, cudaMemcpyDeviceToHost, st));
     }
   }
-  CB_CUDA(cudaStreamSynchronize(st));
+  CB_CUDA(cb::sync_stream(st));
   return CB_OK;
 }
 

@@ -2474,7 +2474,7 @@ int cb_descriptor_create_v2(cb_descriptor** out, const cb_netvlad_v2_weights* w,
 int cb_descriptor_destroy(cb_descriptor* d) {
   if (!d) return CB_OK;
   cb::DeviceGuard g(d->device);
-  if (d->stream) cudaStreamSynchronize(d->stream);
+  if (d->stream) cb::sync_stream(d->stream);
   for (IrBlock& b : d->ir) {
     void* ps[] = {b.expand.w, b.expand.b, b.project.w, b.project.b, b.dw_w, b.dw_b};
     for (void* q : ps)
@@ -2586,7 +2586,7 @@ int cb_descriptor_compute(cb_descriptor* d, int n, const uint8_t* images, int64_
   int rc = compute_to_device(d, n, images, row_stride_bytes);
   if (rc) return rc;
   CB_CUDA(cudaMemcpyAsync(out, d->out_dev, (size_t)n * d->K * d->D * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
-  CB_CUDA(cudaStreamSynchronize(d->stream));
+  CB_CUDA(cb::sync_stream(d->stream));
   return CB_OK;
 }
 
@@ -2601,7 +2601,7 @@ int cb_descriptor_compute_f64(cb_descriptor* d, int n, const uint8_t* images, in
   // fp32 crosses the bus (half the bytes of the service's float64[]), the widening of server.py:648 / Cerebro.cpp:268-271
   // happens while writing the caller's buffer
   CB_CUDA(cudaMemcpyAsync(d->out_host, d->out_dev, ne * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
-  CB_CUDA(cudaStreamSynchronize(d->stream));
+  CB_CUDA(cb::sync_stream(d->stream));
   for (size_t i = 0; i < ne; ++i) out[i] = (double)d->out_host[i];
   return CB_OK;
 }
@@ -2615,7 +2615,7 @@ int64_t cb_descriptor_get_activation(cb_descriptor* d, int layer, float* out, in
   if ((int64_t)ne > max_floats) return cb::fail(CB_EINVAL, "buffer too small: need %zu floats", ne);
   cb::DeviceGuard g(d->device);
   std::vector<__half> tmp(ne);
-  CB_CUDA(cudaStreamSynchronize(d->stream));
+  CB_CUDA(cb::sync_stream(d->stream));
   CB_CUDA(cudaMemcpy(tmp.data(), d->act[d->last_buf], ne * sizeof(__half), cudaMemcpyDeviceToHost));
   const bool q = (size_t)layer < d->layer_q.size() && d->layer_q[layer];  // q15 storage between halo blocks
   if (q) {

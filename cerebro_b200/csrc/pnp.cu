@@ -1680,7 +1680,7 @@ int cb_pnp_create(cb_pnp** out, int max_candidates, int max_points_total, int ma
 int cb_pnp_destroy(cb_pnp* p) {
   if (!p) return CB_OK;
   cb::DeviceGuard g(p->device);
-  if (p->stream) cudaStreamSynchronize(p->stream);
+  if (p->stream) cb::sync_stream(p->stream);
   void* ptrs[] = {p->offsets, p->X, p->uv, p->samples, p->cost, p->ninl, p->model, p->idx, p->status,
                   p->coef, p->T, p->S, p->cmodel, p->out_T, p->out_conf, p->out_i};
   for (void* q : ptrs)
@@ -1763,7 +1763,7 @@ int cb_pnp_solve_batch(cb_pnp* p, int n_cand, const int32_t* offsets, const doub
     CB_CUDA(cudaMemcpyAsync(n_inliers, oi + p->max_cand, (size_t)n_cand * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (best_hyp)
     CB_CUDA(cudaMemcpyAsync(best_hyp, oi + 2 * p->max_cand, (size_t)n_cand * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CB_CUDA(cudaStreamSynchronize(st));
+  CB_CUDA(cb::sync_stream(st));
   return CB_OK;
 }
 
@@ -1854,7 +1854,7 @@ int cb_pnp_icp_batch(cb_pnp* p, int n_cand, const int32_t* offsets, const double
   if (num_iterations) CB_CUDA(cudaMemcpyAsync(num_iterations, oi, (size_t)n_cand * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (n_inliers) CB_CUDA(cudaMemcpyAsync(n_inliers, oi + p->max_cand, (size_t)n_cand * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (best_hyp) CB_CUDA(cudaMemcpyAsync(best_hyp, oi + 2 * p->max_cand, (size_t)n_cand * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CB_CUDA(cudaStreamSynchronize(st));
+  CB_CUDA(cb::sync_stream(st));
   return CB_OK;
 }
 
@@ -1890,7 +1890,7 @@ int cb_pnp_dls_minimal(cb_pnp* p, int n_sets, int m, const double* X, const doub
   cudaMemcpyAsync(p->samples, h_samples, (size_t)n_sets * m * sizeof(int), cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(p->X, X, (size_t)total * 3 * sizeof(double), cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(p->uv, uv, (size_t)total * 2 * sizeof(double), cudaMemcpyHostToDevice, st);
-  cudaStreamSynchronize(st);
+  cb::sync_stream(st);
   delete[] h_off;
   delete[] h_samples;
   if (total < 20) return cb::fail(CB_EINVAL, "need at least 2 sets");
@@ -1926,7 +1926,7 @@ int cb_pnp_dls_minimal(cb_pnp* p, int n_sets, int m, const double* X, const doub
   double* hm = new double[(size_t)n_sets * kMaxSol * 12];
   cudaError_t e1 = cudaMemcpyAsync(hm, p->cmodel, (size_t)n_sets * kMaxSol * 12 * sizeof(double), cudaMemcpyDeviceToHost, st);
   cudaError_t e2 = cudaMemcpyAsync(n_solutions, p->status, (size_t)n_sets * sizeof(int), cudaMemcpyDeviceToHost, st);
-  cudaError_t e3 = cudaStreamSynchronize(st);
+  cudaError_t e3 = cb::sync_stream(st);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
     delete[] hm;
     return cb::fail(CB_ECUDA, "dls_minimal failed: %s", cudaGetErrorString(e3 != cudaSuccess ? e3 : (e1 != cudaSuccess ? e1 : e2)));
@@ -1947,7 +1947,7 @@ int64_t cb_pnp_debug_read(cb_pnp* p, int what, int n_sets, double* out, int64_t 
   const int64_t per = what == 0 ? kN * kN : 60;
   const int64_t n = per * n_sets;
   if (n > max_doubles) return cb::fail(CB_EINVAL, "buffer too small: %lld doubles needed", (long long)n);
-  CB_CUDA(cudaStreamSynchronize(p->stream));
+  CB_CUDA(cb::sync_stream(p->stream));
   CB_CUDA(cudaMemcpy(out, what == 0 ? p->S : p->coef, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
   return n;
 }

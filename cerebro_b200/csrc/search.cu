@@ -1576,7 +1576,7 @@ int cb_index_create(cb_index** out, int d, int64_t capacity, int device, int ran
 int cb_index_destroy(cb_index* ix) {
   if (!ix) return CB_OK;
   cb::DeviceGuard g(ix->device);
-  cudaStreamSynchronize(ix->stream);
+  cb::sync_stream(ix->stream);
   cudaFree(ix->rows);
   cudaFree(ix->partial);
   cudaFree(ix->chunk_k);
@@ -1644,7 +1644,7 @@ int cb_index_add(cb_index* ix, int64_t n, const float* x) {
   cb::DeviceGuard g(ix->device);
   int rc = add_impl(ix, n, x, cudaMemcpyHostToDevice, ix->stream);
   if (rc) return rc;
-  CB_CUDA(cudaStreamSynchronize(ix->stream));
+  CB_CUDA(cb::sync_stream(ix->stream));
   return CB_OK;
 }
 
@@ -1669,7 +1669,7 @@ int cb_index_add_f64(cb_index* ix, int64_t n, const double* x) {
   CB_LAUNCH_CHECK();
   rc = add_impl(ix, n, f32, cudaMemcpyDeviceToDevice, ix->stream);
   if (rc) return rc;
-  CB_CUDA(cudaStreamSynchronize(ix->stream));
+  CB_CUDA(cb::sync_stream(ix->stream));
   return CB_OK;
 }
 
@@ -1753,7 +1753,7 @@ int cb_index_search(cb_index* ix, int nq, const float* xq, int k, int64_t limit_
   double* hs = new double[oe];
   cudaError_t e1 = cudaMemcpyAsync(hs, ix->out_s, oe * sizeof(double), cudaMemcpyDeviceToHost, ix->stream);
   cudaError_t e2 = cudaMemcpyAsync(labels, ix->out_l, oe * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream);
-  cudaError_t e3 = cudaStreamSynchronize(ix->stream);
+  cudaError_t e3 = cb::sync_stream(ix->stream);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
     delete[] hs;
     cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
@@ -1850,7 +1850,7 @@ int cb_index_search_sharded(cb_index* ix, int nq_local, const float* xq_local, i
   std::vector<double> hs(oe);
   CB_CUDA(cudaMemcpyAsync(hs.data(), ix->out_s, oe * sizeof(double), cudaMemcpyDeviceToHost, ix->stream));
   CB_CUDA(cudaMemcpyAsync(labels, ix->out_l, oe * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
-  CB_CUDA(cudaStreamSynchronize(ix->stream));
+  CB_CUDA(cb::sync_stream(ix->stream));
   for (size_t i = 0; i < oe; ++i) {
     if (distances) distances[i] = (float)hs[i];
     if (scores_f64) scores_f64[i] = hs[i];
@@ -1886,7 +1886,7 @@ int cb_index_naive_candidate(cb_index* ix, int64_t l, int lag, int locality_thre
   long long hl[3];
   CB_CUDA(cudaMemcpyAsync(hs, ix->out_s, sizeof(hs), cudaMemcpyDeviceToHost, ix->stream));
   CB_CUDA(cudaMemcpyAsync(hl, ix->out_l, sizeof(hl), cudaMemcpyDeviceToHost, ix->stream));
-  CB_CUDA(cudaStreamSynchronize(ix->stream));
+  CB_CUDA(cb::sync_stream(ix->stream));
   const long long a = hl[2], am = hl[1], amm = hl[0];
   if (argmax3) {
     argmax3[0] = a;
@@ -1910,7 +1910,7 @@ int cb_index_get_rows(cb_index* ix, int64_t first_local, int64_t n, float* out) 
   }
   CB_CUDA(cudaMemcpyAsync(out, ix->rows + (size_t)first_local * ix->d, (size_t)n * ix->d * sizeof(float),
                           cudaMemcpyDeviceToHost, ix->stream));
-  CB_CUDA(cudaStreamSynchronize(ix->stream));
+  CB_CUDA(cb::sync_stream(ix->stream));
   return CB_OK;
 }
 

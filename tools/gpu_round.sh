@@ -35,3 +35,24 @@ if [ -f $out/${tag}_prof.ncu-rep ]; then
   sz=$(stat -c %s $out/${tag}_prof.ncu-rep); if [ "$sz" -gt 40000000 ]; then rm $out/${tag}_prof.ncu-rep; fi
 fi
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.draw --format=csv > $out/${tag}_gpu.txt
+
+# the other two single-GPU configurations of BASELINE.json and the component micro-benchmarks
+timeout 300 python bench.py --workload config2 --no-cpu-baseline > $out/${tag}_bench_config2.json 2> $out/${tag}_bench_config2.err
+echo "config2 exit $?"
+timeout 400 python bench.py --workload pnp5 --steps 3 --warmup 1 > $out/${tag}_bench_pnp5.json 2> $out/${tag}_bench_pnp5.err
+echo "pnp5 exit $?"
+timeout 200 python tools/bench_pnp.py > $out/${tag}_pnp.jsonl 2>&1
+timeout 200 python tools/bench_features.py > $out/${tag}_features.json 2>/dev/null
+timeout 200 python tools/bench_frontend.py > $out/${tag}_frontend.json 2>/dev/null
+timeout 200 python tools/bench_desc.py 64 --layers > $out/${tag}_desc_layers.json 2>/dev/null
+# front-end kernels under ncu --set full (remap, ORB, StereoBM, matcher, GMS)
+FK='regex:sbm_|fast_kernel|describe_kernel|harris_kernel|blur_|resize_kernel|compact_kernel|scan_rows|remap_kernel|hamming|gms_|expand_bits|unpack_matches'
+timeout 400 ncu --set full --clock-control none -k "$FK" -c 45 -f -o $out/${tag}_fe_prof python tools/bench_features.py > /dev/null 2>&1
+timeout 300 ncu --set full --clock-control none -k "$FK" -c 12 -f -o $out/${tag}_fe2_prof python tools/bench_frontend.py > /dev/null 2>&1
+for f in fe fe2; do
+  if [ -f $out/${tag}_${f}_prof.ncu-rep ]; then
+    ncu -i $out/${tag}_${f}_prof.ncu-rep --page raw --csv > $out/${tag}_${f}_prof_raw.csv 2>/dev/null
+    rm $out/${tag}_${f}_prof.ncu-rep
+  fi
+done
+echo "front-end ncu done"
