@@ -514,15 +514,17 @@ def main():
     from concurrent.futures import ThreadPoolExecutor
 
     pool = ThreadPoolExecutor(max_workers=1)
-    desc_pool = ThreadPoolExecutor(max_workers=2)
+    desc_pool = ThreadPoolExecutor(max_workers=3)
     Xs = [X_host.numpy()[i * N_CORR : (i + 1) * N_CORR] for i in range(B)]
     uvs = [uv_host.numpy()[i * N_CORR : (i + 1) * N_CORR] for i in range(B)]
-    # Two descriptor handles (same weights), each driven by one call at a time: batch i+1 is uploaded on one handle's copy
-    # stream while batch i runs its forward pass on the other's -- every handle owns its streams and device buffers.
+    # Three descriptor handles (same weights), each driven by one call at a time: batches i+1 and i+2 are uploaded on their
+    # handles' copy streams while batch i runs its forward pass -- every handle owns its streams and device buffers.  (With
+    # two handles the upload of batch i+2 started only after the search of batch i had returned: ~0.5 ms of idle GPU per step.)
     from cerebro_b200.descriptor import NetvladDescriptor
 
-    descs = [pipe.desc, NetvladDescriptor(net, ROWS, COLS, CHNLS, max_batch=B, device=local_rank)]
-    d_out = [torch.empty((B, DIM), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+    ND = 3  # descriptor handles in flight: the upload of batch i+2 must not wait for the search of batch i
+    descs = [pipe.desc] + [NetvladDescriptor(net, ROWS, COLS, CHNLS, max_batch=B, device=local_rank) for _ in range(ND - 1)]
+    d_out = [torch.empty((B, DIM), dtype=torch.float32).pin_memory().numpy() for _ in range(ND + 1)]
 
     def run_host(n_steps):
         """n_steps keyframe batches through the host C-ABI calls, organised like the reference node: descriptor
@@ -533,23 +535,31 @@ def main():
         all-gathers on the handle's stream, merged lists down): no torch tensor, no extra device round trip."""
         from collections import deque
 
-        futs = deque(desc_pool.submit(descs[j % 2].compute, imgs_host.numpy(), d_out[j % 2]) for j in range(min(2, n_steps)))
+        futs = deque(desc_pool.submit(descs[j % ND].compute, imgs_host.numpy(), d_out[j % (ND + 1)]) for j in range(min(ND, n_steps)))
+        pnp_futs = deque()  # the verifier thread always has the next batch queued (its results are read one step later)
         res = None
+        dbg = os.environ.get("BENCH_E2E_DEBUG", "")  # diagnosis only: drop one stage to see which dependency leaves the GPU idle
         for i in range(n_steps):
-            fut_p = pool.submit(pipe.pnp.solve, Xs, uvs, pipe.params)
+            if "nopnp" not in dbg:
+                pnp_futs.append(pool.submit(pipe.pnp.solve, Xs, uvs, pipe.params))
             d = futs.popleft().result()
-            if world > 1:
+            if i + ND < n_steps:  # handle i % ND is free again; its next batch goes to another output buffer than the one search(i) reads
+                futs.append(desc_pool.submit(descs[i % ND].compute, imgs_host.numpy(), d_out[(i + ND) % (ND + 1)]))
+            if "nosearch" in dbg:
+                res = None
+            elif world > 1:
                 res = pipe.index.search_sharded(d, 5)
             else:
                 res = pipe.index.search(d, 5)
-            if i + 2 < n_steps:  # handle i % 2 and its output buffer are free again: batch i has been searched
-                futs.append(desc_pool.submit(descs[i % 2].compute, imgs_host.numpy(), d_out[i % 2]))
-            res = (res, fut_p.result())
+            if len(pnp_futs) > 1:
+                res = (res, pnp_futs.popleft().result())
+        while pnp_futs:  # every batch's verification finishes inside the timed region
+            res = (res, pnp_futs.popleft().result())
         return res
 
-    run_host(2)
+    run_host(4)
     barrier()
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(4 * args.steps, 80))  # its own timed region: long enough (0.25 s) to average over the host threads' jitter
     t0 = time.perf_counter()
     run_host(e2e_steps)
     barrier()

@@ -1563,7 +1563,18 @@ int cb_index_create(cb_index** out, int d, int64_t capacity, int device, int ran
     delete ix;
     return cb::fail(CB_ENOMEM, "cudaMalloc of %lld x %d fp32 rows failed: %s", (long long)capacity, d, cudaGetErrorString(e));
   }
-  e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+  {
+    // The search sits between the descriptor and the verifier in the node's pipeline and -- sharded -- inside a collective
+    // that every rank waits on, while the other handles keep the GPU busy with 100-250 us persistent kernels.  Its stream
+    // gets the highest priority so that its kernels are scheduled at the next kernel boundary of the other streams instead
+    // of behind everything already queued (CB_INDEX_PRIORITY=0 keeps the default priority).
+    int lo = 0, hi = 0;
+    const char* pe = getenv("CB_INDEX_PRIORITY");
+    if ((!pe || pe[0] != '0') && cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess && hi < lo)
+      e = cudaStreamCreateWithPriority(&ix->stream, cudaStreamNonBlocking, hi);
+    else
+      e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+  }
   if (e != cudaSuccess) {
     cudaFree(ix->rows);
     delete ix;
