@@ -26,5 +26,9 @@ def cuda_device():
     import torch
 
     if not torch.cuda.is_available():
-        pytest.fail("GPU test selected but no CUDA device is visible")
+        # a plain `pytest` on a CPU-only box skips the GPU tests; the GPU visit (tools/gpu_round.sh) sets CB_REQUIRE_GPU=1 so that
+        # a box without a usable device fails loudly instead of reporting a green, empty run
+        if os.environ.get("CB_REQUIRE_GPU") == "1":
+            pytest.fail("GPU test selected but no CUDA device is visible")
+        pytest.skip("no CUDA device visible")
     return 0

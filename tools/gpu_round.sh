@@ -6,6 +6,7 @@ tag=${1:-r1}
 out=gpurun_out
 mkdir -p $out
 export PYTHONUNBUFFERED=1
+export CB_REQUIRE_GPU=1
 K='regex:conv1|dwpw|dw_kernel|pw_gemm|vlad|scores|topk|finalize|merge_lists|split_|dls_|pnp_|icp_|copy_models|hamming|gms_|collect_'
 
 timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1
