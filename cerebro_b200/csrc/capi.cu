@@ -18,7 +18,7 @@ bool decide_blocking_sync() {
     n_dev = 1;
   }
   const long cores = sysconf(_SC_NPROCESSORS_ONLN);
-  return cores > 0 && cores < 4L * (n_dev > 0 ? n_dev : 1);
+  return cores > 0 && cores < 8L * (n_dev > 0 ? n_dev : 1);
 }
 }  // namespace
 

@@ -55,10 +55,10 @@ struct DeviceGuard {
 constexpr unsigned FULL = 0xffffffffu;
 
 // Host-side wait for a stream, used by every blocking (host-pointer) entry point.  cudaStreamSynchronize spins, which is the
-// lowest latency when the calling thread has a core of its own -- and starves the node when it has not: the bench at 8
-// ranks on a 16-core box runs ~5 host threads per rank (descriptor x2, search, verifier, main) on 2 cores, and its e2e step
-// took 6.1 ms against 3.5 ms at one rank.  Policy (CB_SYNC=spin|block overrides): block on an interrupt-driven event when
-// the machine has fewer than 4 online cores per visible GPU, spin otherwise.
+// lowest latency when the calling thread has a core of its own (3-query rule 0.64 ms against 1.02 ms) -- and wastes the cores
+// when it has not: the bench at 8 ranks on a 32-core box runs six host threads per rank (descriptor x3, search, verifier,
+// main) on 4 cores; measured there, sleeping gave 89 k keyframes/s e2e against 86 k spinning.  Policy (CB_SYNC=spin|block
+// overrides): sleep on an interrupt-driven event when the machine has fewer than 8 online cores per visible GPU, spin otherwise.
 cudaError_t sync_stream(cudaStream_t st);  // defined in capi.cu
 
 }  // namespace cb
