@@ -510,7 +510,7 @@ collect_kernel(const float* __restrict__ kp1, const float* __restrict__ kp2, con
 //                          decision (first minimum, texture / uniqueness tests, parabola fit, ROI)
 //   sbm_to3d_kernel      : thread per pixel
 // ---------------------------------------------------------------------------------------------
-constexpr int kSbmSeg = 32;     // output columns per horizontal-pass thread
+constexpr int kSbmSeg = 64;     // output columns per horizontal-pass thread (21 window columns are summed before the first one: 64 instead of 32 measured 517 -> 472 us per 8 pairs)
 constexpr int kSbmStripe = 60;  // rows per vertical-pass block
 
 __global__ void sbm_fill_kernel(int16_t* __restrict__ disp, size_t n, int16_t v) {
