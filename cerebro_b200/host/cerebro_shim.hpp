@@ -8,16 +8,20 @@
 //   Cerebro::descrip_N__dot__descrip_0_N  src/Cerebro.cpp:903-1103  -> cb_index_add_f64 + cb_index_naive_candidate
 //   Cerebro::loopcandiate_consumer_thread src/Cerebro.cpp:1185-1281 -> cb_pnp_solve_batch
 //   StaticTheiaPoseCompute::PNP           src/DlsPnpWithRansac.h:169-179
+//   ProcessedLoopCandidate::makeLoopEdgeMsgWithConsistencyCheck  src/ProcessedLoopCandidate.cpp:40-125 (host logic, no device call)
+//   PoseManipUtils::{R2ypr, eigenmat_to_rawyprt, eigenmat_to_geometry_msgs_Pose}  src/utils/PoseManipUtils.cpp:31-43, 148-163
 //
 // ros::Time, DataNode and DataManager are reduced to what those bodies touch (stamp, keyframe flag,
 // tracked-feature count, image, VectorXd descriptor as std::vector<double>).  No Eigen/OpenCV/ROS needed.
 #pragma once
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <functional>
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <sstream>
@@ -99,6 +103,177 @@ class StaticTheiaPoseCompute {  // src/DlsPnpWithRansac.h:169-179
     pnp__msg += ss.str();
     return conf;
   }
+};
+
+// ---- 4x4 pose algebra (row-major double[16]); stands in for the Eigen calls of the consistency check
+struct Matrix4d {
+  double m[16];
+  double& operator()(int r, int c) { return m[4 * r + c]; }
+  double operator()(int r, int c) const { return m[4 * r + c]; }
+  static Matrix4d Identity() {
+    Matrix4d I{};
+    for (int i = 0; i < 4; ++i) I(i, i) = 1.0;
+    return I;
+  }
+  static Matrix4d from(const double* p) {
+    Matrix4d M;
+    for (int i = 0; i < 16; ++i) M.m[i] = p[i];
+    return M;
+  }
+  Matrix4d operator*(const Matrix4d& o) const {
+    Matrix4d R{};
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        double s = 0.0;
+        for (int k = 0; k < 4; ++k) s += (*this)(i, k) * o(k, j);
+        R(i, j) = s;
+      }
+    return R;
+  }
+  // general inverse (Gauss-Jordan, partial pivoting), as Eigen's Matrix4d::inverse() is: the reference does not assume
+  // that the solver returned a rigid transform
+  Matrix4d inverse() const {
+    double a[4][8];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        a[i][j] = (*this)(i, j);
+        a[i][4 + j] = i == j ? 1.0 : 0.0;
+      }
+    for (int k = 0; k < 4; ++k) {
+      int p = k;
+      for (int i = k + 1; i < 4; ++i)
+        if (std::fabs(a[i][k]) > std::fabs(a[p][k])) p = i;
+      if (p != k)
+        for (int j = 0; j < 8; ++j) std::swap(a[k][j], a[p][j]);
+      const double inv = 1.0 / a[k][k];
+      for (int j = 0; j < 8; ++j) a[k][j] *= inv;
+      for (int i = 0; i < 4; ++i)
+        if (i != k) {
+          const double f = a[i][k];
+          for (int j = 0; j < 8; ++j) a[i][j] -= f * a[k][j];
+        }
+    }
+    Matrix4d R;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) R(i, j) = a[i][4 + j];
+    return R;
+  }
+  bool hasNaN() const {
+    for (double v : m)
+      if (v != v) return true;
+    return false;
+  }
+};
+
+struct PoseManipUtils {
+  // yaw, pitch, roll in DEGREES of R = Rz Ry Rx (src/utils/PoseManipUtils.cpp:148-163)
+  static void R2ypr(const Matrix4d& T, double ypr[3]) {
+    const double n0 = T(0, 0), n1 = T(1, 0), n2 = T(2, 0), o0 = T(0, 1), o1 = T(1, 1), a0 = T(0, 2), a1 = T(1, 2);
+    const double y = std::atan2(n1, n0);
+    const double p = std::atan2(-n2, n0 * std::cos(y) + n1 * std::sin(y));
+    const double r = std::atan2(a0 * std::sin(y) - a1 * std::cos(y), -o0 * std::sin(y) + o1 * std::cos(y));
+    ypr[0] = y / M_PI * 180.0, ypr[1] = p / M_PI * 180.0, ypr[2] = r / M_PI * 180.0;
+  }
+  static void eigenmat_to_rawyprt(const Matrix4d& T, double ypr[3], double t[3]) {
+    R2ypr(T, ypr);
+    t[0] = T(0, 3), t[1] = T(1, 3), t[2] = T(2, 3);
+  }
+  // position + orientation (x, y, z, w) = Eigen::Quaterniond(R): the branch on the trace and the largest diagonal element
+  // that Eigen's rotation-matrix constructor uses (src/utils/PoseManipUtils.cpp:31-43)
+  static void eigenmat_to_geometry_msgs_Pose(const Matrix4d& T, double position[3], double orientation_xyzw[4]) {
+    position[0] = T(0, 3), position[1] = T(1, 3), position[2] = T(2, 3);
+    double q[4];  // x y z w
+    double t = T(0, 0) + T(1, 1) + T(2, 2);
+    if (t > 0.0) {
+      t = std::sqrt(t + 1.0);
+      q[3] = 0.5 * t;
+      t = 0.5 / t;
+      q[0] = (T(2, 1) - T(1, 2)) * t;
+      q[1] = (T(0, 2) - T(2, 0)) * t;
+      q[2] = (T(1, 0) - T(0, 1)) * t;
+    } else {
+      int i = 0;
+      if (T(1, 1) > T(0, 0)) i = 1;
+      if (T(2, 2) > T(i, i)) i = 2;
+      const int j = (i + 1) % 3, k = (j + 1) % 3;
+      t = std::sqrt(T(i, i) - T(j, j) - T(k, k) + 1.0);
+      q[i] = 0.5 * t;
+      t = 0.5 / t;
+      q[3] = (T(k, j) - T(j, k)) * t;
+      q[j] = (T(j, i) + T(i, j)) * t;
+      q[k] = (T(k, i) + T(i, k)) * t;
+    }
+    for (int i = 0; i < 4; ++i) orientation_xyzw[i] = q[i];
+  }
+  static double linf3(const double v[3]) {
+    const double a = std::fabs(v[0]), b = std::fabs(v[1]), c = std::fabs(v[2]);
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
+  }
+};
+
+struct LoopEdge {  // msg/LoopEdge.msg:1-5
+  Time timestamp0, timestamp1;
+  double position[3] = {0, 0, 0};
+  double orientation_xyzw[4] = {0, 0, 0, 1};  // geometry_msgs/Pose pose_1T0
+  float weight = 0.f;
+  std::string description;
+};
+
+// The slice of src/ProcessedLoopCandidate.{h,cpp} that consumes the verifier's three poses (Option A PnP, Option B PnP with
+// the roles swapped and inverted, Option C 3D-3D alignment) and decides whether a LoopEdge is published.
+class ProcessedLoopCandidate {
+ public:
+  ProcessedLoopCandidate(int idx_from_raw_candidates_list_, Time t_1_, Time t_2_, int idx_1 = -1, int idx_2 = -1)
+      : idx_from_raw_candidates_list(idx_from_raw_candidates_list_), t_1(t_1_), t_2(t_2_), idx_from_datamanager_1(idx_1),
+        idx_from_datamanager_2(idx_2) {}
+
+  bool makeLoopEdgeMsg(LoopEdge& msg) const {  // ProcessedLoopCandidate.cpp:16-36
+    if (!isSet_3d2d__2T1) return false;
+    msg.timestamp0 = t_1;
+    msg.timestamp1 = t_2;
+    PoseManipUtils::eigenmat_to_geometry_msgs_Pose(_3d2d__2T1, msg.position, msg.orientation_xyzw);
+    msg.weight = _3d2d__2T1__ransac_confidence;
+    msg.description = std::to_string(idx_from_datamanager_1) + "<=>" + std::to_string(idx_from_datamanager_2);
+    msg.description += "    this pose is: " + std::to_string(idx_from_datamanager_2) + "_T_" + std::to_string(idx_from_datamanager_1);
+    return true;
+  }
+
+  bool makeLoopEdgeMsgWithConsistencyCheck(LoopEdge& msg) {  // ProcessedLoopCandidate.cpp:40-125
+    if (opX_b_T_a.size() != 3) return false;
+    // :49-56 ros::Duration is floor-normalised (0 <= nsec < 1e9), so diff.sec = floor(diff)
+    const int64_t dn = t_1.nsec - t_2.nsec;
+    int64_t dsec = dn / 1000000000LL;
+    if (dn % 1000000000LL < 0) --dsec;
+    if ((dsec < 0 ? -dsec : dsec) < 10) return false;
+    const Matrix4d &op1 = opX_b_T_a[0], &op2 = opX_b_T_a[1], &icp = opX_b_T_a[2];
+    const Matrix4d op1_m_op2 = op1.inverse() * op2, op1_m_icp = op1.inverse() * icp, op2_m_icp = op2.inverse() * icp;
+    double y12[3], t12[3], y1i[3], t1i[3], y2i[3], t2i[3];
+    PoseManipUtils::eigenmat_to_rawyprt(op1_m_op2, y12, t12);
+    PoseManipUtils::eigenmat_to_rawyprt(op1_m_icp, y1i, t1i);
+    PoseManipUtils::eigenmat_to_rawyprt(op2_m_icp, y2i, t2i);
+    const bool is_consistent_ypr =
+        PoseManipUtils::linf3(y12) < 5.0 && PoseManipUtils::linf3(y1i) < 5.0 && PoseManipUtils::linf3(y2i) < 5.0;  // :77-81
+    // :83-87 the reference tests op1-icp twice and never the op1-op2 translation; kept as is
+    const bool is_consistent_tr = PoseManipUtils::linf3(t1i) < .2 && PoseManipUtils::linf3(t1i) < .2 && PoseManipUtils::linf3(t2i) < .2;
+    (void)t12;
+    if (pf_matches > 800 && is_consistent_ypr && is_consistent_tr) {  // :110
+      _3d2d__2T1 = opX_b_T_a[0];
+      isSet_3d2d__2T1 = true;
+      _3d2d__2T1__ransac_confidence = std::max(std::max(opX_goodness[0], opX_goodness[1]), opX_goodness[2]);
+      return makeLoopEdgeMsg(msg);
+    }
+    return false;
+  }
+
+  int idx_from_raw_candidates_list;
+  Time t_1, t_2;  // node_1->getT(), node_2->getT()
+  int idx_from_datamanager_1, idx_from_datamanager_2;
+  std::vector<Matrix4d> opX_b_T_a;
+  std::vector<float> opX_goodness;
+  int pf_matches = 0;
+  bool isSet_3d2d__2T1 = false;
+  Matrix4d _3d2d__2T1 = Matrix4d::Identity();
+  float _3d2d__2T1__ransac_confidence = 0.f;
 };
 
 class Cerebro {

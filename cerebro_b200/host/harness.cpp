@@ -2,10 +2,14 @@
 // cerebro_node.cpp:487-509 drives the three threads, on keyframes read from a raw file.
 //
 //   harness <weights.cbw> <images.raw> <n> <rows> <cols> <chnls> [<pnp.raw> <npts>]
+//   harness --consistency <trials.raw> <n>     (no device call: ProcessedLoopCandidate::makeLoopEdgeMsgWithConsistencyCheck on n
+//                                               trials of 54 doubles: t_1, t_2 [s], pf_matches, 3 goodness values, op1, op2, icp
+//                                               row-major 4x4; prints one JSON object per trial)
 //
 // images.raw : n * rows*cols*chnls bytes; keyframes arrive 3 at a time (the search thread acts on >= 3 new
 // descriptors, src/Cerebro.cpp:962).  pnp.raw : npts*3 doubles (w_X) followed by npts*2 doubles (uv).
 // Prints one JSON object: {"descriptor_size":..,"found":[[curr,prev,score],..],"pnp":{"confidence":..,"T":[16]}}
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -94,7 +98,35 @@ bool load_cbw(const char* path, Cbw& w) {
 
 }  // namespace
 
+int run_consistency(const char* path, int n) {
+  using namespace cerebro_b200;
+  std::ifstream f(path, std::ios::binary);
+  if (!f) {
+    std::fprintf(stderr, "cannot read %s\n", path);
+    return 2;
+  }
+  std::vector<double> v(54);
+  for (int i = 0; i < n; ++i) {
+    f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(54 * sizeof(double)));
+    if (!f) return 2;
+    Time t1, t2;
+    t1.nsec = (int64_t)std::llround(v[0] * 1e9);
+    t2.nsec = (int64_t)std::llround(v[1] * 1e9);
+    ProcessedLoopCandidate c(i, t1, t2, 2 * i, 2 * i + 1);
+    c.pf_matches = (int)v[2];
+    c.opX_goodness = {(float)v[3], (float)v[4], (float)v[5]};
+    c.opX_b_T_a = {Matrix4d::from(&v[6]), Matrix4d::from(&v[22]), Matrix4d::from(&v[38])};
+    LoopEdge e;
+    const bool ok = c.makeLoopEdgeMsgWithConsistencyCheck(e);
+    std::printf("{\"ok\":%d,\"weight\":%.9g,\"position\":[%.17g,%.17g,%.17g],\"orientation\":[%.17g,%.17g,%.17g,%.17g],\"description\":\"%s\"}\n",
+                ok ? 1 : 0, ok ? (double)e.weight : 0.0, e.position[0], e.position[1], e.position[2], e.orientation_xyzw[0],
+                e.orientation_xyzw[1], e.orientation_xyzw[2], e.orientation_xyzw[3], ok ? e.description.c_str() : "");
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 4 && std::strcmp(argv[1], "--consistency") == 0) return run_consistency(argv[2], std::atoi(argv[3]));
   if (argc < 7) {
     std::fprintf(stderr, "usage: harness weights.cbw images.raw n rows cols chnls [pnp.raw npts]\n");
     return 2;
