@@ -59,3 +59,12 @@ def test_header_is_plain_c(tmp_path):
     for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror"], ["g++", "-std=c++11", "-Wall", "-Werror", "-x", "c++"]):
         r = subprocess.run(cmd + ["-I" + inc, "-c", str(src), "-o", str(tmp_path / "cabi.o")], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_package_root_exports_the_reference_named_mirrors():
+    import cerebro_b200 as cb
+
+    for name in cb.__all__:
+        assert getattr(cb, name) is not None
+    for name in ("HDF5ModelImageDescriptor", "IndexFlatIP", "StaticTheiaPoseCompute", "Cerebro", "LoopEdge"):
+        assert name in cb.__all__
