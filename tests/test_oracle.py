@@ -318,3 +318,95 @@ def test_ghostvlad_oracle_drops_ghost_clusters():
     # same directions as the un-ghosted layer's first K blocks (the softmax is shared), different global scale
     fb = full.reshape(2, K + G, D)[:, :K]
     assert np.allclose(blocks * np.sqrt(K), fb * np.sqrt(K + G), atol=1e-12)
+
+
+def test_register_resident_elimination_prototype_matches_dense_oracle():
+    """numpy prototype of the control flow of dls_eliminate2_kernel (csrc/pnp.cu): per-row assembly from the template tables,
+    Gauss-Jordan with the (high word, low word) arg-max and lowest-row tie rule, pivot scaling deferred to the read-out,
+    D^T Y = E_J for the degree-7 block and the contraction with its right-hand sides -- against the dense 93 x 93 Schur
+    complement of the oracle.  Guards the tables of csrc/dls_tables.h and the algebra the kernel relies on (CPU only)."""
+    import re
+    import struct
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "cerebro_b200", "csrc", "dls_tables.h")).read()
+
+    def tab(name, shape):
+        m = re.search(name + r"(\[\d+\])+ = \{([^}]*)\}", src)
+        return np.array([float(x) for x in m.group(2).split(",")]).reshape(shape)
+
+    row_poly, row_terms = tab("kRowPoly", (93,)).astype(int), tab("kRowTerms", (93, 20)).astype(int)
+    border7, f0_terms, f0 = tab("kBorder7", (3,)).astype(int), tab("kF0Terms", (27, 4)).astype(int), tab("kF0", (4,))
+    off = [0, 3, 12, 30, 57, 93]
+
+    def key(x):
+        b = struct.unpack("<Q", struct.pack("<d", abs(x)))[0]
+        return b >> 32, b & 0xFFFFFFFF
+
+    def gauss_jordan(A, n):
+        used, myk, mypiv = [False] * n, [-1] * n, [1.0] * n
+        for k in range(n):
+            cands = [(key(A[i, k]), -i) for i in range(n) if not used[i] and A[i, k] == A[i, k]]
+            p = -max(cands)[1]
+            used[p], myk[p], mypiv[p] = True, k, A[p, k]
+            pr, inv = A[p].copy(), 1.0 / A[p, k]
+            for i in range(n):
+                if i != p:
+                    A[i, k + 1:] -= (A[i, k] * inv) * pr[k + 1:]
+        return myk, mypiv
+
+    def action(coef):
+        cf, N = coef.reshape(60), np.zeros((60, 27))
+        for blk in range(4):
+            o0, n = off[blk], off[blk + 1] - off[blk]
+            A = np.zeros((n, n + 27))
+            for r in range(n):
+                for t in range(20):
+                    c, cd = cf[row_poly[o0 + r] * 20 + t], row_terms[o0 + r][t]
+                    if cd < 27:
+                        A[r, n + cd] += -c
+                    elif cd - 27 >= o0:
+                        A[r, cd - 27 - o0] = c
+                    else:
+                        A[r, n:] -= c * N[cd - 27]
+            myk, mypiv = gauss_jordan(A, n)
+            for i in range(n):
+                N[o0 + myk[i]] = A[i, n:] / mypiv[i]
+        o0, n = 57, 36
+        A = np.zeros((36, 39))
+        for r in range(n):
+            for t in range(20):
+                cd = row_terms[o0 + r][t]
+                if cd >= 27 and cd - 27 >= o0:
+                    A[cd - 27 - o0, r] = cf[row_poly[o0 + r] * 20 + t]
+        for t in range(3):
+            A[border7[t], 36 + t] = 1.0
+        myk, mypiv = gauss_jordan(A, n)
+        Y = np.zeros((36, 3))
+        for i in range(n):
+            Y[myk[i]] = A[i, 36:] / mypiv[i]
+        for r in range(n):
+            rr = np.zeros(27)
+            for t in range(20):
+                c, cd = cf[row_poly[o0 + r] * 20 + t], row_terms[o0 + r][t]
+                if cd < 27:
+                    rr[cd] -= c
+                elif cd - 27 < o0:
+                    rr -= c * N[cd - 27]
+            N[57:60] += np.outer(Y[r], rr)
+        S = np.zeros((27, 27))
+        for b in range(27):
+            for k in range(4):
+                cd = f0_terms[b][k]
+                if cd < 27:
+                    S[b, cd] += f0[k]
+                else:
+                    S[b] += f0[k] * N[cd - 27]
+        return S
+
+    rng = np.random.default_rng(7)
+    for _ in range(6):
+        X, uv, _, _ = D.synth_candidate(rng, n=15, noise=1e-3, outlier_frac=0.0)
+        coef = np.asarray(D.dls_setup(X, uv)[1])
+        S, S0 = action(coef), D.action_matrix(coef)
+        assert np.abs(S - S0).max() < 1e-8 * max(1.0, np.abs(S0).max())
